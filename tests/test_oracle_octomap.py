@@ -1,0 +1,181 @@
+"""Known-answer tests of the OctoMap restatement (oracle/octomap_oracle.c).
+
+PARITY UNPINNED: the reference ships no fixtures for the `octomap` boundary and the module is not
+installable here, so these answers are hand-derived from the published constants and the .bt
+format."""
+import struct
+
+import numpy as np
+
+from oracle import octomap_oracle as oo
+
+HDR = (b"# Octomap OcTree binary file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n"
+       b"id OcTree\nsize %d\nres %s\ndata\n")
+
+
+def f32bits(v):
+    return struct.unpack("<I", struct.pack("<f", v))[0]
+
+
+def test_constants_bit_patterns():
+    p = oo.OcTree(0.1).params()
+    assert f32bits(p["hit"]) == 0x3F58E883
+    assert f32bits(p["miss"]) == 0xBECF991F
+    assert f32bits(p["clamp_min"]) == 0xC0000075
+    assert f32bits(p["clamp_max"]) == 0x4060B4BA
+    assert p["occ_thres"] == 0.0
+
+
+def test_coord_to_key_boundaries():
+    t = oo.OcTree(0.1)
+    assert t.coordToKey([0.0, 0.0, 0.0]) == (32768, 32768, 32768)
+    assert t.coordToKey([-1e-9, 0.05, 0.1]) == (32767, 32768, 32769)
+    # float32(0.3) = 0.300000011920929 -> 10*x = 3.0000001 -> 3 ; float32(0.7)=0.699999988 -> 6
+    assert t.coordToKey([0.3, 0.7, -0.3]) == (32771, 32774, 32764)
+    assert t.coordToKey([3276.75, 0, 0]) == (65535, 32768, 32768)
+    assert t.coordToKey([3276.8, 0, 0]) is None           # float32(3276.8) = 3276.80005 -> out of range
+    assert t.coordToKey([-3276.8, 0, 0]) is None          # float32 -> -3276.80005 -> floor = -32769
+    assert t.coordToKey([-3276.75, 0, 0]) == (0, 32768, 32768)
+    t5 = oo.OcTree(0.05)
+    assert t5.coordToKey([1638.39, 0, 0])[0] == 65535
+    assert t5.coordToKey([1638.41, 0, 0]) is None
+
+
+def test_logodds_ladder_and_early_abort():
+    t = oo.OcTree(0.1)
+    k = t.coordToKey([1, 2, 3])
+    seen = []
+    for _ in range(6):
+        t.updateNode(np.array([1.0, 2.0, 3.0]), True)
+        seen.append(np.float32(t.search(k)))
+    hit = np.float32(0.84729785)
+    acc = np.float32(0)
+    want = []
+    for _ in range(6):
+        acc = np.float32(min(np.float32(acc + hit), np.float32(3.5110307)))
+        want.append(acc)
+    assert [f32bits(float(a)) for a in seen] == [f32bits(float(a)) for a in want]
+    for _ in range(20):
+        t.updateNode(np.array([1.0, 2.0, 3.0]), False)
+    assert f32bits(t.search(k)) == 0xC0000075
+    # raw float update path of the binding
+    t.updateNode(np.array([1.0, 2.0, 3.0]), 1.0)
+    assert np.float32(t.search(k)) == np.float32(np.float32(-2.0000279) + np.float32(1.0))
+
+
+def test_bt_single_voxel_bytes():
+    t = oo.OcTree(0.1)
+    t.updateNode(np.array([0.05, 0.05, 0.05]), True)
+    assert t.size() == 17
+    t.updateInnerOccupancy()
+    want = HDR % (17, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 14 + b"\x02\x00"
+    assert t.write_binary_bytes() == want
+
+
+def test_bt_free_voxel_and_res_text():
+    t = oo.OcTree(0.05)
+    t.updateNode(np.array([-0.01, -0.01, -0.01]), False)   # key 32767 each: child 0 at root, child 7 below
+    want = HDR % (17, b"0.05") + b"\x03\x00" + b"\x00\xc0" * 14 + b"\x00\x40"
+    assert t.write_binary_bytes() == want
+
+
+def test_bt_eight_siblings_prune_to_parent():
+    t = oo.OcTree(0.1)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                t.updateNode(np.array([0.05 + 0.1 * dx, 0.05 + 0.1 * dy, 0.05 + 0.1 * dz]), True)
+    assert t.size() == 16          # pruned at update time: 8 equal-valued leaves collapse
+    want = HDR % (16, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 13 + b"\x02\x00"
+    assert t.write_binary_bytes() == want
+
+
+def test_bt_mixed_children():
+    t = oo.OcTree(0.1)
+    t.updateNode(np.array([0.05, 0.05, 0.05]), True)     # child 0 of the depth-15 node: occupied
+    t.updateNode(np.array([0.15, 0.05, 0.05]), False)    # child 1: free
+    t.updateNode(np.array([0.05, 0.15, 0.15]), True)     # child 6: occupied
+    want = HDR % (19, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 14 + bytes([0x02 | 0x04, 0x20])
+    assert t.write_binary_bytes() == want
+
+
+def test_prune_early_break_quirk():
+    """64 voxels filling one depth-14 node, node A hit once, the 7 others hit twice: every depth-15 node
+    is pruned at update time (equal values inside), the depth-14 node is not (values differ). writeBinary's
+    prune() starts at depth 15, prunes nothing there and stops, so the depth-14 node keeps 8 leaf children."""
+    t = oo.OcTree(0.1)
+    for ix in range(4):
+        for iy in range(4):
+            for iz in range(4):
+                p = np.array([0.05 + 0.1 * ix, 0.05 + 0.1 * iy, 0.05 + 0.1 * iz])
+                t.updateNode(p, True)
+                if not (ix < 2 and iy < 2 and iz < 2):
+                    t.updateNode(p, True)
+    assert t.size() == 1 + 14 + 8
+    data = t.write_binary_bytes()
+    assert data == HDR % (23, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 13 + b"\xaa\xaa"
+    # whereas mixed values INSIDE the depth-15 nodes let the passes run and the whole cube collapses
+    t2 = oo.OcTree(0.1)
+    for ix in range(4):
+        for iy in range(4):
+            for iz in range(4):
+                p = np.array([0.05 + 0.1 * ix, 0.05 + 0.1 * iy, 0.05 + 0.1 * iz])
+                t2.updateNode(p, True)
+                if ix % 2 == 0:
+                    t2.updateNode(p, True)
+    assert t2.write_binary_bytes() == HDR % (15, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 12 + b"\x02\x00"
+
+
+def test_ray_keys_axis_aligned_and_zero_length():
+    t = oo.OcTree(0.1)
+    assert len(t.computeRayKeys([0.05, 0.05, 0.05], [0.06, 0.06, 0.06])) == 0      # same voxel
+    r = t.computeRayKeys([0.05, 0.05, 0.05], [1.05, 0.05, 0.05])
+    assert np.array_equal(r[:, 0], np.arange(32768, 32778)) and np.all(r[:, 1:] == 32768)   # end voxel not included
+    r = t.computeRayKeys([0.05, 0.05, 0.05], [0.05, -0.95, 0.05])
+    assert np.array_equal(r[:, 1], np.arange(32768, 32758, -1))
+    assert t.computeRayKeys([0.05, 0.05, 0.05], [4000.0, 0, 0]) is None             # out of bounds
+
+
+def test_ray_keys_are_connected_and_bounded():
+    rng = np.random.default_rng(1)
+    t = oo.OcTree(0.1)
+    for _ in range(200):
+        o = rng.uniform(-5, 5, 3)
+        e = o + rng.uniform(-30, 30, 3)
+        r = t.computeRayKeys(o, e).astype(np.int64)
+        ko, ke = np.array(t.coordToKey(o)), np.array(t.coordToKey(e))
+        if len(r) == 0:
+            assert np.array_equal(ko, ke)
+            continue
+        assert np.array_equal(r[0], ko)
+        steps = np.abs(np.diff(r, axis=0)).sum(axis=1)
+        assert np.all(steps == 1)
+        assert not np.any(np.all(r == ke, axis=1))
+        assert np.abs(r[-1] - ke).sum() <= 3
+
+
+def test_compute_update_occupied_wins_and_maxrange():
+    t = oo.OcTree(0.1)
+    pts = np.array([[1.05, 0.05, 0.05], [2.05, 0.05, 0.05], [100.0, 0.05, 0.05]], dtype=np.float32)
+    fr, oc = t.computeUpdate(pts, [0.05, 0.05, 0.05], maxrange=10.0)
+    frk, ock = oo.unpack_keys(fr), oo.unpack_keys(oc)
+    assert sorted(ock[:, 0].tolist()) == [32778, 32788]       # third point beyond maxrange: no endpoint
+    # voxel 32778 is on the way to the second point but stays occupied-only
+    assert 32778 not in frk[:, 0].tolist()
+    # truncated ray: end = origin + dir*10 -> x = 10.05 -> key 32868, not included as free
+    assert frk[:, 0].max() == 32867
+    t.insertPointCloud(pts.astype(np.float64), np.array([0.05, 0.05, 0.05]), maxrange=10.0)
+    assert f32bits(t.search((32778, 32768, 32768))) == 0x3F58E883
+    assert f32bits(t.search((32770, 32768, 32768))) == 0xBECF991F
+    assert t.search((32868, 32768, 32768)) is None
+
+
+def test_leaves_roundtrip_matches_search():
+    rng = np.random.default_rng(5)
+    t = oo.OcTree(0.1)
+    pts = rng.uniform(-3, 3, size=(500, 3))
+    t.updateNodes(pts, True)
+    keys, vals, depths = t.leaves()
+    assert np.all(depths <= 16)
+    for k, v in list(zip(keys, vals))[:50]:
+        assert np.float32(t.search(k)) == v
