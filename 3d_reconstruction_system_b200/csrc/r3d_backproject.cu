@@ -1,0 +1,660 @@
+// r3d_backproject.cu -- K1: fused depth decode -> pinhole back-projection -> pose transform -> xyz records.
+//
+// Replaces gentxtcord + get_pointdata/point_camera of the reference (transfer/camera_to_world.py:57-59,
+// 67-105; transfer/pixel_to_camera.py:24-44).  HBM-bound: sizeof(depth sample) + 12 B per pixel.
+//
+// Main kernel (k1_bulk): persistent CTAs, each owning a contiguous run of 1024-pixel tiles of the
+// flattened frame batch.  Depth tiles arrive in shared memory through a 4-stage cp.async.bulk (UBLKCP)
+// ring signalled by mbarriers; xyz records are assembled in shared memory and leave through
+// cp.async.bulk shared->global stores (bulk groups), so the SM's LSU only sees conflict-free LDS/STS.
+// All arithmetic is fp64 with separately rounded products/sums (r3d_math.cuh) and is cast once.
+#include <cub/device/device_scan.cuh>
+
+#include "r3d_common.cuh"
+
+namespace r3d {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_PPT = 4;                       // pixels per thread per tile
+constexpr int K1_TILE = K1_THREADS * K1_PPT;    // 1024 pixels
+constexpr int K1_STAGES = 4;
+
+struct K1Args {
+    const void* depth;
+    void* out;
+    const double* rt;              // n_frames x 12 or nullptr (camera frame)
+    unsigned long long px_begin;   // first flat pixel handled by this launch (generic kernels)
+    unsigned long long px_count;   // pixels handled by this launch
+    unsigned long long n_tiles;    // bulk: full tiles
+    unsigned W, H, WH;
+    unsigned long long pitch;      // bytes per row
+    double fx, fy, cx, cy, depth_scale, fB;
+    int mode;
+    // compaction
+    const unsigned long long* tile_offsets;  // exclusive scan of valid counts per tile
+    unsigned long long* tile_counts;
+    unsigned long long* frame_counts;
+};
+
+// ------------------------------------------------------------------ PTX helpers (mbarrier + bulk async copy)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by bulk async-groups
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------ per-pixel arithmetic
+template <typename DepthT>
+__device__ __forceinline__ double raw_to_double(DepthT v) { return (double)v; }
+
+template <typename OutT>
+__device__ __forceinline__ OutT out_cast(double v);
+template <>
+__device__ __forceinline__ float out_cast<float>(double v) { return __double2float_rn(v); }
+template <>
+__device__ __forceinline__ double out_cast<double>(double v) { return v; }
+
+// One pixel: raw sample + table entries -> record.  `pose_frame` caches which frame `pose` holds.
+template <typename OutT, bool kWorld>
+__device__ __forceinline__ bool k1_pixel(const K1Args& a, double raw, double au, double bv, unsigned frame,
+                                         unsigned& pose_frame, Pose& pose, OutT& ox, OutT& oy, OutT& oz) {
+    bool valid;
+    const double Z = decode_z(raw, a.mode, a.depth_scale, a.fB, valid);
+    const double X = dmul(au, Z);
+    const double Y = dmul(bv, Z);
+    if (kWorld) {
+        if (frame != pose_frame) {
+            pose_load(a.rt + (size_t)frame * 12, pose);
+            pose_frame = frame;
+        }
+        double wx, wy, wz;
+        pose_apply(pose, X, Y, Z, wx, wy, wz);
+        ox = out_cast<OutT>(wx); oy = out_cast<OutT>(wy); oz = out_cast<OutT>(wz);
+    } else {
+        ox = out_cast<OutT>(X); oy = out_cast<OutT>(Y); oz = out_cast<OutT>(Z);
+    }
+    return valid;
+}
+
+__device__ __forceinline__ void k1_tables(const K1Args& a, double* col, double* row) {
+    for (unsigned i = threadIdx.x; i < a.W; i += blockDim.x) col[i] = pixel_coeff((int)i, a.cx, a.fx);
+    for (unsigned j = threadIdx.x; j < a.H; j += blockDim.x) row[j] = pixel_coeff((int)j, a.cy, a.fy);
+}
+
+// ------------------------------------------------------------------ k1_bulk: the hot kernel
+template <typename DepthT, typename OutT, bool kWorld, int kOutBufs>
+__global__ void __launch_bounds__(K1_THREADS) k1_bulk(const K1Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // K1_STAGES mbarriers
+    double* col = reinterpret_cast<double*>(smem + 128);
+    double* row = col + a.W;
+    size_t off = 128 + ((size_t)(a.W + a.H) * 8 + 127) / 128 * 128;
+    DepthT* in_s = reinterpret_cast<DepthT*>(smem + off);               // K1_STAGES x K1_TILE
+    off += (size_t)K1_STAGES * K1_TILE * sizeof(DepthT);
+    OutT* out_s = reinterpret_cast<OutT*>(smem + off);                  // kOutBufs x K1_TILE x 3
+
+    const unsigned tid = threadIdx.x;
+    constexpr uint32_t kInBytes = K1_TILE * sizeof(DepthT);
+    constexpr uint32_t kOutBytes = K1_TILE * 3 * sizeof(OutT);
+
+    // contiguous run of tiles for this CTA
+    const unsigned long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
+    unsigned long long t1 = t0 + per;
+    if (t1 > a.n_tiles) t1 = a.n_tiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    k1_tables(a, col, row);
+    __syncthreads();
+    if (t0 >= t1) return;
+
+    const DepthT* gin = reinterpret_cast<const DepthT*>(a.depth);
+    OutT* gout = reinterpret_cast<OutT*>(a.out);
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) {
+            if (t0 + s < t1) {
+                mbar_arrive_expect_tx(&full[s], kInBytes);
+                bulk_load(in_s + (size_t)s * K1_TILE, gin + (t0 + s) * K1_TILE, kInBytes, &full[s]);
+            }
+        }
+    }
+
+    // (frame, row, column) of this thread's first pixel, advanced incrementally: no division in the tile loop
+    const unsigned long long px0 = t0 * K1_TILE + tid;
+    unsigned f0 = (unsigned)(px0 / a.WH);
+    const unsigned r0 = (unsigned)(px0 - (unsigned long long)f0 * a.WH);
+    unsigned v0 = r0 / a.W, u0 = r0 - v0 * a.W;
+    const unsigned q_thr = K1_THREADS / a.W, r_thr = K1_THREADS - q_thr * a.W;   // +256 pixels
+    const unsigned q_tile = K1_TILE / a.W, r_tile = K1_TILE - q_tile * a.W;      // +1024 pixels
+    unsigned pose_frame = 0xffffffffu;
+    Pose pose;
+
+    unsigned it = 0;
+    for (unsigned long long t = t0; t < t1; ++t, ++it) {
+        const unsigned stage = it % K1_STAGES;
+        const unsigned parity = (it / K1_STAGES) & 1u;
+        const unsigned ob = it % kOutBufs;
+        mbar_wait(&full[stage], parity);
+        const DepthT* tin = in_s + (size_t)stage * K1_TILE;
+        OutT* tout = out_s + (size_t)ob * K1_TILE * 3;
+        unsigned u = u0, v = v0, f = f0;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            const unsigned idx = tid + j * K1_THREADS;
+            OutT x, y, z;
+            k1_pixel<OutT, kWorld>(a, raw_to_double(tin[idx]), col[u], row[v], f, pose_frame, pose, x, y, z);
+            tout[idx * 3 + 0] = x; tout[idx * 3 + 1] = y; tout[idx * 3 + 2] = z;
+            u += r_thr; v += q_thr;
+            if (u >= a.W) { u -= a.W; ++v; }
+            while (v >= a.H) { v -= a.H; ++f; }
+        }
+        // the bulk store issued kOutBufs-1 tiles ago must have finished reading the buffer the NEXT tile writes
+        if (tid == 0) bulk_wait_read<kOutBufs - 2>();
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_store(gout + t * (unsigned long long)K1_TILE * 3, tout, kOutBytes);
+            bulk_commit();
+            const unsigned long long tn = t + K1_STAGES;
+            if (tn < t1) {   // every thread is past its reads of this stage (barrier above): refill it
+                mbar_arrive_expect_tx(&full[stage], kInBytes);
+                bulk_load(in_s + (size_t)stage * K1_TILE, gin + tn * K1_TILE, kInBytes, &full[stage]);
+            }
+        }
+        u0 += r_tile; v0 += q_tile;
+        if (u0 >= a.W) { u0 -= a.W; ++v0; }
+        while (v0 >= a.H) { v0 -= a.H; ++f0; }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+// ------------------------------------------------------------------ generic kernels (tails, pitched / unaligned input)
+template <typename DepthT>
+__device__ __forceinline__ double load_raw(const K1Args& a, unsigned f, unsigned v, unsigned u) {
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(a.depth) +
+                             ((size_t)f * a.H + v) * a.pitch + (size_t)u * sizeof(DepthT);
+    return raw_to_double(*reinterpret_cast<const DepthT*>(p));
+}
+
+template <typename DepthT, typename OutT, bool kWorld>
+__global__ void __launch_bounds__(K1_THREADS) k1_generic(const K1Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* col = reinterpret_cast<double*>(smem);
+    double* row = col + a.W;
+    k1_tables(a, col, row);
+    __syncthreads();
+    OutT* gout = reinterpret_cast<OutT*>(a.out);
+    unsigned pose_frame = 0xffffffffu;
+    Pose pose;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.px_count; i += stride) {
+        const unsigned long long p = a.px_begin + i;
+        const unsigned f = (unsigned)(p / a.WH);
+        const unsigned r = (unsigned)(p - (unsigned long long)f * a.WH);
+        const unsigned v = r / a.W, u = r - v * a.W;
+        OutT x, y, z;
+        k1_pixel<OutT, kWorld>(a, load_raw<DepthT>(a, f, v, u), col[u], row[v], f, pose_frame, pose, x, y, z);
+        gout[p * 3 + 0] = x; gout[p * 3 + 1] = y; gout[p * 3 + 2] = z;
+    }
+}
+
+// compaction pass 1: valid pixels per 1024-pixel tile and per frame
+template <typename DepthT>
+__global__ void __launch_bounds__(K1_THREADS) k1_count(const K1Args a) {
+    __shared__ unsigned warp_cnt[K1_THREADS / 32];
+    const unsigned long long n_tiles = (a.px_count + K1_TILE - 1) / K1_TILE;
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        unsigned mine = 0;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            const unsigned long long p = t * K1_TILE + threadIdx.x + j * K1_THREADS;
+            bool valid = false;
+            unsigned f = 0;
+            if (p < a.px_count) {
+                f = (unsigned)(p / a.WH);
+                const unsigned r = (unsigned)(p - (unsigned long long)f * a.WH);
+                const unsigned v = r / a.W, u = r - v * a.W;
+                decode_z(load_raw<DepthT>(a, f, v, u), a.mode, a.depth_scale, a.fB, valid);
+            }
+            mine += valid ? 1u : 0u;
+            // per-frame counts, one atomic per (warp, frame)
+            const unsigned key = valid ? f : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (valid && (threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1))
+                atomicAdd(&a.frame_counts[f], (unsigned long long)__popc(peers));
+        }
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31u) == 0) warp_cnt[threadIdx.x >> 5] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned s = 0;
+            for (int w = 0; w < K1_THREADS / 32; ++w) s += warp_cnt[w];
+            a.tile_counts[t] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// compaction pass 2: ordered write of the valid records
+template <typename DepthT, typename OutT, bool kWorld>
+__global__ void __launch_bounds__(K1_THREADS) k1_compact(const K1Args a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* col = reinterpret_cast<double*>(smem);
+    double* row = col + a.W;
+    __shared__ unsigned warp_cnt[K1_PPT][K1_THREADS / 32];
+    k1_tables(a, col, row);
+    __syncthreads();
+    OutT* gout = reinterpret_cast<OutT*>(a.out);
+    unsigned pose_frame = 0xffffffffu;
+    Pose pose;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned long long n_tiles = (a.px_count + K1_TILE - 1) / K1_TILE;
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        OutT x[K1_PPT], y[K1_PPT], z[K1_PPT];
+        unsigned rank[K1_PPT];
+        bool ok[K1_PPT];
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            const unsigned long long p = t * K1_TILE + threadIdx.x + j * K1_THREADS;
+            ok[j] = false;
+            if (p < a.px_count) {
+                const unsigned f = (unsigned)(p / a.WH);
+                const unsigned r = (unsigned)(p - (unsigned long long)f * a.WH);
+                const unsigned v = r / a.W, u = r - v * a.W;
+                ok[j] = k1_pixel<OutT, kWorld>(a, load_raw<DepthT>(a, f, v, u), col[u], row[v], f, pose_frame, pose,
+                                               x[j], y[j], z[j]);
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, ok[j]);
+            rank[j] = __popc(b & ((1u << lane) - 1u));
+            if (lane == 0) warp_cnt[j][warp] = __popc(b);
+        }
+        __syncthreads();
+        const unsigned long long base = a.tile_offsets[t];
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            unsigned before = 0;
+            for (int jj = 0; jj < K1_PPT; ++jj)
+                for (int w = 0; w < K1_THREADS / 32; ++w)
+                    if (jj < j || (jj == j && w < (int)warp)) before += warp_cnt[jj][w];
+            if (ok[j]) {
+                const unsigned long long q = base + before + rank[j];
+                gout[q * 3 + 0] = x[j]; gout[q * 3 + 1] = y[j]; gout[q * 3 + 2] = z[j];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// T . [x y z 1]^T (other_tools/transfer_T_icp.py:10-12), rows left to right
+__global__ void k_transform_points(const double* __restrict__ in, double* __restrict__ out, unsigned long long n,
+                                   const double* __restrict__ T) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            out[3 * i + k] = dadd(dadd(dadd(dmul(T[4 * k], x), dmul(T[4 * k + 1], y)), dmul(T[4 * k + 2], z)), T[4 * k + 3]);
+    }
+}
+
+// point_camera on explicit points: Rinv . (p - t)
+__global__ void k_pose_apply_points(const double* __restrict__ in, double* __restrict__ out, unsigned long long n,
+                                    const double* __restrict__ rt) {
+    Pose pose;
+    pose_load(rt, pose);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double wx, wy, wz;
+        pose_apply(pose, in[3 * i], in[3 * i + 1], in[3 * i + 2], wx, wy, wz);
+        out[3 * i] = wx; out[3 * i + 1] = wy; out[3 * i + 2] = wz;
+    }
+}
+
+// ------------------------------------------------------------------ launch plumbing
+static size_t elem_size(int dtype) { return dtype == R3D_U8 ? 1 : (dtype == R3D_U16 ? 2 : 4); }
+
+template <typename DepthT, typename OutT, bool kWorld>
+static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok, int compact, unsigned long long total) {
+    const size_t table_bytes = ((size_t)(a.W + a.H) * 8 + 127) / 128 * 128;
+    if (compact) {
+        const unsigned long long n_tiles = (total + K1_TILE - 1) / K1_TILE;
+        R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)n_tiles * 16 + 256));
+        unsigned long long* counts = (unsigned long long*)ctx->scratch[SCR_TILE];
+        unsigned long long* offsets = counts + n_tiles;
+        a.tile_counts = counts;
+        a.tile_offsets = offsets;
+        a.px_begin = 0;
+        a.px_count = total;
+        const int grid = (int)((n_tiles < (unsigned long long)ctx->sm_count * 8) ? n_tiles : (unsigned long long)ctx->sm_count * 8);
+        k1_count<DepthT><<<grid, K1_THREADS, 0, st>>>(a);
+        ctx->launches++;
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offsets, (int)n_tiles, st);
+        R3D_TRY(scratch_reserve(ctx, SCR_CUBTMP, tmp_bytes + 256));
+        R3D_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->scratch[SCR_CUBTMP], tmp_bytes, counts, offsets, (int)n_tiles, st));
+        ctx->launches++;
+        R3D_CUDA_OK(ctx, cudaFuncSetAttribute(k1_compact<DepthT, OutT, kWorld>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+        k1_compact<DepthT, OutT, kWorld><<<grid, K1_THREADS, table_bytes, st>>>(a);
+        ctx->launches++;
+        R3D_CUDA_OK(ctx, cudaGetLastError());
+        return R3D_OK;
+    }
+    unsigned long long done = 0;
+    if (bulk_ok && total >= K1_TILE) {
+        constexpr int kOutBufs = sizeof(OutT) == 4 ? 3 : 2;
+        a.n_tiles = total / K1_TILE;
+        const size_t smem = 128 + table_bytes + (size_t)K1_STAGES * K1_TILE * sizeof(DepthT) +
+                            (size_t)kOutBufs * K1_TILE * 3 * sizeof(OutT);
+        auto kern = k1_bulk<DepthT, OutT, kWorld, kOutBufs>;
+        R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem));
+        if (per_sm < 1) return set_error(ctx, R3D_ERR_UNSUPPORTED, "image %ux%u needs %zu B of shared memory per CTA", a.W, a.H, smem);
+        unsigned long long grid = (unsigned long long)ctx->sm_count * per_sm;
+        if (grid > a.n_tiles) grid = a.n_tiles;
+        kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(a);
+        ctx->launches++;
+        done = a.n_tiles * K1_TILE;
+    }
+    if (done < total) {
+        a.px_begin = done;
+        a.px_count = total - done;
+        unsigned long long blocks = (a.px_count + K1_THREADS - 1) / K1_THREADS;
+        const unsigned long long cap = (unsigned long long)ctx->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        R3D_CUDA_OK(ctx, cudaFuncSetAttribute(k1_generic<DepthT, OutT, kWorld>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+        k1_generic<DepthT, OutT, kWorld><<<(unsigned)blocks, K1_THREADS, table_bytes, st>>>(a);
+        ctx->launches++;
+    }
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    return R3D_OK;
+}
+
+template <typename DepthT>
+static int launch_k1_depth(r3d_ctx* ctx, cudaStream_t st, const K1Args& a, bool bulk_ok, int compact, int out_dtype,
+                           unsigned long long total) {
+    const bool world = a.rt != nullptr;
+    if (out_dtype == R3D_OUT_F32)
+        return world ? launch_k1_typed<DepthT, float, true>(ctx, st, a, bulk_ok, compact, total)
+                     : launch_k1_typed<DepthT, float, false>(ctx, st, a, bulk_ok, compact, total);
+    return world ? launch_k1_typed<DepthT, double, true>(ctx, st, a, bulk_ok, compact, total)
+                 : launch_k1_typed<DepthT, double, false>(ctx, st, a, bulk_ok, compact, total);
+}
+
+// Everything on the device already: depth/out/rt are device pointers.
+static int launch_k1(r3d_ctx* ctx, cudaStream_t st, const void* d_depth, int dtype, int W, int H, size_t pitch, int n_frames,
+                     const double intr[4], const double* d_rt, int mode, double depth_scale, double fB, int compact,
+                     int out_dtype, void* d_out, unsigned long long* d_frame_counts) {
+    K1Args a;
+    memset(&a, 0, sizeof a);
+    a.depth = d_depth; a.out = d_out; a.rt = d_rt;
+    a.W = (unsigned)W; a.H = (unsigned)H; a.WH = (unsigned)W * (unsigned)H;
+    a.pitch = pitch;
+    a.fx = intr[0]; a.fy = intr[1]; a.cx = intr[2]; a.cy = intr[3];
+    a.depth_scale = depth_scale; a.fB = fB; a.mode = mode;
+    a.frame_counts = d_frame_counts;
+    const unsigned long long total = (unsigned long long)n_frames * a.WH;
+    const size_t es = elem_size(dtype);
+    const size_t osz = out_dtype == R3D_OUT_F32 ? 4 : 8;
+    const bool bulk_ok = pitch == (size_t)W * es && ((uintptr_t)d_depth % 16 == 0) && ((uintptr_t)d_out % 16 == 0) &&
+                         ((size_t)(W + H) * 8 + (size_t)K1_STAGES * K1_TILE * es + 3 * (size_t)K1_TILE * 3 * osz < 200 * 1024);
+    switch (dtype) {
+        case R3D_U8: return launch_k1_depth<unsigned char>(ctx, st, a, bulk_ok, compact, out_dtype, total);
+        case R3D_U16: return launch_k1_depth<unsigned short>(ctx, st, a, bulk_ok, compact, out_dtype, total);
+        case R3D_F32: return launch_k1_depth<float>(ctx, st, a, bulk_ok, compact, out_dtype, total);
+    }
+    return set_error(ctx, R3D_ERR_ARG, "unknown depth dtype %d", dtype);
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+// ------------------------------------------------------------------ C ABI
+extern "C" int r3d_pose_to_rt(const double* poses, int n, double t_scale, double* rt) {
+    if (!poses || !rt || n < 0) return set_error(nullptr, R3D_ERR_ARG, "r3d_pose_to_rt: null argument");
+    for (int i = 0; i < n; ++i) {
+        const double* q = poses + (size_t)i * 7;
+        double* o = rt + (size_t)i * 12;
+        // scipy Rotation.from_quat: normalise; as_matrix: the formula below (scalar-last)
+        const double nrm = sqrt(((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]);
+        if (!(nrm > 0.0)) return set_error(nullptr, R3D_ERR_ARG, "Found zero norm quaternions in `quat` (frame %d)", i);
+        const double x = q[0] / nrm, y = q[1] / nrm, z = q[2] / nrm, w = q[3] / nrm;
+        const double x2 = x * x, y2 = y * y, z2 = z * z, w2 = w * w;
+        const double xy = x * y, zw = z * w, xz = x * z, yw = y * w, yz = y * z, xw = x * w;
+        const double m00 = ((x2 - y2) - z2) + w2, m01 = 2.0 * (xy - zw), m02 = 2.0 * (xz + yw);
+        const double m10 = 2.0 * (xy + zw), m11 = ((-x2 + y2) - z2) + w2, m12 = 2.0 * (yz - xw);
+        const double m20 = 2.0 * (xz - yw), m21 = 2.0 * (yz + xw), m22 = ((-x2 - y2) + z2) + w2;
+        // np.matrix(...).I: general inverse (cofactor form, fixed order)
+        const double c00 = m11 * m22 - m12 * m21, c01 = m12 * m20 - m10 * m22, c02 = m10 * m21 - m11 * m20;
+        const double det = (m00 * c00 + m01 * c01) + m02 * c02;
+        o[0] = c00 / det; o[1] = (m02 * m21 - m01 * m22) / det; o[2] = (m01 * m12 - m02 * m11) / det;
+        o[3] = c01 / det; o[4] = (m00 * m22 - m02 * m20) / det; o[5] = (m02 * m10 - m00 * m12) / det;
+        o[6] = c02 / det; o[7] = (m01 * m20 - m00 * m21) / det; o[8] = (m00 * m11 - m01 * m10) / det;
+        o[9] = t_scale * q[4]; o[10] = t_scale * q[5]; o[11] = t_scale * q[6];
+    }
+    return R3D_OK;
+}
+
+extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, int W, int H, size_t pitch, int n_frames,
+                                  const double intr[4], const double* rt, int mode, double depth_scale, double fB,
+                                  int compact, int out_dtype, void* out_xyz, uint64_t* out_counts) {
+    if (!ctx) return set_error(nullptr, R3D_ERR_ARG, "null context");
+    if (!depth || !out_xyz || !intr) return set_error(ctx, R3D_ERR_ARG, "r3d_backproject: null buffer");
+    if (W <= 0 || H <= 0 || n_frames < 0 || W > 65535 || H > 65535) return set_error(ctx, R3D_ERR_ARG, "bad image shape %dx%dx%d", n_frames, H, W);
+    if (dtype < R3D_U8 || dtype > R3D_F32) return set_error(ctx, R3D_ERR_ARG, "bad depth dtype %d", dtype);
+    if (mode != R3D_MODE_DEPTH && mode != R3D_MODE_DISPARITY) return set_error(ctx, R3D_ERR_ARG, "bad mode %d", mode);
+    if (out_dtype != R3D_OUT_F32 && out_dtype != R3D_OUT_F64) return set_error(ctx, R3D_ERR_ARG, "bad out dtype %d", out_dtype);
+    const size_t es = elem_size(dtype);
+    if (pitch == 0) pitch = (size_t)W * es;
+    if (pitch < (size_t)W * es) return set_error(ctx, R3D_ERR_ARG, "pitch %zu smaller than a row", pitch);
+    if (dtype != R3D_U8 && pitch % es) return set_error(ctx, R3D_ERR_ARG, "pitch %zu not a multiple of the sample size", pitch);
+    DeviceSetter ds(ctx->device);
+    if (n_frames == 0) return R3D_OK;
+    const size_t osz = out_dtype == R3D_OUT_F32 ? 4 : 8;
+    const size_t frame_in = (size_t)H * pitch, frame_out = (size_t)W * H * 3 * osz;
+    const bool depth_dev = is_device_ptr(depth), out_dev = is_device_ptr(out_xyz);
+    const bool counts_dev = out_counts && is_device_ptr(out_counts);
+
+    // pose table on the device
+    const double* d_rt = nullptr;
+    if (rt) {
+        if (is_device_ptr(rt)) d_rt = rt;
+        else {
+            R3D_TRY(scratch_reserve(ctx, SCR_POSE, (size_t)n_frames * 96));
+            R3D_CUDA_OK(ctx, cudaMemcpyAsync(ctx->scratch[SCR_POSE], rt, (size_t)n_frames * 96, cudaMemcpyHostToDevice, ctx->stream));
+            // the staging streams below must see the table
+            R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            d_rt = (const double*)ctx->scratch[SCR_POSE];
+        }
+    }
+    // per-frame counters (compaction) live in device scratch slot 1 after the pose table
+    unsigned long long* d_counts = nullptr;
+    cudaError_t ce;
+    if (compact) {
+        ce = cudaMalloc((void**)&d_counts, (size_t)n_frames * 8);
+        if (ce != cudaSuccess) return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(frame counts) failed: %s", cudaGetErrorString(ce));
+        cudaMemsetAsync(d_counts, 0, (size_t)n_frames * 8, ctx->stream);
+    }
+    int rc = R3D_OK;
+    if (depth_dev && out_dev) {
+        cudaEventRecord(ctx->ev_a, ctx->stream);
+        rc = launch_k1(ctx, ctx->stream, depth, dtype, W, H, pitch, n_frames, intr, d_rt, mode, depth_scale, fB, compact,
+                       out_dtype, out_xyz, d_counts);
+        cudaEventRecord(ctx->ev_b, ctx->stream);
+    } else if (compact) {
+        // compaction needs the whole batch resident (output offsets depend on every earlier tile)
+        void *d_in = nullptr, *d_out = nullptr;
+        if (!depth_dev) {
+            ce = cudaMalloc(&d_in, frame_in * n_frames);
+            if (ce != cudaSuccess) { cudaFree(d_counts); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(depth staging) failed: %s", cudaGetErrorString(ce)); }
+            cudaMemcpyAsync(d_in, depth, frame_in * n_frames, cudaMemcpyHostToDevice, ctx->stream);
+        }
+        if (!out_dev) {
+            ce = cudaMalloc(&d_out, frame_out * n_frames);
+            if (ce != cudaSuccess) { cudaFree(d_in); cudaFree(d_counts); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(xyz staging) failed: %s", cudaGetErrorString(ce)); }
+        }
+        rc = launch_k1(ctx, ctx->stream, depth_dev ? depth : d_in, dtype, W, H, pitch, n_frames, intr, d_rt, mode, depth_scale,
+                       fB, compact, out_dtype, out_dev ? out_xyz : d_out, d_counts);
+        if (rc == R3D_OK && !out_dev) {
+            // copy back only what was written
+            unsigned long long* h = (unsigned long long*)malloc((size_t)n_frames * 8);
+            cudaMemcpyAsync(h, d_counts, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            unsigned long long tot = 0;
+            for (int i = 0; i < n_frames; ++i) tot += h[i];
+            free(h);
+            cudaMemcpyAsync(out_xyz, d_out, (size_t)tot * 3 * osz, cudaMemcpyDeviceToHost, ctx->stream);
+        }
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_in); cudaFree(d_out);
+    } else {
+        // host-side buffers: chunked H2D -> kernel -> D2H pipeline on two streams with two device slots
+        size_t per_frame = (depth_dev ? 0 : frame_in) + (out_dev ? 0 : frame_out);
+        int chunk = (int)((size_t)(192u << 20) / (per_frame ? per_frame : 1));
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_frames) chunk = n_frames;
+        for (int s = 0; s < 2 && rc == R3D_OK; ++s) {
+            if (!depth_dev) rc = scratch_reserve(ctx, SCR_IN0 + s, frame_in * chunk);
+            if (rc == R3D_OK && !out_dev) rc = scratch_reserve(ctx, SCR_OUT0 + s, frame_out * chunk);
+        }
+        for (int f0 = 0, c = 0; f0 < n_frames && rc == R3D_OK; f0 += chunk, ++c) {
+            const int s = c & 1;
+            const int nf = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+            cudaStream_t st = ctx->copy_stream[s];
+            const void* din = depth_dev ? (const void*)((const char*)depth + (size_t)f0 * frame_in) : ctx->scratch[SCR_IN0 + s];
+            void* dout = out_dev ? (void*)((char*)out_xyz + (size_t)f0 * frame_out) : ctx->scratch[SCR_OUT0 + s];
+            if (!depth_dev)
+                cudaMemcpyAsync(ctx->scratch[SCR_IN0 + s], (const char*)depth + (size_t)f0 * frame_in, frame_in * nf, cudaMemcpyHostToDevice, st);
+            rc = launch_k1(ctx, st, din, dtype, W, H, pitch, nf, intr, d_rt ? d_rt + (size_t)f0 * 12 : nullptr, mode, depth_scale,
+                           fB, 0, out_dtype, dout, nullptr);
+            if (rc == R3D_OK && !out_dev)
+                cudaMemcpyAsync((char*)out_xyz + (size_t)f0 * frame_out, dout, frame_out * nf, cudaMemcpyDeviceToHost, st);
+        }
+        cudaStreamSynchronize(ctx->copy_stream[0]);
+        cudaStreamSynchronize(ctx->copy_stream[1]);
+    }
+    if (rc != R3D_OK) { cudaFree(d_counts); return rc; }
+    if (out_counts) {
+        if (compact) {
+            cudaMemcpyAsync(out_counts, d_counts, (size_t)n_frames * 8, counts_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        } else if (!counts_dev) {
+            for (int i = 0; i < n_frames; ++i) out_counts[i] = (uint64_t)W * H;
+        } else {
+            uint64_t* h = (uint64_t*)malloc((size_t)n_frames * 8);
+            for (int i = 0; i < n_frames; ++i) h[i] = (uint64_t)W * H;
+            cudaMemcpy(out_counts, h, (size_t)n_frames * 8, cudaMemcpyHostToDevice);
+            free(h);
+        }
+    }
+    if (d_counts) { cudaStreamSynchronize(ctx->stream); cudaFree(d_counts); }
+    rc = finish(ctx);
+    if (rc == R3D_OK && depth_dev && out_dev && ctx->blocking) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
+    return rc;
+}
+
+extern "C" int r3d_backproject(r3d_ctx* ctx, const void* depth, int dtype, int W, int H, size_t pitch, int n_frames,
+                               const double intr[4], const double* poses, int mode, double depth_scale, double fB,
+                               int compact, float* out_xyz, uint64_t* out_counts) {
+    if (!ctx) return set_error(nullptr, R3D_ERR_ARG, "null context");
+    if (n_frames < 0) return set_error(ctx, R3D_ERR_ARG, "negative frame count");
+    double* rt = nullptr;
+    if (poses) {
+        if (is_device_ptr(poses)) return set_error(ctx, R3D_ERR_ARG, "poses must be host memory (converted per frame on the host)");
+        rt = (double*)malloc((size_t)(n_frames ? n_frames : 1) * 96);
+        int rc = r3d_pose_to_rt(poses, n_frames, 1.0, rt);
+        if (rc != R3D_OK) { free(rt); strncpy(ctx->err, g_last_error, sizeof ctx->err - 1); return rc; }
+    }
+    int rc = r3d_backproject_rt(ctx, depth, dtype, W, H, pitch, n_frames, intr, rt, mode, depth_scale, fB, compact,
+                                R3D_OUT_F32, out_xyz, out_counts);
+    free(rt);
+    return rc;
+}
+
+static int points_affine(r3d_ctx* ctx, const double* xyz, uint64_t n, const double* coeffs, int n_coeffs, double* out_xyz,
+                         bool homogeneous) {
+    if (!ctx) return set_error(nullptr, R3D_ERR_ARG, "null context");
+    if ((!xyz || !out_xyz) && n) return set_error(ctx, R3D_ERR_ARG, "null buffer");
+    if (!coeffs) return set_error(ctx, R3D_ERR_ARG, "null transform");
+    if (n == 0) return R3D_OK;
+    DeviceSetter ds(ctx->device);
+    const bool in_dev = is_device_ptr(xyz), out_dev = is_device_ptr(out_xyz);
+    const size_t bytes = (size_t)n * 24;
+    R3D_TRY(scratch_reserve(ctx, SCR_POSE, 128));
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(ctx->scratch[SCR_POSE], coeffs, (size_t)n_coeffs * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const double* din = xyz;
+    double* dout = out_xyz;
+    if (!in_dev) {
+        R3D_TRY(scratch_reserve(ctx, SCR_IN0, bytes));
+        R3D_CUDA_OK(ctx, cudaMemcpyAsync(ctx->scratch[SCR_IN0], xyz, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        din = (const double*)ctx->scratch[SCR_IN0];
+    }
+    if (!out_dev) {
+        R3D_TRY(scratch_reserve(ctx, SCR_OUT0, bytes));
+        dout = (double*)ctx->scratch[SCR_OUT0];
+    }
+    unsigned long long blocks = (n + 255) / 256;
+    if (blocks > (unsigned long long)ctx->sm_count * 16) blocks = (unsigned long long)ctx->sm_count * 16;
+    if (homogeneous) k_transform_points<<<(unsigned)blocks, 256, 0, ctx->stream>>>(din, dout, n, (const double*)ctx->scratch[SCR_POSE]);
+    else k_pose_apply_points<<<(unsigned)blocks, 256, 0, ctx->stream>>>(din, dout, n, (const double*)ctx->scratch[SCR_POSE]);
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    if (!out_dev) {
+        R3D_CUDA_OK(ctx, cudaMemcpyAsync(out_xyz, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return finish(ctx);
+}
+
+extern "C" int r3d_transform_points(r3d_ctx* ctx, const double* xyz, uint64_t n, const double T[16], double* out_xyz) {
+    return points_affine(ctx, xyz, n, T, 16, out_xyz, true);
+}
+
+extern "C" int r3d_pose_apply_points(r3d_ctx* ctx, const double* xyz, uint64_t n, const double rt[12], double* out_xyz) {
+    return points_affine(ctx, xyz, n, rt, 12, out_xyz, false);
+}

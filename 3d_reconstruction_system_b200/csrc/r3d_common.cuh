@@ -1,0 +1,75 @@
+// r3d_common.cuh -- context object, error plumbing and small device helpers shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/r3d.h"
+#include "r3d_math.cuh"
+
+struct r3d_ctx {
+    int device = 0;
+    int sm_count = 148;
+    int blocking = 1;
+    cudaStream_t stream = nullptr;   // every kernel of this context
+    cudaStream_t copy_stream[2] = {nullptr, nullptr};  // host-pointer staging pipeline
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    float last_kernel_ms = 0.f;
+    uint64_t launches = 0;
+    char err[1024] = {0};
+    // reusable device scratch (grown on demand, freed in r3d_destroy)
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* pinned = nullptr;          // small pinned mailbox for counters read back from the device
+    size_t pinned_bytes = 0;
+};
+
+namespace r3d {
+
+// scratch slots
+enum { SCR_POSE = 0, SCR_IN0 = 1, SCR_IN1 = 2, SCR_OUT0 = 3, SCR_OUT1 = 4, SCR_TILE = 5, SCR_CUBTMP = 6, SCR_MISC = 7, SCR_COUNT = 8 };
+
+extern char g_last_error[1024];
+
+inline int set_error(r3d_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    strncpy(g_last_error, buf, sizeof g_last_error - 1);
+    if (ctx) strncpy(ctx->err, buf, sizeof ctx->err - 1);
+    return code;
+}
+
+#define R3D_CUDA_OK(ctx, expr)                                                                          \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return r3d::set_error(ctx, e__ == cudaErrorMemoryAllocation ? R3D_ERR_OOM : R3D_ERR_CUDA,   \
+                                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define R3D_TRY(expr)                   \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != R3D_OK) return rc__; \
+    } while (0)
+
+// Grows ctx->scratch[slot] to at least `bytes` (contents are NOT preserved).
+int scratch_reserve(r3d_ctx* ctx, int slot, size_t bytes);
+// true when p is device (or managed) memory; false for any host pointer.  *pinned = page-locked host.
+bool is_device_ptr(const void* p, bool* pinned = nullptr);
+int device_set(r3d_ctx* ctx);
+int finish(r3d_ctx* ctx);   // sync if blocking, surface async errors
+
+struct DeviceSetter {
+    int prev = -1;
+    explicit DeviceSetter(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceSetter() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace r3d

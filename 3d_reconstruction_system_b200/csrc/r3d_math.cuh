@@ -1,0 +1,242 @@
+// r3d_math.cuh -- scalar arithmetic shared by every kernel, written so the SAME source also compiles for
+// the host (tests/hostmath builds it with g++ to check the formulas against the oracle without a GPU;
+// that build is test infrastructure, the product only ever runs the device code).
+//
+// Every floating-point operation whose rounding is part of the parity contract goes through the
+// explicit round-to-nearest wrappers below so that no FMA contraction can change a result
+// (device: __dmul_rn & co; host: plain operators, built with -ffp-contract=off).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <float.h>
+
+#if defined(__CUDACC__)
+#define R3D_HD __host__ __device__ __forceinline__
+#else
+#define R3D_HD inline
+#endif
+
+namespace r3d {
+
+// ---------------------------------------------------------------- rounding-explicit ops
+R3D_HD double dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+R3D_HD double dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+R3D_HD double dsub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+R3D_HD double ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+R3D_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+R3D_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+R3D_HD float fsub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+R3D_HD float fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+R3D_HD double dsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+    return __dsqrt_rn(a);
+#else
+    return sqrt(a);
+#endif
+}
+
+// ---------------------------------------------------------------- K1: back-projection + pose
+// point_camera (transfer/camera_to_world.py:57-59): w = Rinv . (p - t), rows evaluated left to right.
+// rt = Rinv row-major (9) followed by t (3).
+struct Pose {
+    double r00, r01, r02, r10, r11, r12, r20, r21, r22, t0, t1, t2;
+};
+R3D_HD void pose_load(const double* __restrict__ rt, Pose& p) {
+    p.r00 = rt[0]; p.r01 = rt[1]; p.r02 = rt[2];
+    p.r10 = rt[3]; p.r11 = rt[4]; p.r12 = rt[5];
+    p.r20 = rt[6]; p.r21 = rt[7]; p.r22 = rt[8];
+    p.t0 = rt[9]; p.t1 = rt[10]; p.t2 = rt[11];
+}
+R3D_HD void pose_apply(const Pose& p, double X, double Y, double Z, double& wx, double& wy, double& wz) {
+    const double d0 = dsub(X, p.t0), d1 = dsub(Y, p.t1), d2 = dsub(Z, p.t2);
+    wx = dadd(dadd(dmul(p.r00, d0), dmul(p.r01, d1)), dmul(p.r02, d2));
+    wy = dadd(dadd(dmul(p.r10, d0), dmul(p.r11, d1)), dmul(p.r12, d2));
+    wz = dadd(dadd(dmul(p.r20, d0), dmul(p.r21, d1)), dmul(p.r22, d2));
+}
+// gentxtcord tables (transfer/camera_to_world.py:77-78): ((i - cx) / fx) and ((j - cy) / fy)
+R3D_HD double pixel_coeff(int i, double c, double f) { return ddiv(dsub((double)i, c), f); }
+
+// depth decode: a1/a2 (Z = raw * depth_scale) and a3 (Z = fB / (raw*depth_scale), d <= 0 -> 0)
+R3D_HD double decode_z(double raw, int mode, double depth_scale, double fB, bool& valid) {
+    const double d = dmul(raw, depth_scale);
+    valid = (d > 0.0) && (d <= DBL_MAX);
+    if (mode == 0) return d;
+    return (d > 0.0) ? ddiv(fB, d) : 0.0;
+}
+
+// ---------------------------------------------------------------- OctoMap keys (a10)
+constexpr int kTreeDepth = 16;
+constexpr int kTreeMaxVal = 32768;
+
+// coordToKeyChecked(double coordinate): (int)floor(resolution_factor * coordinate) + tree_max_val in [0, 65536)
+R3D_HD bool coord_to_key(double res_factor, float x, uint16_t& key) {
+    const double f = floor(dmul(res_factor, (double)x));
+    if (!(f >= -32768.0 && f < 32768.0)) return false;  // also rejects NaN / inf like the x86 cast does
+    key = (uint16_t)((int)f + kTreeMaxVal);
+    return true;
+}
+R3D_HD bool coord_to_key3(double res_factor, float x, float y, float z, uint16_t& kx, uint16_t& ky, uint16_t& kz) {
+    return coord_to_key(res_factor, x, kx) & coord_to_key(res_factor, y, ky) & coord_to_key(res_factor, z, kz);
+}
+// keyToCoord(key) = (double(int(key) - tree_max_val) + 0.5) * resolution
+R3D_HD double key_to_coord(double res, uint16_t key) { return dmul(dadd((double)((int)key - kTreeMaxVal), 0.5), res); }
+
+// updateNodeLogOdds (float add, clamp to [min, max])
+R3D_HD float clamped_add(float v, float upd, float cmin, float cmax) {
+    v = fadd(v, upd);
+    if (v < cmin) return cmin;
+    if (v > cmax) return cmax;
+    return v;
+}
+
+// ---------------------------------------------------------------- bricks
+// A brick is the 8x8x8 voxel block under one depth-13 node.  brick key = bx | by<<13 | bz<<26.
+// Voxel index inside a brick = 9-bit Morton code, child-index convention (x lowest bit per level), so that
+// the 8 children of a depth-15 node are 8 consecutive voxels and a depth-14 node is 64 consecutive voxels.
+R3D_HD uint32_t spread3(uint32_t v) { return (v | (v << 2) | (v << 4)) & 0x49u; }
+R3D_HD uint32_t brick_voxel_index(uint32_t kx, uint32_t ky, uint32_t kz) {
+    return spread3(kx & 7u) | (spread3(ky & 7u) << 1) | (spread3(kz & 7u) << 2);
+}
+R3D_HD uint32_t compact3(uint32_t m) { m &= 0x49u; return (m | (m >> 2) | (m >> 4)) & 7u; }
+R3D_HD void brick_voxel_coords(uint32_t idx, uint32_t& x, uint32_t& y, uint32_t& z) {
+    x = compact3(idx); y = compact3(idx >> 1); z = compact3(idx >> 2);
+}
+R3D_HD uint64_t brick_key(uint32_t kx, uint32_t ky, uint32_t kz) {
+    return (uint64_t)(kx >> 3) | ((uint64_t)(ky >> 3) << 13) | ((uint64_t)(kz >> 3) << 26);
+}
+R3D_HD void brick_key_unpack(uint64_t bk, uint32_t& bx, uint32_t& by, uint32_t& bz) {
+    bx = (uint32_t)(bk & 0x1fffu); by = (uint32_t)((bk >> 13) & 0x1fffu); bz = (uint32_t)((bk >> 26) & 0x1fffu);
+}
+// 39-bit Morton code of the brick coordinates (13 levels, x lowest): pre-order position of the depth-13 node
+R3D_HD uint64_t spread13(uint64_t v) {
+    uint64_t r = 0;
+    for (int i = 0; i < 13; ++i) r |= ((v >> i) & 1ull) << (3 * i);
+    return r;
+}
+R3D_HD uint64_t brick_morton(uint64_t bk) {
+    uint32_t bx, by, bz;
+    brick_key_unpack(bk, bx, by, bz);
+    return spread13(bx) | (spread13(by) << 1) | (spread13(bz) << 2);
+}
+R3D_HD uint64_t hash64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+// ---------------------------------------------------------------- 3-D DDA (a11: computeRayKeys)
+// Mixed float / double exactly as upstream: direction, length, origin are float; tMax, tDelta and the voxel
+// border are double; the half-voxel offset is rounded through float.
+struct Ray {
+    int kx, ky, kz;        // current key
+    int ex, ey, ez;        // end key
+    int sx, sy, sz;        // step
+    double tmx, tmy, tmz;  // tMax
+    double tdx, tdy, tdz;  // tDelta
+    float length;
+};
+// returns: -1 origin or end out of bounds (no free cells), 0 same cell (empty ray), 1 walk (first key = origin key)
+R3D_HD int ray_setup(double res, double res_factor, float ox, float oy, float oz, float ex, float ey, float ez, Ray& r) {
+    uint16_t a, b, c, d, e, f;
+    if (!coord_to_key3(res_factor, ox, oy, oz, a, b, c) || !coord_to_key3(res_factor, ex, ey, ez, d, e, f)) return -1;
+    r.kx = a; r.ky = b; r.kz = c; r.ex = d; r.ey = e; r.ez = f;
+    if (a == d && b == e && c == f) return 0;
+    float dx = fsub(ex, ox), dy = fsub(ey, oy), dz = fsub(ez, oz);
+    const float nsq = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    r.length = (float)dsqrt((double)nsq);
+    dx = fdiv(dx, r.length); dy = fdiv(dy, r.length); dz = fdiv(dz, r.length);
+#define R3D_AXIS(dir, step, key, org, tmax, tdelta)                                        \
+    if (dir > 0.0f) step = 1; else if (dir < 0.0f) step = -1; else step = 0;                \
+    if (step != 0) {                                                                        \
+        double border = key_to_coord(res, (uint16_t)key);                                   \
+        border = dadd(border, (double)(float)dmul(dmul((double)step, res), 0.5));           \
+        tmax = ddiv(dsub(border, (double)org), (double)dir);                                \
+        tdelta = ddiv(res, fabs((double)dir));                                              \
+    } else { tmax = DBL_MAX; tdelta = DBL_MAX; }
+    R3D_AXIS(dx, r.sx, r.kx, ox, r.tmx, r.tdx)
+    R3D_AXIS(dy, r.sy, r.ky, oy, r.tmy, r.tdy)
+    R3D_AXIS(dz, r.sz, r.kz, oz, r.tmz, r.tdz)
+#undef R3D_AXIS
+    return 1;
+}
+// One DDA step.  Returns true when the new current key is a free cell to record, false when the ray is done.
+R3D_HD bool ray_step(Ray& r) {
+    if (r.tmx < r.tmy) {
+        if (r.tmx < r.tmz) { r.kx += r.sx; r.tmx = dadd(r.tmx, r.tdx); }
+        else               { r.kz += r.sz; r.tmz = dadd(r.tmz, r.tdz); }
+    } else {
+        if (r.tmy < r.tmz) { r.ky += r.sy; r.tmy = dadd(r.tmy, r.tdy); }
+        else               { r.kz += r.sz; r.tmz = dadd(r.tmz, r.tdz); }
+    }
+    r.kx &= 0xffff; r.ky &= 0xffff; r.kz &= 0xffff;   // key_type is uint16: wraps like upstream
+    if (r.kx == r.ex && r.ky == r.ey && r.kz == r.ez) return false;
+    const double m01 = r.tmx < r.tmy ? r.tmx : r.tmy;
+    const double dist = m01 < r.tmz ? m01 : r.tmz;
+    if (dist > (double)r.length) return false;
+    return true;
+}
+// computeUpdate's per-point prologue: decides whether the endpoint is an occupied cell and where the ray ends.
+// maxrange < 0: unlimited.  Returns true when the endpoint (px,py,pz) is within range (occupied candidate);
+// (ex,ey,ez) receives the ray end (the point itself, or origin + dir * maxrange).
+R3D_HD bool scan_point_end(float ox, float oy, float oz, float px, float py, float pz, double maxrange,
+                           float& ex, float& ey, float& ez) {
+    ex = px; ey = py; ez = pz;
+    if (maxrange < 0.0) return true;
+    float dx = fsub(px, ox), dy = fsub(py, oy), dz = fsub(pz, oz);
+    const float nsq = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
+    const double len = dsqrt((double)nsq);
+    if (len <= maxrange) return true;
+    if (len > 0) { const float fl = (float)len; dx = fdiv(dx, fl); dy = fdiv(dy, fl); dz = fdiv(dz, fl); }
+    const float mr = (float)maxrange;
+    ex = fadd(ox, fmul(dx, mr)); ey = fadd(oy, fmul(dy, mr)); ez = fadd(oz, fmul(dz, mr));
+    return false;
+}
+
+}  // namespace r3d

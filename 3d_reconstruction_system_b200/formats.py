@@ -1,0 +1,196 @@
+"""File formats either side of the hot path: pose files, depth PNGs, x,y,z txt, PLY, exactly as the
+reference scripts read and write them."""
+import os
+
+import numpy as np
+
+# ------------------------------------------------------------------------------------------------ poses
+
+
+def read_pose_file(path):
+    """The hand-preprocessed comma format get_file_name parses (transfer/camera_to_world.py:138-158):
+    first line skipped; per line split(','): [0] id (ignored), [1:4] t, [4:8] q (fed as is to scipy's
+    scalar-last from_quat), [8] depth PNG file name.  Returns dict(t (n,3), q (n,4), names list)."""
+    t, q, names = [], [], []
+    with open(path, "r") as f:
+        f.readline()
+        for line in f:
+            if not line.strip():
+                continue
+            d = line.split(",")
+            if len(d) < 9:
+                raise ValueError("pose line needs >= 9 comma-separated fields: %r" % line)
+            t.append([float(v) for v in d[1:4]])
+            q.append([float(v) for v in d[4:8]])
+            names.append(d[8].strip())
+    return {"t": np.array(t, dtype=np.float64).reshape(-1, 3), "q": np.array(q, dtype=np.float64).reshape(-1, 4),
+            "names": names}
+
+
+def read_colmap_images_txt(path):
+    """Raw Colmap images.txt (named by BASELINE.json north_star): `IMAGE_ID QW QX QY QZ TX TY TZ CAMERA_ID NAME`
+    on every first line of a pair, `#` comments.  Quaternion reordered (w,x,y,z) -> scipy's (x,y,z,w)."""
+    t, q, names = [], [], []
+    with open(path, "r") as f:
+        lines = [ln for ln in f if not ln.startswith("#")]
+    i = 0
+    while i < len(lines):
+        parts = lines[i].split()
+        if len(parts) >= 10:
+            qw, qx, qy, qz = (float(v) for v in parts[1:5])
+            q.append([qx, qy, qz, qw])
+            t.append([float(v) for v in parts[5:8]])
+            names.append(parts[9])
+            i += 2   # the following line lists the 2-D points
+        else:
+            i += 1
+    return {"t": np.array(t, dtype=np.float64).reshape(-1, 3), "q": np.array(q, dtype=np.float64).reshape(-1, 4),
+            "names": names}
+
+
+def write_pose_file(path, t, q, names):
+    with open(path, "w") as f:
+        f.write("id,tx,ty,tz,qx,qy,qz,qw,name,pad\n")
+        for k, name in enumerate(names):
+            f.write("%d,%r,%r,%r,%r,%r,%r,%r,%s,0\n" % ((k,) + tuple(float(v) for v in t[k]) + tuple(float(v) for v in q[k]) + (name,)))
+
+
+# ------------------------------------------------------------------------------------------------ depth images
+
+
+def imread_gray(path):
+    """cv.imread(path, IMREAD_GRAYSCALE) (transfer/camera_to_world.py:160): always uint8 (16-bit -> >>8)."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+    if img is None:
+        raise FileNotFoundError(path)
+    return img
+
+
+def imread_unchanged_green(path):
+    """cv.imread(path, IMREAD_UNCHANGED)[:, :, 1] (transfer/pixel_to_camera.py:133-134)."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise FileNotFoundError(path)
+    return np.ascontiguousarray(img[:, :, 1])
+
+
+def imread_raw(path):
+    """Full-precision single-channel depth / disparity (uint8 or uint16), for the metric pipelines."""
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise FileNotFoundError(path)
+    if img.ndim == 3:
+        img = img[:, :, 0]
+    return np.ascontiguousarray(img)
+
+
+# ------------------------------------------------------------------------------------------------ txt clouds
+
+
+def _fmt_floats(vals):
+    # str(np.float64) == repr(python float): shortest round-trip representation
+    return [repr(v) for v in vals]
+
+
+def write_xyz_txt(path, x, y, z, z_raw=None, mode="w"):
+    """`str(X),str(Y),str(Z)\\n` per point (camera_to_world.py:79-81,103-104).  z_raw: integer pixel values printed
+    as integers, as the reference does for camera-frame files (Z is still np.uint8 there)."""
+    xs = _fmt_floats(np.asarray(x, dtype=np.float64).ravel().tolist())
+    ys = _fmt_floats(np.asarray(y, dtype=np.float64).ravel().tolist())
+    if z_raw is not None:
+        zr = np.asarray(z_raw).ravel()
+        if zr.dtype.kind in "iu":
+            zs = [str(v) for v in zr.tolist()]
+        else:
+            zs = [str(v) for v in zr]   # numpy scalar str (float32 shortest repr)
+    else:
+        zs = _fmt_floats(np.asarray(z, dtype=np.float64).ravel().tolist())
+    with open(path, mode) as f:
+        f.write("".join([a + "," + b + "," + c + "\n" for a, b, c in zip(xs, ys, zs)]))
+
+
+def read_xyz_txt(path):
+    """x,y,z per line, comma separated (octomap/txt_transfer_octomap.py:16-25; camera_to_world.py:92-98)."""
+    import pandas as pd
+    try:
+        df = pd.read_csv(path, header=None, usecols=[0, 1, 2], dtype=np.float64, float_precision="round_trip")
+    except pd.errors.EmptyDataError:
+        return np.zeros((0, 3), dtype=np.float64)
+    return np.ascontiguousarray(df.to_numpy(dtype=np.float64))
+
+
+# ------------------------------------------------------------------------------------------------ PLY
+
+PLY_HEADER_XYZ = ("ply\n    format ascii 1.0\n    element vertex %d\n    property float x\n"
+                  "    property float y\n    property float z\n    end_header\n    ")
+PLY_HEADER_RGB = ("ply\n    format ascii 1.0\n    element vertex %d\n    property float x\n    property float y\n"
+                  "    property float z\n    property uchar red\n    property uchar green\n    property uchar blue\n"
+                  "    property uchar alpha\n    end_header\n    ")
+PLY_TRAILER = "\n    "
+
+
+def ply_ascii_text(x, y, z, rgb=None):
+    """Exact text of genply (camera_to_world.py:112-134): indented header, '%.4f %.4f %.4f \\n' rows,
+    trailing newline + 4 spaces.  rgb (n,3) -> the genply_noRGB variant (pixel_to_camera.py:55-91)."""
+    x = np.asarray(x, dtype=np.float64).ravel()
+    y = np.asarray(y, dtype=np.float64).ravel()
+    z = np.asarray(z, dtype=np.float64).ravel()
+    n = x.size
+    chunks = []
+    step = 1 << 16
+    if rgb is None:
+        for s in range(0, n, step):
+            m = min(step, n - s)
+            flat = np.stack([x[s:s + m], y[s:s + m], z[s:s + m]], axis=1).ravel().tolist()
+            chunks.append(("%.4f %.4f %.4f \n" * m) % tuple(flat))
+        return (PLY_HEADER_XYZ % n) + "".join(chunks) + PLY_TRAILER
+    rgb = np.asarray(rgb).reshape(n, 3)
+    for s in range(0, n, step):
+        m = min(step, n - s)
+        rows = []
+        for k in range(s, s + m):
+            rows.append("%.4f %.4f %.4f %d %d %d 0\n" % (x[k], y[k], z[k], int(rgb[k, 0]), int(rgb[k, 1]), int(rgb[k, 2])))
+        chunks.append("".join(rows))
+    return (PLY_HEADER_RGB % n) + "".join(chunks) + PLY_TRAILER
+
+
+def write_ply_ascii(path, x, y, z, rgb=None):
+    with open(path, "w") as f:
+        f.write(ply_ascii_text(x, y, z, rgb))
+
+
+def write_ply_binary(path, xyz_f32):
+    """binary_little_endian PLY: the float32 records the back-projection kernel writes are the body as is."""
+    xyz = np.ascontiguousarray(xyz_f32, dtype="<f4").reshape(-1, 3)
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+           "property float z\nend_header\n" % xyz.shape[0])
+    with open(path, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        f.write(xyz.tobytes())
+
+
+def read_ply_points(path, skip_lines=8, max_points=5400001):
+    """txt_read of octomap/ply_transfer_octomap.py:16-40: skip exactly `skip_lines` lines, then whitespace-split rows
+    (first three tokens used), stop after `max_points` points (the reference breaks at generation >= 5 400 000 after
+    inserting that point).  Blank / indentation-only lines are skipped instead of raising (documented deviation)."""
+    pts = []
+    with open(path, "r") as f:
+        for _ in range(skip_lines):
+            f.readline()
+        for line in f:
+            tok = line.split()
+            if len(tok) < 3:
+                continue
+            pts.append((float(tok[0]), float(tok[1]), float(tok[2])))
+            if len(pts) >= max_points:
+                break
+    return np.array(pts, dtype=np.float64).reshape(-1, 3)
+
+
+def ensure_dir(path):
+    d = os.path.dirname(path)
+    if d and not os.path.isdir(d):
+        os.makedirs(d, exist_ok=True)

@@ -1,0 +1,171 @@
+"""Host-side mirror of the reference's transfer/ scripts (same function names, arguments and files),
+with every per-point loop executed by the CUDA kernels of libr3d_b200.so.
+
+Reference                                   here
+  pixel_to_camera.gentxtcord   :24-44        gentxtcord(filename, depth)            -> K1 (camera frame)
+  camera_to_world.scipy_transfer :53-55      scipy_transfer(quat)                   -> r3d_pose_to_rt
+  camera_to_world.point_camera :57-59        point_camera(p1, r_inverse, t)         -> r3d_pose_apply_points
+  camera_to_world.get_pointdata :86-105      get_pointdata(p_path, q, t, x, y, z)   -> r3d_pose_apply_points
+  camera_to_world.genply :112-134            genply / genply_RGB / genply_noRGB     (byte-identical ASCII PLY)
+  camera_to_world.get_file_name :138-174     get_file_name(qt_path)                 -> one fused K1 batch
+
+Module-level constants play the role of the constants the reference hard-codes in its sources.
+"""
+import os
+import time
+
+import numpy as np
+
+from . import formats
+from ._lib import MODE_DEPTH
+from .runtime import default_context
+
+# intrinsics hard-coded at camera_to_world.py:68-71 / pixel_to_camera.py:25-28
+FX, FY, CX, CY = 600.391, 600.079, 320, 240
+# paths hard-coded at camera_to_world.py:87,160,163,174
+POINT_WORLD_PATH = './point_world/small_worldpoint_5_23_5.txt'
+DEPTH_DIR = './depth/'
+POINT_DIR = './point/'
+PLY_PATH = './ply/small_035_p8.ply'
+DEVICE = 0
+
+
+def _intr(intr=None):
+    return (FX, FY, CX, CY) if intr is None else tuple(intr)
+
+
+def str_tofloat(data):
+    """camera_to_world.py:28-30 (np.float was an alias of float)."""
+    return np.array([float(v) for v in data])
+
+
+def scipy_transfer(quat):
+    """R^-1 of the scalar-last quaternion (normalised first), camera_to_world.py:53-55."""
+    rt = default_context(DEVICE).pose_to_rt(np.asarray(quat, dtype=np.float64), np.zeros(3))
+    return np.matrix(rt[0, :9].reshape(3, 3))
+
+
+def point_camera(p1, r_inverse, t):
+    """R^-1 (p - t) (camera_to_world.py:57-59).  A single point returns shape (3, 1) like the reference;
+    an (n, 3) array returns (n, 3)."""
+    p = np.asarray(p1, dtype=np.float64)
+    rt = np.concatenate([np.asarray(r_inverse, dtype=np.float64).reshape(9), np.asarray(t, dtype=np.float64).reshape(3)])
+    ctx = default_context(DEVICE)
+    import ctypes as C  # noqa: F401
+    from ._lib import check
+    pts = np.ascontiguousarray(p.reshape(-1, 3))
+    out = np.empty_like(pts)
+    check(ctx.lib.r3d_pose_apply_points(ctx.handle, pts.ctypes.data, pts.shape[0], rt.ctypes.data, out.ctypes.data), ctx.handle)
+    return out.reshape(3, 1) if p.ndim == 1 else out
+
+
+def camera_points(depth, intr=None, mode=MODE_DEPTH, depth_scale=1.0, fB=0.0):
+    """Back-projection of one frame in fp64: (H*W, 3) camera-frame points, row-major pixel order."""
+    ctx = default_context(DEVICE)
+    xyz, _ = ctx.backproject(np.ascontiguousarray(depth), _intr(intr), rt=None, mode=mode, depth_scale=depth_scale, fB=fB,
+                             out_dtype=np.float64)
+    return xyz
+
+
+def gentxtcord(filename, depth, intr=None):
+    """Depth image -> camera-frame points, written as `str(X),str(Y),str(Z)` lines (camera_to_world.py:67-83,
+    pixel_to_camera.py:24-44).  Returns [xcord, ycord, zcord] like the pixel_to_camera variant (the
+    camera_to_world variant returns None; its caller ignores the value)."""
+    depth = np.ascontiguousarray(depth)
+    xyz = camera_points(depth, intr)
+    formats.write_xyz_txt(filename, xyz[:, 0], xyz[:, 1], xyz[:, 2], z_raw=depth)
+    return [xyz[:, 0].tolist(), xyz[:, 1].tolist(), depth.ravel().tolist()]
+
+
+def get_pointdata(p_path, q, t, xcord, ycord, zcord, point_world_path=None):
+    """Re-read the camera-frame txt, move it to the world frame, append to the three coordinate lists and write the
+    world txt (opened 'w' per call exactly like camera_to_world.py:86-105, so only the last frame survives)."""
+    cam = formats.read_xyz_txt(p_path)
+    r = scipy_transfer(q)
+    world = point_camera(cam, r, t) if cam.shape[0] else cam
+    xcord.extend(world[:, 0].tolist())
+    ycord.extend(world[:, 1].tolist())
+    zcord.extend(world[:, 2].tolist())
+    formats.write_xyz_txt(point_world_path or POINT_WORLD_PATH, world[:, 0], world[:, 1], world[:, 2])
+
+
+def genply(gtxyz, pc_file, lenth_point):
+    """ASCII PLY, byte-identical to camera_to_world.py:112-134."""
+    x = np.asarray(gtxyz[0], dtype=np.float64)[:lenth_point]
+    y = np.asarray(gtxyz[1], dtype=np.float64)[:lenth_point]
+    z = np.asarray(gtxyz[2], dtype=np.float64)[:lenth_point]
+    if not (x.size == y.size == z.size == lenth_point):
+        raise ValueError("could not broadcast input array into shape (%d,)" % lenth_point)
+    formats.write_ply_ascii(pc_file, x, y, z)
+    print("Write into .ply file Done.")
+
+
+def genply_RGB(gtxyz, pc_file):
+    """pixel_to_camera.py:98-124 (despite the name: xyz only)."""
+    genply(gtxyz, pc_file, len(gtxyz[0]))
+
+
+def genply_noRGB(gtxyz, imgpath, pc_file):
+    """pixel_to_camera.py:55-91 (despite the name: xyz + rgb + alpha 0)."""
+    from PIL import Image
+    t1 = time.time()
+    img = np.array(Image.open(imgpath))
+    n = img.shape[0] * img.shape[1]
+    rgb = img[:, :, 0:3].reshape(n, 3)
+    formats.write_ply_ascii(pc_file, np.asarray(gtxyz[0])[:n], np.asarray(gtxyz[1])[:n], np.asarray(gtxyz[2])[:n], rgb=rgb)
+    print("Write into .ply file Done.", time.time() - t1)
+
+
+def sequence_to_world(depths, quats, trans, intr=None, mode=MODE_DEPTH, depth_scale=1.0, fB=0.0, t_scale=1.0,
+                      out_dtype=np.float32, compact=False):
+    """The fused in-memory path: (n, H, W) depth stack + poses -> (n*H*W, 3) world points in one kernel launch."""
+    ctx = default_context(DEVICE)
+    rt = ctx.pose_to_rt(quats, trans, t_scale=t_scale)
+    return ctx.backproject(np.ascontiguousarray(depths), _intr(intr), rt=rt, mode=mode, depth_scale=depth_scale, fB=fB,
+                           out_dtype=out_dtype, compact=compact)
+
+
+def get_file_name(qt_path, intr=None, write_intermediate=True, ply_path=None, pose_format="comma"):
+    """Sequence driver (camera_to_world.py:138-174): pose file -> per frame depth PNG -> world points -> one merged PLY.
+    Frames are read with IMREAD_GRAYSCALE like the reference and pushed through ONE fused kernel launch per image
+    shape; write_intermediate keeps the reference's side files (./point/<name>.txt per frame and the world txt)."""
+    poses = formats.read_pose_file(qt_path) if pose_format == "comma" else formats.read_colmap_images_txt(qt_path)
+    print('data start transfer')
+    n = len(poses["names"])
+    xs, ys, zs = [], [], []
+    k = 0
+    while k < n:
+        t1 = time.time()
+        first = formats.imread_gray(os.path.join(DEPTH_DIR, poses["names"][k]))
+        batch = [first]
+        j = k + 1
+        while j < n and len(batch) < 256:
+            img = formats.imread_gray(os.path.join(DEPTH_DIR, poses["names"][j]))
+            if img.shape != first.shape:
+                break
+            batch.append(img)
+            j += 1
+        stack = np.stack(batch)
+        world, _ = sequence_to_world(stack, poses["q"][k:j], poses["t"][k:j], intr, out_dtype=np.float64)
+        world = world.reshape(j - k, -1, 3)
+        if write_intermediate:
+            cam, _ = default_context(DEVICE).backproject(stack, _intr(intr), rt=None, out_dtype=np.float64)
+            cam = cam.reshape(j - k, -1, 3)
+            for i in range(j - k):
+                name = poses["names"][k + i]
+                formats.write_xyz_txt(os.path.join(POINT_DIR, name[0:-4] + '.txt'), cam[i, :, 0], cam[i, :, 1], cam[i, :, 2],
+                                      z_raw=batch[i])
+            formats.write_xyz_txt(POINT_WORLD_PATH, world[-1, :, 0], world[-1, :, 1], world[-1, :, 2])
+        xs.append(world[:, :, 0].ravel())
+        ys.append(world[:, :, 1].ravel())
+        zs.append(world[:, :, 2].ravel())
+        t2 = time.time()
+        print('##################')
+        print("two epoch cost .", t2 - t1)
+        print('the picture generation is: ', j)
+        k = j
+    x = np.concatenate(xs) if xs else np.zeros(0)
+    y = np.concatenate(ys) if ys else np.zeros(0)
+    z = np.concatenate(zs) if zs else np.zeros(0)
+    genply([x, y, z], ply_path or PLY_PATH, x.size)
+    return x, y, z

@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: world points/s for depth -> world (+PLY record).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--frames F]
+
+One "step" = one pass of the hot path (fused back-projection + pose transform, float32 PLY records) over the
+KITTI-odometry-shape sequence of BASELINE config 2: 4 500 synthetic 1242x375 uint16 depth frames with poses.
+`value` times the kernel with inputs and outputs resident in HBM (CUDA events on the launching stream);
+`e2e` times the same call through the C ABI with HOST (pinned) buffers, H2D and D2H copies inside the timed region.
+Under torchrun every rank runs its own shard of frames (weak scaling: the per-GPU sequence is fixed), no data-path
+collective; the time is the max over ranks.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/points_oracle.py, numpy float64: the
+reference itself is pure Python at ~38 k points/s/core and cannot travel to the GPU box) on all host cores.
+"""
+import argparse
+import importlib
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1242, 375
+N_FRAMES_C2 = 4500
+DEPTH_SCALE = 1.0 / 256.0
+BYTES_PER_PX = 2 + 12          # uint16 depth in, xyz float32 out
+METRIC = "world points/s (depth->world+PLY record)"
+WORKLOAD = "C2: KITTI-odometry-shape 4500 x 1242x375 uint16 depth + Colmap-style poses -> world float32 xyz (binary PLY body)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _cpu_worker(args):
+    from oracle import points_oracle as po
+    seed, k0, nf, n_total = args
+    intr = po.KITTI_INTRINSICS
+    t_acc = 0.0
+    pts = 0
+    for k in range(k0, k0 + nf):
+        depth = po.synth_depth_u16(W, H, intr, seed + (k % 32), "street")
+        q, t = po.synth_pose(k, n_total)
+        t0 = time.perf_counter()
+        rinv = po.scipy_transfer(q)
+        _, world = po.depth_to_world(depth, intr, rinv, t, po.MODE_DEPTH, DEPTH_SCALE)
+        rec = world.astype(np.float32)          # the PLY record
+        t_acc += time.perf_counter() - t0
+        pts += rec.shape[0]
+    return pts, t_acc
+
+
+def cpu_reference_pass(frames_per_core, cores, pool):
+    """One bounded sample of the workload on `cores` processes.  Returns (points, seconds) where seconds is the
+    slowest worker's compute time (pose inverse + back-projection + transform + float32 cast; synthesising the
+    depth frames is not counted)."""
+    jobs = [(20261018 + 2, c * frames_per_core, frames_per_core, N_FRAMES_C2) for c in range(cores)]
+    res = pool.map(_cpu_worker, jobs)
+    return sum(r[0] for r in res), max(r[1] for r in res)
+
+
+def cpu_baseline_sample(min_seconds=5.0):
+    cores = os.cpu_count() or 1
+    with mp.get_context("fork").Pool(cores) as pool:
+        cpu_reference_pass(1, cores, pool)
+        fpc = 2
+        pts, sec = cpu_reference_pass(fpc, cores, pool)
+        while sec < min_seconds and fpc < 64:
+            fpc *= 2
+            pts, sec = cpu_reference_pass(fpc, cores, pool)
+    return {"value": pts / sec, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d frames (%d per core) of the C2 sequence, numpy float64 oracle port, %.1f s" % (fpc * cores, fpc, sec)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    frames_per_core = 4
+    with mp.get_context("fork").Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_reference_pass(1, cores, pool)
+        pts, wall = 0, 0.0
+        for _ in range(args.steps):
+            p, sec = cpu_reference_pass(frames_per_core, cores, pool)
+            pts += p
+            wall += sec
+    value = pts / wall
+    sample = "%d frames/step (%d per core) of the C2 sequence, synthetic street depth, numpy float64 oracle port" % (frames_per_core * cores, frames_per_core)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index, uuid=None):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            if uuid:
+                try:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+                except Exception:
+                    self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def synth_on_device(torch, n_frames, rank, dev):
+    """Synthetic depth of the named shape: 32 analytic 'street' frames made on the host (oracle generator, the same
+    data the CPU arm uses), expanded on the device to n_frames distinct frames (shift + offset per frame)."""
+    from oracle import points_oracle as po
+    base = np.stack([po.synth_depth_u16(W, H, po.KITTI_INTRINSICS, 20261018 + 2 + k, "street") for k in range(32)])
+    b = torch.from_numpy(base.astype(np.int32)).to(dev).reshape(32, H * W)
+    out = torch.empty((n_frames, H * W), dtype=torch.int16, device=dev)
+    step = 256
+    for a in range(0, n_frames, step):
+        k = torch.arange(a, min(a + step, n_frames), device=dev)
+        fr = b[k % 32]
+        fr = torch.where(fr > 0, (fr + ((k * 37) % 64)[:, None]).clamp_(1, 65535), fr)
+        fr = torch.where(fr >= 32768, fr - 65536, fr)          # store the uint16 bit pattern in int16
+        out[a:a + fr.shape[0]] = fr.to(torch.int16)
+    poses = [po.synth_pose(k, max(n_frames, 1)) for k in range(n_frames)]
+    q = np.stack([p[0] for p in poses])
+    t = np.stack([p[1] for p in poses])
+    return out.reshape(n_frames, H, W), q, t
+
+
+def run_gpu_arm(args):
+    import torch
+    r3d = importlib.import_module("3d_reconstruction_system_b200")
+    from oracle import points_oracle as po
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    # CPU baseline first (rank 0, N=1 only): worker processes are forked before any CUDA state exists
+    cpu = cpu_baseline_sample() if (world == 1 and rank == 0 and not args.no_cpu_baseline) else None
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    ctx = r3d.Context(local_rank)
+    n_frames = args.frames or N_FRAMES_C2
+    depth, q, t = synth_on_device(torch, n_frames, rank, dev)
+    rt_host = ctx.pose_to_rt(q, t)
+    rt = torch.from_numpy(rt_host).to(dev)
+    px = n_frames * H * W
+    out = torch.empty((px, 3), dtype=torch.float32, device=dev)
+    counts = np.zeros(n_frames, np.uint64)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def step():
+        ctx.backproject(depth, po.KITTI_INTRINSICS, rt=rt, depth_scale=DEPTH_SCALE, out=out, shape=(n_frames, H, W), counts=counts)
+
+    ctx.set_blocking(False)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    ctx.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(dev), "uuid", None))
+    sampler.start()
+    launches0 = ctx.launch_count()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    if dist is not None:
+        tm = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms_max = float(tm.item())
+    else:
+        total_ms_max = total_ms
+    ctx.set_blocking(True)
+    value = world * px * args.steps / (total_ms_max * 1e-3)
+
+    # sampled parity check of what was just timed (never a fallback: it only asserts)
+    k = n_frames // 2
+    ref = po.depth_to_world(depth[k].cpu().numpy().view(np.uint16), po.KITTI_INTRINSICS, rt_host[k, :9].reshape(3, 3), rt_host[k, 9:],
+                            po.MODE_DEPTH, DEPTH_SCALE)[1].astype(np.float32)
+    got = out[k * H * W:(k + 1) * H * W].cpu().numpy()
+    parity_ok = bool(np.array_equal(got, ref))
+
+    # ---- end to end through the C ABI with host buffers
+    e2e = None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    e2e_frames = n_frames
+    while e2e_frames > 64 and e2e_frames * H * W * 14 * 1.3 > avail * 0.5:
+        e2e_frames //= 2
+    lib = ctx.lib
+    in_bytes, out_bytes = e2e_frames * H * W * 2, e2e_frames * H * W * 12
+    h_in, h_out = lib.r3d_host_alloc(in_bytes), lib.r3d_host_alloc(out_bytes)
+    if h_in and h_out:
+        import ctypes as C
+        np_in = np.ctypeslib.as_array(C.cast(h_in, C.POINTER(C.c_uint16)), shape=(e2e_frames, H, W))
+        np_in[:] = depth[:e2e_frames].cpu().numpy().view(np.uint16)
+        np_out = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_float)), shape=(e2e_frames * H * W, 3))
+        e_steps = max(1, min(args.steps, 3))
+        ctx.backproject(np_in, po.KITTI_INTRINSICS, rt=rt_host[:e2e_frames], depth_scale=DEPTH_SCALE, out=np_out, counts=counts)
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            ctx.backproject(np_in, po.KITTI_INTRINSICS, rt=rt_host[:e2e_frames], depth_scale=DEPTH_SCALE, out=np_out, counts=counts)
+        wall = time.perf_counter() - t0
+        if dist is not None:
+            tw = torch.tensor([wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            wall = float(tw.item())
+        e2e_ok = bool(np.array_equal(np_out[k * H * W:(k + 1) * H * W], ref)) if k < e2e_frames else None
+        e2e = {"value": world * e2e_frames * H * W * e_steps / wall, "unit": "points/s", "h2d_bytes_per_step": in_bytes + e2e_frames * 96,
+               "d2h_bytes_per_step": out_bytes, "frames": e2e_frames, "steps": e_steps, "parity_ok": e2e_ok,
+               "path": "r3d_backproject_rt with pinned host buffers (chunked H2D -> kernel -> D2H on two streams)"}
+        del np_in, np_out
+    lib.r3d_host_free(h_in)
+    lib.r3d_host_free(h_out)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        kernel_ms = float(np.mean(per_step))
+        achieved = px * BYTES_PER_PX / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n_frames == N_FRAMES_C2 else WORKLOAD.replace("4500", str(n_frames)),
+                       "frames_per_gpu": n_frames, "pixels_per_step_per_gpu": px, "l2": "inputs+outputs %.1f GB per step >> 126 MB L2" % (px * 14 / 1e9),
+                       "parity_sample_ok": parity_ok},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "k1_bulk<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
+                         "kernel_ms": kernel_ms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the 4500 of BASELINE config 2)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,210 @@
+"""Parity of the fused back-projection / pose-transform kernel (K1) with the oracle, through the C ABI.
+
+Bars (BASELINE.json north_star): points within 1e-5 relative or 1e-4 m absolute of the float64 numpy reference;
+voxel keys bit-exact.  The kernel mirrors the oracle's operation order in fp64, so the tests below assert the much
+stronger property that fp64 records are BIT-IDENTICAL to the oracle and fp32 records are its correctly rounded cast."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import points_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(r3d):
+    c = r3d.Context(0)
+    yield c
+    c.close()
+
+
+def oracle_batch(depths, intr, rts, mode=0, depth_scale=1.0, fB=0.0):
+    cams, worlds = [], []
+    for k in range(depths.shape[0]):
+        rinv = rts[k, :9].reshape(3, 3) if rts is not None else np.eye(3)
+        t = rts[k, 9:] if rts is not None else np.zeros(3)
+        cam, world = po.depth_to_world(depths[k], intr, rinv, t, mode, depth_scale, fB)
+        cams.append(cam)
+        worlds.append(world)
+    return np.concatenate(cams), np.concatenate(worlds)
+
+
+def random_rt(n, rng, spread=1700.0):
+    q = rng.normal(size=(n, 4))
+    t = rng.uniform(-spread, spread, size=(n, 3))
+    return np.concatenate([np.stack([po.scipy_transfer(q[k]).reshape(9) for k in range(n)]), t], axis=1)
+
+
+def keys_of(xyz32, res=0.1):
+    return np.floor((1.0 / res) * xyz32.astype(np.float64)).astype(np.int64) + 32768
+
+
+def assert_tolerance(got, ref):
+    err = np.abs(got.astype(np.float64) - ref)
+    assert np.all((err <= 1e-4) | (err <= 1e-5 * np.abs(ref)))
+
+
+def test_golden_reference_frames(ctx, golden_dir):
+    """The three frames the reference itself processed (tests/golden, made by oracle/gen_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "ref_c2w_small.npz"))
+    rt = np.concatenate([z["rinv"].reshape(3, 9), z["trans"]], axis=1)
+    got64, counts = ctx.backproject(z["depths"], po.REF_INTRINSICS, rt=rt, out_dtype=np.float64)
+    ref = z["world"].reshape(-1, 3)
+    assert_tolerance(got64, ref)
+    scale = np.abs(z["trans"]).max(axis=1).repeat(77)[:, None] + np.abs(ref) + 255.0
+    assert np.max(np.abs(got64 - ref) / scale) <= 4 * np.finfo(np.float64).eps      # reference BLAS order: <= 2 ulp
+    _, oracle_world = oracle_batch(z["depths"], po.REF_INTRINSICS, rt)
+    assert np.array_equal(got64, oracle_world)                                        # fixed-order oracle: bit-exact
+    got32, _ = ctx.backproject(z["depths"], po.REF_INTRINSICS, rt=rt)
+    assert np.array_equal(got32, oracle_world.astype(np.float32))
+    assert np.array_equal(keys_of(got32), keys_of(ref.astype(np.float32)))
+    assert counts.tolist() == [77, 77, 77]
+    # through the quaternion entry point (C++ pose conversion): still within tolerance and key-identical
+    got_q, _ = ctx.backproject_qt(z["depths"], po.REF_INTRINSICS, z["quats"], z["trans"])
+    assert_tolerance(got_q, ref)
+    assert np.array_equal(keys_of(got_q), keys_of(ref.astype(np.float32)))
+
+
+def test_camera_frame_matches_reference_text(ctx, golden_dir):
+    """gentxtcord: camera-frame fp64 records reproduce the reference's txt bytes."""
+    z = np.load(os.path.join(golden_dir, "ref_c2w_small.npz"))
+    txt = json.load(open(os.path.join(golden_dir, "ref_c2w_small_text.json")))
+    cam, _ = ctx.backproject(z["depths"], po.REF_INTRINSICS, rt=None, out_dtype=np.float64)
+    cam = cam.reshape(3, -1, 3)
+    for k in range(3):
+        assert po.txt_lines_camera(cam[k, :, 0], cam[k, :, 1], z["depths"][k]) == txt["cam_txt"][k]
+    g = np.load(os.path.join(golden_dir, "ref_p2c_640.npz"))
+    cam, _ = ctx.backproject(g["depth"], po.REF_INTRINSICS, rt=None, out_dtype=np.float64)
+    assert np.array_equal(cam[g["sel"], 0], g["X"]) and np.array_equal(cam[g["sel"], 1], g["Y"])
+    assert np.array_equal(cam[g["sel"], 2], g["Z"])
+
+
+@pytest.mark.parametrize("dtype,scale", [(np.uint16, 1.0 / 256.0), (np.uint8, 1.0), (np.float32, 1.0)])
+@pytest.mark.parametrize("shape", [(5, 375, 1242), (3, 480, 640), (2, 7, 11), (1, 1, 1), (1, 33, 1025)])
+def test_bit_exact_vs_oracle(ctx, dtype, scale, shape):
+    rng = np.random.default_rng(20261018 + shape[2])
+    n, H, W = shape
+    if dtype == np.float32:
+        depths = rng.uniform(0, 80, size=shape).astype(np.float32)
+    else:
+        depths = rng.integers(0, np.iinfo(dtype).max + 1, size=shape).astype(dtype)
+    depths.reshape(-1)[0] = 0
+    intr = po.KITTI_INTRINSICS if W == 1242 else po.REF_INTRINSICS
+    rt = random_rt(n, rng)
+    cam_ref, world_ref = oracle_batch(depths, intr, rt, 0, scale)
+    got64, _ = ctx.backproject(depths, intr, rt=rt, depth_scale=scale, out_dtype=np.float64)
+    assert np.array_equal(got64, world_ref)
+    got32, _ = ctx.backproject(depths, intr, rt=rt, depth_scale=scale)
+    assert np.array_equal(got32, world_ref.astype(np.float32))
+    assert np.array_equal(keys_of(got32), keys_of(world_ref.astype(np.float32)))
+    cam64, _ = ctx.backproject(depths, intr, rt=None, depth_scale=scale, out_dtype=np.float64)
+    assert np.array_equal(cam64, cam_ref)
+
+
+def test_disparity_mode(ctx):
+    rng = np.random.default_rng(4)
+    shape = (3, 480, 640)
+    disp = rng.integers(0, 65536, size=shape).astype(np.uint16)
+    disp[0, :10] = 0                                       # invalid disparities -> Z = 0
+    fB = 269.5 * 0.25
+    rt = random_rt(3, rng, spread=100.0)
+    _, world_ref = oracle_batch(disp, po.AIRSIM_INTRINSICS, rt, po.MODE_DISPARITY, 1.0 / 256.0, fB)
+    got64, _ = ctx.backproject(disp, po.AIRSIM_INTRINSICS, rt=rt, mode=po.MODE_DISPARITY, depth_scale=1.0 / 256.0, fB=fB,
+                               out_dtype=np.float64)
+    assert np.array_equal(got64, world_ref)
+
+
+def test_compaction_keeps_order_and_counts(ctx):
+    rng = np.random.default_rng(5)
+    shape = (4, 375, 1242)
+    depths = rng.integers(0, 4, size=shape).astype(np.uint16) * rng.integers(0, 20000, size=shape).astype(np.uint16)
+    depths[2] = 0                                          # a frame with no valid pixel
+    rt = random_rt(4, rng)
+    _, world_ref = oracle_batch(depths, po.KITTI_INTRINSICS, rt, 0, 1.0 / 256.0)
+    mask = np.concatenate([po.valid_mask(depths[k], 0, 1.0 / 256.0).ravel() for k in range(4)])
+    got, counts = ctx.backproject(depths, po.KITTI_INTRINSICS, rt=rt, depth_scale=1.0 / 256.0, compact=True, out_dtype=np.float64)
+    assert counts.tolist() == [int(po.valid_mask(depths[k]).sum()) for k in range(4)]
+    assert counts[2] == 0
+    assert np.array_equal(got, world_ref[mask])
+    got32, _ = ctx.backproject(depths, po.KITTI_INTRINSICS, rt=rt, depth_scale=1.0 / 256.0, compact=True)
+    assert np.array_equal(got32, world_ref[mask].astype(np.float32))
+
+
+def test_pitched_rows_and_empty_batch(ctx):
+    rng = np.random.default_rng(6)
+    n, H, W = 2, 37, 101
+    padded = rng.integers(0, 65536, size=(n, H, W + 27)).astype(np.uint16)
+    depths = np.ascontiguousarray(padded[:, :, :W])
+    rt = random_rt(n, rng)
+    _, world_ref = oracle_batch(depths, po.REF_INTRINSICS, rt, 0, 0.001)
+    got, _ = ctx.backproject(padded, po.REF_INTRINSICS, rt=rt, depth_scale=0.001, out_dtype=np.float64, shape=(n, H, W),
+                             pitch=(W + 27) * 2)
+    assert np.array_equal(got, world_ref)
+    got0, c0 = ctx.backproject(np.zeros((0, 4, 4), np.uint8), po.REF_INTRINSICS, rt=np.zeros((0, 12)))
+    assert got0.shape == (0, 3)
+
+
+def test_device_pointers_equal_host_path(ctx):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(8)
+    shape = (9, 375, 1242)
+    depths = rng.integers(0, 65536, size=shape).astype(np.uint16)
+    rt = random_rt(9, rng)
+    host, _ = ctx.backproject(depths, po.KITTI_INTRINSICS, rt=rt, depth_scale=1 / 256.0)
+    d_depth = torch.from_numpy(depths.view(np.int16)).cuda()
+    d_rt = torch.from_numpy(rt).cuda()
+    d_out = torch.empty((9 * 375 * 1242, 3), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    before = ctx.launch_count()
+    ctx.backproject(d_depth, po.KITTI_INTRINSICS, rt=d_rt, depth_scale=1 / 256.0, out=d_out, shape=shape,
+                    counts=np.zeros(9, np.uint64))
+    assert ctx.launch_count() > before
+    assert np.array_equal(d_out.cpu().numpy(), host)
+    assert ctx.last_kernel_ms() > 0
+
+
+def test_large_batch_properties(ctx):
+    """BASELINE-size frames, 256 of them: chunk invariance + sampled oracle check (the full oracle would take minutes)."""
+    rng = np.random.default_rng(9)
+    n, H, W = 256, 375, 1242
+    depths = rng.integers(0, 65536, size=(n, H, W)).astype(np.uint16)
+    q = np.stack([po.synth_pose(k, n)[0] for k in range(n)])
+    t = np.stack([po.synth_pose(k, n)[1] for k in range(n)])
+    rt = ctx.pose_to_rt(q, t)
+    whole, _ = ctx.backproject(depths, po.KITTI_INTRINSICS, rt=rt, depth_scale=1 / 256.0)
+    parts = [ctx.backproject(depths[a:a + 37], po.KITTI_INTRINSICS, rt=rt[a:a + 37], depth_scale=1 / 256.0)[0] for a in range(0, n, 37)]
+    assert np.array_equal(whole, np.concatenate(parts))
+    for k in (0, 101, 255):
+        _, wref = po.depth_to_world(depths[k], po.KITTI_INTRINSICS, rt[k, :9].reshape(3, 3), rt[k, 9:], 0, 1 / 256.0)
+        assert np.array_equal(whole[k * H * W:(k + 1) * H * W], wref.astype(np.float32))
+
+
+def test_bad_arguments_raise(ctx, r3d):
+    with pytest.raises(r3d.R3DError):
+        ctx.backproject(np.zeros((1, 4, 4), np.uint8), po.REF_INTRINSICS, mode=7)
+    with pytest.raises(TypeError):
+        ctx.backproject(np.zeros((1, 4, 4), np.int64), po.REF_INTRINSICS)
+    with pytest.raises(ValueError):
+        ctx.pose_to_rt(np.zeros((1, 4)), np.zeros((1, 3)))
+
+
+def test_point_camera_and_transform_points(ctx, golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_c2w_small.npz"))
+    import importlib
+    tr = importlib.import_module("3d_reconstruction_system_b200.transfer")
+    k = 2
+    cam, _ = po.depth_to_world(z["depths"][k], po.REF_INTRINSICS, z["rinv"][k], z["trans"][k])
+    got = tr.point_camera(cam, z["rinv"][k], z["trans"][k])
+    assert np.array_equal(got, po.point_camera(cam, z["rinv"][k], z["trans"][k]))
+    assert tr.point_camera(cam[3], z["rinv"][k], z["trans"][k]).shape == (3, 1)
+    r = tr.scipy_transfer(z["quats"][k])
+    assert np.max(np.abs(np.asarray(r) - z["rinv"][k])) <= 4 * np.finfo(np.float64).eps
+    T = np.eye(4)
+    T[:3, :3] = z["rinv"][0]
+    T[:3, 3] = [1.0, -2.0, 3.5]
+    out = ctx.transform_points(cam, T)
+    want = np.stack([((T[i, 0] * cam[:, 0] + T[i, 1] * cam[:, 1]) + T[i, 2] * cam[:, 2]) + T[i, 3] for i in range(3)], axis=1)
+    assert np.array_equal(out, want)

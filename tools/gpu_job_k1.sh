@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU job: K1 parity tests, smoke, bench, ncu launch list + full capture of k1_bulk.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/smi.txt 2>&1
+nproc >> gpurun_out/smi.txt; free -g >> gpurun_out/smi.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
+tail -3 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err; echo "bench exit $?"
+cat gpurun_out/bench_full.json
+CMD="python bench.py --frames 512 --steps 2 --warmup 3 --no-cpu-baseline"
+timeout 600 $CMD > gpurun_out/plain.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+timeout 600 $CMD > gpurun_out/plain2.log 2>&1 &&
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k1_bulk -s 3 -c 2 -o gpurun_out/k1_prof -f $CMD > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out
