@@ -26,7 +26,7 @@ struct K1Args {
     unsigned long long px_begin;   // first flat pixel handled by this launch (generic kernels)
     unsigned long long px_count;   // pixels handled by this launch
     unsigned long long n_tiles;    // bulk: full tiles
-    unsigned W, H, WH;
+    unsigned W, H, WH, n_frames;
     unsigned long long pitch;      // bytes per row
     double fx, fy, cx, cy, depth_scale, fB;
     int mode;
@@ -96,11 +96,11 @@ template <>
 __device__ __forceinline__ double out_cast<double>(double v) { return v; }
 
 // One pixel: raw sample + table entries -> record.  `pose_frame` caches which frame `pose` holds.
-template <typename OutT, bool kWorld>
+template <typename OutT, bool kWorld, int kMode = -1>
 __device__ __forceinline__ bool k1_pixel(const K1Args& a, double raw, double au, double bv, unsigned frame,
                                          unsigned& pose_frame, Pose& pose, OutT& ox, OutT& oy, OutT& oz) {
     bool valid;
-    const double Z = decode_z(raw, a.mode, a.depth_scale, a.fB, valid);
+    const double Z = decode_z(raw, kMode < 0 ? a.mode : kMode, a.depth_scale, a.fB, valid);
     const double X = dmul(au, Z);
     const double Y = dmul(bv, Z);
     if (kWorld) {
@@ -117,14 +117,33 @@ __device__ __forceinline__ bool k1_pixel(const K1Args& a, double raw, double au,
     return valid;
 }
 
+// Same with the pose already in registers (hot kernel: the reload sits on the rare frame-wrap path).
+template <typename OutT, bool kWorld, int kMode>
+__device__ __forceinline__ void k1_pixel_pose(const K1Args& a, double raw, double au, double bv, const Pose& pose, OutT& ox,
+                                              OutT& oy, OutT& oz) {
+    bool valid;
+    const double Z = decode_z(raw, kMode, a.depth_scale, a.fB, valid);
+    const double X = dmul(au, Z);
+    const double Y = dmul(bv, Z);
+    if (kWorld) {
+        double wx, wy, wz;
+        pose_apply(pose, X, Y, Z, wx, wy, wz);
+        ox = out_cast<OutT>(wx); oy = out_cast<OutT>(wy); oz = out_cast<OutT>(wz);
+    } else {
+        ox = out_cast<OutT>(X); oy = out_cast<OutT>(Y); oz = out_cast<OutT>(Z);
+    }
+}
+
 __device__ __forceinline__ void k1_tables(const K1Args& a, double* col, double* row) {
     for (unsigned i = threadIdx.x; i < a.W; i += blockDim.x) col[i] = pixel_coeff((int)i, a.cx, a.fx);
     for (unsigned j = threadIdx.x; j < a.H; j += blockDim.x) row[j] = pixel_coeff((int)j, a.cy, a.fy);
 }
 
 // ------------------------------------------------------------------ k1_bulk: the hot kernel
-template <typename DepthT, typename OutT, bool kWorld, int kOutBufs>
-__global__ void __launch_bounds__(K1_THREADS) k1_bulk(const K1Args a) {
+// Requires W >= K1_THREADS and H >= 8 (smaller images take the generic kernel) so that stepping a pixel index by
+// 256 or 1024 wraps the column at most (1 + 1024/W) times and the row at most once.
+template <typename DepthT, typename OutT, bool kWorld, int kMode, int kOutBufs>
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_bulk(const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // K1_STAGES mbarriers
     double* col = reinterpret_cast<double*>(smem + 128);
@@ -163,41 +182,43 @@ __global__ void __launch_bounds__(K1_THREADS) k1_bulk(const K1Args a) {
         }
     }
 
-    // (frame, row, column) of this thread's first pixel, advanced incrementally: no division in the tile loop
+    // (frame, row, column) of this thread's first pixel of the tile, advanced incrementally: no division in the loop
     const unsigned long long px0 = t0 * K1_TILE + tid;
     unsigned f0 = (unsigned)(px0 / a.WH);
     const unsigned r0 = (unsigned)(px0 - (unsigned long long)f0 * a.WH);
     unsigned v0 = r0 / a.W, u0 = r0 - v0 * a.W;
-    const unsigned q_thr = K1_THREADS / a.W, r_thr = K1_THREADS - q_thr * a.W;   // +256 pixels
-    const unsigned q_tile = K1_TILE / a.W, r_tile = K1_TILE - q_tile * a.W;      // +1024 pixels
+    const unsigned W = a.W, H = a.H;
+    const unsigned q_tile = K1_TILE / W, r_tile = K1_TILE - q_tile * W;      // +1024 pixels
     unsigned pose_frame = 0xffffffffu;
     Pose pose;
 
-    unsigned it = 0;
-    for (unsigned long long t = t0; t < t1; ++t, ++it) {
-        const unsigned stage = it % K1_STAGES;
-        const unsigned parity = (it / K1_STAGES) & 1u;
-        const unsigned ob = it % kOutBufs;
+    unsigned stage = 0, parity = 0, ob = 0;
+    for (unsigned long long t = t0; t < t1; ++t) {
         mbar_wait(&full[stage], parity);
-        const DepthT* tin = in_s + (size_t)stage * K1_TILE;
-        OutT* tout = out_s + (size_t)ob * K1_TILE * 3;
-        unsigned u = u0, v = v0, f = f0;
-#pragma unroll
+        const DepthT* tin = in_s + (size_t)stage * K1_TILE + tid;
+        OutT* tout = out_s + (size_t)ob * K1_TILE * 3 + tid * 3;
+        unsigned u = u0, v = v0;
+        if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
+#pragma unroll 1
         for (int j = 0; j < K1_PPT; ++j) {
-            const unsigned idx = tid + j * K1_THREADS;
             OutT x, y, z;
-            k1_pixel<OutT, kWorld>(a, raw_to_double(tin[idx]), col[u], row[v], f, pose_frame, pose, x, y, z);
-            tout[idx * 3 + 0] = x; tout[idx * 3 + 1] = y; tout[idx * 3 + 2] = z;
-            u += r_thr; v += q_thr;
-            if (u >= a.W) { u -= a.W; ++v; }
-            while (v >= a.H) { v -= a.H; ++f; }
+            k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(tin[j * K1_THREADS]), col[u], row[v], pose, x, y, z);
+            tout[j * K1_THREADS * 3 + 0] = x; tout[j * K1_THREADS * 3 + 1] = y; tout[j * K1_THREADS * 3 + 2] = z;
+            u += K1_THREADS;                       // W >= 256: at most one column wrap
+            if (u >= W) {
+                u -= W;
+                if (++v == H) {                    // next frame (rare): switch pose
+                    v = 0;
+                    if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
+                }
+            }
         }
         // the bulk store issued kOutBufs-1 tiles ago must have finished reading the buffer the NEXT tile writes
         if (tid == 0) bulk_wait_read<kOutBufs - 2>();
         fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
-            bulk_store(gout + t * (unsigned long long)K1_TILE * 3, tout, kOutBytes);
+            bulk_store(gout + t * (unsigned long long)K1_TILE * 3, out_s + (size_t)ob * K1_TILE * 3, kOutBytes);
             bulk_commit();
             const unsigned long long tn = t + K1_STAGES;
             if (tn < t1) {   // every thread is past its reads of this stage (barrier above): refill it
@@ -206,8 +227,10 @@ __global__ void __launch_bounds__(K1_THREADS) k1_bulk(const K1Args a) {
             }
         }
         u0 += r_tile; v0 += q_tile;
-        if (u0 >= a.W) { u0 -= a.W; ++v0; }
-        while (v0 >= a.H) { v0 -= a.H; ++f0; }
+        if (u0 >= W) { u0 -= W; ++v0; }
+        if (v0 >= H) { v0 -= H; ++f0; }
+        if (++stage == K1_STAGES) { stage = 0; parity ^= 1u; }
+        if (++ob == kOutBufs) ob = 0;
     }
     if (tid == 0) bulk_wait_all<0>();
 }
@@ -389,7 +412,7 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
         a.n_tiles = total / K1_TILE;
         const size_t smem = 128 + table_bytes + (size_t)K1_STAGES * K1_TILE * sizeof(DepthT) +
                             (size_t)kOutBufs * K1_TILE * 3 * sizeof(OutT);
-        auto kern = k1_bulk<DepthT, OutT, kWorld, kOutBufs>;
+        auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk<DepthT, OutT, kWorld, 0, kOutBufs> : k1_bulk<DepthT, OutT, kWorld, 1, kOutBufs>;
         R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem));
@@ -432,7 +455,7 @@ static int launch_k1(r3d_ctx* ctx, cudaStream_t st, const void* d_depth, int dty
     K1Args a;
     memset(&a, 0, sizeof a);
     a.depth = d_depth; a.out = d_out; a.rt = d_rt;
-    a.W = (unsigned)W; a.H = (unsigned)H; a.WH = (unsigned)W * (unsigned)H;
+    a.W = (unsigned)W; a.H = (unsigned)H; a.WH = (unsigned)W * (unsigned)H; a.n_frames = (unsigned)n_frames;
     a.pitch = pitch;
     a.fx = intr[0]; a.fy = intr[1]; a.cx = intr[2]; a.cy = intr[3];
     a.depth_scale = depth_scale; a.fB = fB; a.mode = mode;
@@ -440,7 +463,7 @@ static int launch_k1(r3d_ctx* ctx, cudaStream_t st, const void* d_depth, int dty
     const unsigned long long total = (unsigned long long)n_frames * a.WH;
     const size_t es = elem_size(dtype);
     const size_t osz = out_dtype == R3D_OUT_F32 ? 4 : 8;
-    const bool bulk_ok = pitch == (size_t)W * es && ((uintptr_t)d_depth % 16 == 0) && ((uintptr_t)d_out % 16 == 0) &&
+    const bool bulk_ok = W >= K1_THREADS && H >= 8 && pitch == (size_t)W * es && ((uintptr_t)d_depth % 16 == 0) && ((uintptr_t)d_out % 16 == 0) &&
                          ((size_t)(W + H) * 8 + (size_t)K1_STAGES * K1_TILE * es + 3 * (size_t)K1_TILE * 3 * osz < 200 * 1024);
     switch (dtype) {
         case R3D_U8: return launch_k1_depth<unsigned char>(ctx, st, a, bulk_ok, compact, out_dtype, total);

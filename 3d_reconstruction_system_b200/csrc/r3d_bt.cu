@@ -1,0 +1,482 @@
+// r3d_bt.cu -- K5: tree shape, size() and the .bt byte stream, derived on the GPU from the flat voxel store.
+//
+// Replaces OcTree.writeBinary / size() of the `octomap` extension (octomap/txt_transfer_octomap.py:36,
+// octomap/ply_transfer_octomap.py:48): toMaxLikelihood -> prune -> header -> pre-order 2-bits-per-child stream.
+//
+// Upstream's tree after any sequence of non-lazy updateNode calls is maximally pruned under EXACT float equality
+// of sibling leaves (every update re-tests all ancestors), so its shape is a pure function of the leaf values:
+// "S0" below.  writeBinary then thresholds every node and runs prune(): passes over depth 15, 14, ... 1 that
+// collapse nodes whose 8 children are leaves with the same occupancy, STOPPING at the first pass that prunes
+// nothing.  Both rules are reproduced level by level: three levels inside each brick (one warp per brick), then
+// one small kernel per level above over the Morton-sorted brick list.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <string>
+#include <vector>
+
+#include "r3d_octree.cuh"
+
+namespace r3d {
+
+struct UpNode {            // a node at depth <= 13
+    uint64_t prefix;       // Morton code of the node (3 bits per level, child-index convention)
+    uint64_t node_cnt;     // nodes in the subtree, this one included
+    uint64_t offset;       // pre-order index among INNER nodes (~0: not emitted)
+    float s0val;           // common log-odds when S0-collapsed
+    uint32_t inner_cnt;    // inner nodes in the subtree, this one included (0 for a leaf)
+    uint32_t first_child;  // index of the first child in the next level's array
+    uint16_t mask;         // the 2 bytes writeBinaryNode emits for this node
+    uint8_t flags;         // bit0 leaf, bit1 occupied, bit2 S0 leaf
+    uint8_t nchild;
+};
+enum { F_LEAF = 1, F_OCC = 2, F_S0 = 4 };
+
+struct BtCounters {
+    unsigned long long pruned[17];   // nodes collapsed by the max-likelihood pass at each depth
+};
+
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x & 1u) | ((x & 2u) << 1) | ((x & 4u) << 2) | ((x & 8u) << 3); }
+// children c = 0..7 of 14-node k live in lanes 4k + c/2, half c&1
+__device__ __forceinline__ uint32_t gather8(uint32_t b0, uint32_t b1, uint32_t k) {
+    return spread4((b0 >> (4 * k)) & 0xfu) | (spread4((b1 >> (4 * k)) & 0xfu) << 1);
+}
+
+// Per-brick structure, computed cooperatively by one warp.  ran15 / ran14 / ran13: whether the max-likelihood prune
+// passes at depth 15 / 14 / 13 run (all false: the value-pruned shape only, for size()).
+struct BrickShape {
+    // per lane: its two depth-15 nodes
+    uint32_t kn[2], oc[2];         // known / occupied bits of the 8 voxels
+    bool exists15[2], leaf15[2], occ15[2], s0leaf15[2], mlc15[2];
+    // per lane, about the depth-14 node k = lane / 4 (identical in the 4 lanes of a group)
+    bool exists14, leaf14, occ14, s0leaf14, mlc14;
+    uint32_t ex15_8, leaf15_8, occ15_8;   // 8-bit child summaries of node k
+    // brick root (identical in all lanes)
+    bool leaf13, occ13, s0leaf13, mlc13;
+    uint32_t ex14_8, leaf14_8, occ14_8;
+    float s0val;                  // lane 0's first value (the S0 value when s0leaf13)
+};
+
+__device__ __forceinline__ void brick_shape(const float* __restrict__ values, const uint32_t* __restrict__ known, float thres,
+                                            bool ran15, bool ran14, bool ran13, BrickShape& s) {
+    const unsigned lane = threadIdx.x & 31u;
+    const float4* v4 = reinterpret_cast<const float4*>(values + lane * 16);
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = v4[q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    const uint32_t kn16 = (known[lane >> 1] >> ((lane & 1u) * 16u)) & 0xffffu;
+    float first[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t kn = (kn16 >> (8 * h)) & 0xffu;
+        uint32_t oc = 0;
+        bool alleq = true;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (v[8 * h + b] >= thres) oc |= 1u << b;
+            alleq = alleq && (v[8 * h + b] == v[8 * h]);
+        }
+        oc &= kn;
+        s.kn[h] = kn; s.oc[h] = oc;
+        s.exists15[h] = kn != 0;
+        const bool full = kn == 0xffu;
+        s.s0leaf15[h] = full && alleq;
+        s.mlc15[h] = ran15 && !s.s0leaf15[h] && full && (oc == 0xffu || oc == 0u);
+        s.leaf15[h] = s.s0leaf15[h] || s.mlc15[h];
+        s.occ15[h] = (oc & 1u) != 0;
+        first[h] = v[8 * h];
+    }
+    const uint32_t k = lane >> 2;
+    const uint32_t ex0 = __ballot_sync(0xffffffffu, s.exists15[0]), ex1 = __ballot_sync(0xffffffffu, s.exists15[1]);
+    const uint32_t lf0 = __ballot_sync(0xffffffffu, s.leaf15[0]), lf1 = __ballot_sync(0xffffffffu, s.leaf15[1]);
+    const uint32_t oc0 = __ballot_sync(0xffffffffu, s.occ15[0]), oc1 = __ballot_sync(0xffffffffu, s.occ15[1]);
+    const uint32_t s00 = __ballot_sync(0xffffffffu, s.s0leaf15[0]), s01 = __ballot_sync(0xffffffffu, s.s0leaf15[1]);
+    const float ref14 = __shfl_sync(0xffffffffu, first[0], lane & ~3u);
+    const uint32_t eq0 = __ballot_sync(0xffffffffu, first[0] == ref14), eq1 = __ballot_sync(0xffffffffu, first[1] == ref14);
+    s.ex15_8 = gather8(ex0, ex1, k);
+    s.leaf15_8 = gather8(lf0, lf1, k);
+    s.occ15_8 = gather8(oc0, oc1, k);
+    const uint32_t s0_8 = gather8(s00, s01, k), eq_8 = gather8(eq0, eq1, k);
+    s.exists14 = s.ex15_8 != 0;
+    s.s0leaf14 = (s0_8 == 0xffu) && (eq_8 == 0xffu);
+    s.mlc14 = ran14 && !s.s0leaf14 && (s.ex15_8 == 0xffu) && (s.leaf15_8 == 0xffu) && (s.occ15_8 == 0xffu || s.occ15_8 == 0u);
+    s.leaf14 = s.s0leaf14 || s.mlc14;
+    s.occ14 = (s.occ15_8 & 1u) != 0;
+    // brick root: one representative lane per group (lane % 4 == 0) votes
+    const bool rep = (lane & 3u) == 0;
+    const float ref13 = __shfl_sync(0xffffffffu, first[0], 0);
+    auto pick8 = [&](bool p) {   // bit k = predicate of group k
+        const uint32_t b = __ballot_sync(0xffffffffu, rep && p);
+        uint32_t r = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) r |= ((b >> (4 * g)) & 1u) << g;
+        return r;
+    };
+    s.ex14_8 = pick8(s.exists14);
+    s.leaf14_8 = pick8(s.leaf14);
+    s.occ14_8 = pick8(s.occ14);
+    const uint32_t s014_8 = pick8(s.s0leaf14), eq14_8 = pick8(ref14 == ref13);
+    s.s0leaf13 = (s014_8 == 0xffu) && (eq14_8 == 0xffu);
+    s.mlc13 = ran13 && !s.s0leaf13 && (s.ex14_8 == 0xffu) && (s.leaf14_8 == 0xffu) && (s.occ14_8 == 0xffu || s.occ14_8 == 0u);
+    s.leaf13 = s.s0leaf13 || s.mlc13;
+    s.occ13 = (s.occ14_8 & 1u) != 0;
+    s.s0val = ref13;
+}
+
+__device__ __forceinline__ uint32_t group4_sum(uint32_t x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    return x;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ uint16_t child_codes(uint32_t exists8, uint32_t leaf8, uint32_t occ8) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (!((exists8 >> c) & 1u)) continue;
+        const uint32_t code = ((leaf8 >> c) & 1u) ? (((occ8 >> c) & 1u) ? 2u : 1u) : 3u;
+        m |= code << (2 * c);
+    }
+    return (uint16_t)m;
+}
+
+// pass A: how many nodes would the max-likelihood passes at depth 15 / 14 / 13 collapse (assuming each runs)
+__global__ void __launch_bounds__(256) k_bt_count(const float* values, const uint32_t* known, uint32_t n_bricks, float thres,
+                                                  BtCounters* cnt) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t c15 = 0, c14 = 0, c13 = 0;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_bricks; b += warps) {
+        BrickShape s;
+        brick_shape(values + (size_t)b * kBrickVoxels, known + (size_t)b * 16, thres, true, true, true, s);
+        c15 += (s.mlc15[0] ? 1u : 0u) + (s.mlc15[1] ? 1u : 0u);
+        if ((lane & 3u) == 0 && s.mlc14) c14++;
+        if (lane == 0 && s.mlc13) c13++;
+    }
+    c15 = warp_sum(c15); c14 = warp_sum(c14); c13 = warp_sum(c13);
+    if (lane == 0) {
+        if (c15) atomicAdd(&cnt->pruned[15], (unsigned long long)c15);
+        if (c14) atomicAdd(&cnt->pruned[14], (unsigned long long)c14);
+        if (c13) atomicAdd(&cnt->pruned[13], (unsigned long long)c13);
+    }
+}
+
+// pass B: the depth-13 node of every brick, in Morton order
+__global__ void __launch_bounds__(256) k_bt_bricks(const float* values, const uint32_t* known, const uint32_t* order,
+                                                   const uint64_t* sorted_morton, uint32_t n_bricks, float thres, int ran15, int ran14,
+                                                   int ran13, UpNode* out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_bricks; i += warps) {
+        const uint32_t b = order[i];
+        BrickShape s;
+        brick_shape(values + (size_t)b * kBrickVoxels, known + (size_t)b * 16, thres, ran15 != 0, ran14 != 0, ran13 != 0, s);
+        uint32_t nodes15 = 0, inner15 = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!s.exists15[h]) continue;
+            nodes15 += 1u + (s.leaf15[h] ? 0u : (uint32_t)__popc(s.kn[h]));
+            inner15 += s.leaf15[h] ? 0u : 1u;
+        }
+        const uint32_t nodes_g = group4_sum(nodes15), inner_g = group4_sum(inner15);
+        uint32_t nodes14 = 0, inner14 = 0;
+        if ((lane & 3u) == 0 && s.exists14) {
+            nodes14 = 1u + (s.leaf14 ? 0u : nodes_g);
+            inner14 = s.leaf14 ? 0u : 1u + inner_g;
+        }
+        const uint32_t nodes_b = warp_sum(nodes14), inner_b = warp_sum(inner14);
+        if (lane == 0) {
+            UpNode n;
+            n.prefix = sorted_morton[i];
+            n.node_cnt = 1ull + (s.leaf13 ? 0ull : (unsigned long long)nodes_b);
+            n.inner_cnt = s.leaf13 ? 0u : 1u + inner_b;
+            n.offset = ~0ull;
+            n.s0val = s.s0val;
+            n.first_child = b;   // pool index of the brick
+            n.mask = child_codes(s.ex14_8, s.leaf14_8, s.occ14_8);
+            n.flags = (uint8_t)((s.leaf13 ? F_LEAF : 0) | (s.occ13 ? F_OCC : 0) | (s.s0leaf13 ? F_S0 : 0));
+            n.nchild = (uint8_t)__popc(s.ex14_8);
+            out[i] = n;
+        }
+    }
+}
+
+// pass C: bytes of the inner nodes inside every emitted brick
+__global__ void __launch_bounds__(256) k_bt_emit_bricks(const float* values, const uint32_t* known, const UpNode* nodes,
+                                                        uint32_t n_bricks, float thres, int ran15, int ran14, int ran13, uint16_t* out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_bricks; i += warps) {
+        const UpNode nd = nodes[i];
+        if (nd.offset == ~0ull || (nd.flags & F_LEAF)) continue;
+        const uint32_t b = nd.first_child;
+        BrickShape s;
+        brick_shape(values + (size_t)b * kBrickVoxels, known + (size_t)b * 16, thres, ran15 != 0, ran14 != 0, ran13 != 0, s);
+        if (lane == 0) out[nd.offset] = nd.mask;
+        // inner nodes per 14-node subtree (1 + inner 15-children), exclusive prefix over k
+        const uint32_t in15 = ((s.exists15[0] && !s.leaf15[0]) ? 1u : 0u) + ((s.exists15[1] && !s.leaf15[1]) ? 1u : 0u);
+        const uint32_t in15_g = group4_sum(in15);
+        const bool inner14 = s.exists14 && !s.leaf14;
+        const uint32_t sub14 = inner14 ? 1u + in15_g : 0u;       // same in the 4 lanes of the group
+        const uint32_t k = lane >> 2;
+        uint32_t before = 0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t sg = __shfl_sync(0xffffffffu, sub14, 4 * g);
+            if ((uint32_t)g < k) before += sg;
+        }
+        const unsigned long long off14 = nd.offset + 1ull + before;
+        if (inner14 && (lane & 3u) == 0) out[off14] = child_codes(s.ex15_8, s.leaf15_8, s.occ15_8);
+        // inner 15-nodes of this group, in child order c = 2*(lane%4) + h
+        const uint32_t inner_bits = s.ex15_8 & ~s.leaf15_8;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (!(inner14 && s.exists15[h] && !s.leaf15[h])) continue;
+            const uint32_t c = 2u * (lane & 3u) + h;
+            const unsigned long long off15 = off14 + 1ull + __popc(inner_bits & ((1u << c) - 1u));
+            uint32_t m = 0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+                if ((s.kn[h] >> v) & 1u) m |= (((s.oc[h] >> v) & 1u) ? 2u : 1u) << (2 * v);
+            out[off15] = (uint16_t)m;
+        }
+    }
+}
+
+// heads of sibling groups in a sorted level
+__global__ void k_bt_heads(const UpNode* child, uint32_t n, uint32_t* heads) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    heads[i] = (i == 0 || (child[i].prefix >> 3) != (child[i - 1].prefix >> 3)) ? 1u : 0u;
+}
+
+// one parent per sibling group
+__global__ void k_bt_parents(const UpNode* child, uint32_t n, const uint32_t* heads, const uint32_t* incl, UpNode* parent, int depth,
+                             int ran, BtCounters* cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !heads[i]) return;
+    const uint64_t pp = child[i].prefix >> 3;
+    UpNode p;
+    p.prefix = pp;
+    p.first_child = i;
+    p.offset = ~0ull;
+    uint32_t exists8 = 0, leaf8 = 0, occ8 = 0, s08 = 0, eq8 = 0, nch = 0;
+    unsigned long long nodes = 0;
+    uint32_t inner = 0;
+    const float ref = child[i].s0val;
+    for (uint32_t c = i; c < n && (child[c].prefix >> 3) == pp && nch < 8; ++c, ++nch) {
+        const UpNode ch = child[c];
+        const uint32_t ci = (uint32_t)(ch.prefix & 7u);
+        exists8 |= 1u << ci;
+        if (ch.flags & F_LEAF) leaf8 |= 1u << ci;
+        if (ch.flags & F_OCC) occ8 |= 1u << ci;
+        if (ch.flags & F_S0) s08 |= 1u << ci;
+        if (ch.s0val == ref) eq8 |= 1u << ci;
+        nodes += ch.node_cnt;
+        inner += ch.inner_cnt;
+    }
+    const bool s0leaf = (s08 == 0xffu) && (eq8 == 0xffu);
+    const bool mlc = ran && depth > 0 && !s0leaf && exists8 == 0xffu && leaf8 == 0xffu && (occ8 == 0xffu || occ8 == 0u);
+    const bool leaf = s0leaf || mlc;
+    if (mlc) atomicAdd(&cnt->pruned[depth], 1ull);
+    const bool occ = leaf ? ((occ8 >> (child[i].prefix & 7u)) & 1u) != 0 : occ8 != 0;
+    p.flags = (uint8_t)((leaf ? F_LEAF : 0) | (occ ? F_OCC : 0) | (s0leaf ? F_S0 : 0));
+    p.s0val = ref;
+    p.nchild = (uint8_t)nch;
+    p.node_cnt = 1ull + (leaf ? 0ull : nodes);
+    p.inner_cnt = leaf ? 0u : 1u + inner;
+    p.mask = child_codes(exists8, leaf8, occ8);
+    parent[incl[i] - 1] = p;
+}
+
+// pre-order offsets of the children of every emitted inner node
+__global__ void k_bt_offsets(const UpNode* parent, uint32_t n_parent, UpNode* child, uint16_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_parent) return;
+    const UpNode p = parent[i];
+    if (p.offset == ~0ull || (p.flags & F_LEAF)) return;
+    out[p.offset] = p.mask;
+    unsigned long long run = p.offset + 1ull;
+    for (uint32_t c = 0; c < p.nchild; ++c) {
+        UpNode& ch = child[p.first_child + c];
+        if (!(ch.flags & F_LEAF)) { ch.offset = run; run += ch.inner_cnt; }
+    }
+}
+
+__global__ void k_bt_morton(const uint64_t* pool_keys, uint32_t n, uint64_t* morton, uint32_t* idx) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    morton[i] = brick_morton(pool_keys[i]);
+    idx[i] = i;
+}
+
+__global__ void k_bt_set_root_offset(UpNode* root) { root->offset = 0; }
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+};
+
+static unsigned blocks_for(uint64_t n, int block = 256) { return (unsigned)((n + block - 1) / block > 0 ? (n + block - 1) / block : 1); }
+
+// Derives the tree shape.  ml = false: value-pruned shape only (size()).  payload may be null.
+static int tree_shape(r3d_tree* t, bool ml, uint64_t* n_nodes, std::vector<uint8_t>* payload) {
+    r3d_ctx* ctx = t->ctx;
+    *n_nodes = 0;
+    if (payload) payload->clear();
+    const uint32_t nb = t->pool_used;
+    if (nb == 0) return R3D_OK;
+    R3D_TRY(tree_refresh_pool_keys(t));
+    cudaStream_t st = ctx->stream;
+    DevBuf morton_in, morton_out, idx_in, idx_out, cub_tmp, counters, heads, incl;
+    R3D_CUDA_OK(ctx, morton_in.alloc((size_t)nb * 8));
+    R3D_CUDA_OK(ctx, morton_out.alloc((size_t)nb * 8));
+    R3D_CUDA_OK(ctx, idx_in.alloc((size_t)nb * 4));
+    R3D_CUDA_OK(ctx, idx_out.alloc((size_t)nb * 4));
+    R3D_CUDA_OK(ctx, counters.alloc(sizeof(BtCounters)));
+    R3D_CUDA_OK(ctx, heads.alloc((size_t)nb * 4));
+    R3D_CUDA_OK(ctx, incl.alloc((size_t)nb * 4));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(counters.p, 0, sizeof(BtCounters), st));
+    k_bt_morton<<<blocks_for(nb), 256, 0, st>>>(t->pool_keys, nb, morton_in.as<uint64_t>(), idx_in.as<uint32_t>());
+    ctx->launches++;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, morton_in.as<uint64_t>(), morton_out.as<uint64_t>(), idx_in.as<uint32_t>(),
+                                    idx_out.as<uint32_t>(), (int)nb, 0, 39, st);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, heads.as<uint32_t>(), incl.as<uint32_t>(), (int)nb, st);
+    R3D_CUDA_OK(ctx, cub_tmp.alloc((tmp_sort > tmp_scan ? tmp_sort : tmp_scan) + 256));
+    R3D_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_sort, morton_in.as<uint64_t>(), morton_out.as<uint64_t>(),
+                                                     idx_in.as<uint32_t>(), idx_out.as<uint32_t>(), (int)nb, 0, 39, st));
+    ctx->launches++;
+
+    const float thres = ml ? t->occ_thres : 0.f;
+    BtCounters hc;
+    memset(&hc, 0, sizeof hc);
+    bool ran[17] = {false};
+    const unsigned brick_grid = blocks_for((uint64_t)nb * 32) < (unsigned)ctx->sm_count * 8 ? blocks_for((uint64_t)nb * 32) : (unsigned)ctx->sm_count * 8;
+    if (ml) {
+        k_bt_count<<<brick_grid, 256, 0, st>>>(t->values, t->known, nb, thres, counters.as<BtCounters>());
+        ctx->launches++;
+        R3D_CUDA_OK(ctx, cudaMemcpyAsync(&hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        ran[15] = true;
+        ran[14] = hc.pruned[15] > 0;
+        ran[13] = ran[14] && hc.pruned[14] > 0;
+        ran[12] = ran[13] && hc.pruned[13] > 0;
+    }
+    // levels 13 .. 0
+    std::vector<DevBuf> level(14);
+    std::vector<uint32_t> count(14, 0);
+    count[13] = nb;
+    R3D_CUDA_OK(ctx, level[13].alloc((size_t)nb * sizeof(UpNode)));
+    if (ml) {
+        k_bt_bricks<<<brick_grid, 256, 0, st>>>(t->values, t->known, idx_out.as<uint32_t>(), morton_out.as<uint64_t>(), nb, thres, 1,
+                                                ran[14] ? 1 : 0, ran[13] ? 1 : 0, level[13].as<UpNode>());
+    } else {
+        // size(): exact-equality leaves only, no max-likelihood pass at any depth
+        k_bt_bricks<<<brick_grid, 256, 0, st>>>(t->values, t->known, idx_out.as<uint32_t>(), morton_out.as<uint64_t>(), nb, thres, 0, 0, 0,
+                                                level[13].as<UpNode>());
+    }
+    ctx->launches++;
+    for (int d = 12; d >= 0; --d) {
+        const uint32_t nc = count[d + 1];
+        k_bt_heads<<<blocks_for(nc), 256, 0, st>>>(level[d + 1].as<UpNode>(), nc, heads.as<uint32_t>());
+        R3D_CUDA_OK(ctx, cub::DeviceScan::InclusiveSum(cub_tmp.p, tmp_scan, heads.as<uint32_t>(), incl.as<uint32_t>(), (int)nc, st));
+        uint32_t np = 0;
+        R3D_CUDA_OK(ctx, cudaMemcpyAsync(&np, incl.as<uint32_t>() + (nc - 1), 4, cudaMemcpyDeviceToHost, st));
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        count[d] = np;
+        R3D_CUDA_OK(ctx, level[d].alloc((size_t)np * sizeof(UpNode)));
+        k_bt_parents<<<blocks_for(nc), 256, 0, st>>>(level[d + 1].as<UpNode>(), nc, heads.as<uint32_t>(), incl.as<uint32_t>(),
+                                                     level[d].as<UpNode>(), d, ran[d] ? 1 : 0, counters.as<BtCounters>());
+        ctx->launches += 3;
+        if (ml && d > 0) {
+            R3D_CUDA_OK(ctx, cudaMemcpyAsync(&hc, counters.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+            R3D_CUDA_OK(ctx, cudaStreamSynchronize(st));
+            ran[d - 1] = ran[d] && hc.pruned[d] > 0;
+        }
+    }
+    if (count[0] != 1) return set_error(ctx, R3D_ERR_STATE, "tree shape: %u roots", count[0]);
+    UpNode root;
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(&root, level[0].p, sizeof root, cudaMemcpyDeviceToHost, st));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    *n_nodes = root.node_cnt;
+    if (!payload) return R3D_OK;
+    if (root.flags & F_LEAF) {   // a fully collapsed root still writes its (empty) child bytes
+        payload->assign(2, 0);
+        return R3D_OK;
+    }
+    const uint64_t n_inner = root.inner_cnt;
+    DevBuf out;
+    R3D_CUDA_OK(ctx, out.alloc((size_t)n_inner * 2));
+    k_bt_set_root_offset<<<1, 1, 0, st>>>(level[0].as<UpNode>());
+    for (int d = 0; d <= 12; ++d) {
+        k_bt_offsets<<<blocks_for(count[d]), 256, 0, st>>>(level[d].as<UpNode>(), count[d], level[d + 1].as<UpNode>(), out.as<uint16_t>());
+        ctx->launches++;
+    }
+    k_bt_emit_bricks<<<brick_grid, 256, 0, st>>>(t->values, t->known, level[13].as<UpNode>(), nb, thres, ml ? 1 : 0, ran[14] ? 1 : 0,
+                                                 ran[13] ? 1 : 0, out.as<uint16_t>());
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    payload->resize((size_t)n_inner * 2);
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(payload->data(), out.p, (size_t)n_inner * 2, cudaMemcpyDeviceToHost, st));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return R3D_OK;
+}
+
+static std::string bt_header(uint64_t n_nodes, double res) {
+    char buf[512];
+    snprintf(buf, sizeof buf,
+             "# Octomap OcTree binary file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n"
+             "id OcTree\nsize %llu\nres %g\ndata\n",
+             (unsigned long long)n_nodes, res);
+    return std::string(buf);
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" int r3d_tree_size(r3d_tree* t, uint64_t* n_nodes) {
+    if (!t || !n_nodes) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    DeviceSetter ds(t->ctx->device);
+    return tree_shape(t, false, n_nodes, nullptr);
+}
+
+extern "C" int r3d_tree_write_bt_mem(r3d_tree* t, uint8_t* buf, size_t cap, size_t* len) {
+    if (!t || !len) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    DeviceSetter ds(t->ctx->device);
+    uint64_t n_nodes = 0;
+    std::vector<uint8_t> payload;
+    R3D_TRY(tree_shape(t, true, &n_nodes, &payload));
+    const std::string hdr = bt_header(n_nodes, t->res);
+    *len = hdr.size() + payload.size();
+    if (buf && cap >= *len) {
+        memcpy(buf, hdr.data(), hdr.size());
+        if (!payload.empty()) memcpy(buf + hdr.size(), payload.data(), payload.size());
+    }
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_write_bt(r3d_tree* t, const char* path) {
+    if (!t || !path) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    DeviceSetter ds(t->ctx->device);
+    uint64_t n_nodes = 0;
+    std::vector<uint8_t> payload;
+    R3D_TRY(tree_shape(t, true, &n_nodes, &payload));
+    const std::string hdr = bt_header(n_nodes, t->res);
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_error(t->ctx, R3D_ERR_IO, "cannot open %s for writing", path);
+    bool ok = fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size();
+    if (ok && !payload.empty()) ok = fwrite(payload.data(), 1, payload.size(), f) == payload.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return set_error(t->ctx, R3D_ERR_IO, "short write to %s", path);
+    return R3D_OK;
+}

@@ -1,26 +1,820 @@
-// r3d_octree.cu -- occupancy entry points (placeholder bodies until the brick store lands).
-#include "r3d_common.cuh"
+// r3d_octree.cu -- occupancy half of the path: OcTree(res), updateNode, insertPointCloud, writeBinary.
+//
+// Replaces the un-vendored `octomap` extension the reference imports (octomap/txt_transfer_octomap.py:2,25,33-36;
+// octomap/ply_transfer_octomap.py:2,33,45-48).  Data layout in HBM:
+//
+//   * the map is a flat voxel store, not a pointer tree: a depth-16 OcTreeKey (3 x uint16) is split into a BRICK
+//     (key >> 3 per axis: the depth-13 node) and a 9-bit Morton voxel index inside it.  Bricks live in a pool
+//     (512 float32 log-odds + 512 "known" bits each) addressed through an open-addressing hash table
+//     brick key -> pool index.  Leaf log-odds of the flat store equal the leaf log-odds of upstream's tree
+//     (update-time pruning / expansion never changes a leaf value); the tree shape needed for .bt and size() is
+//     derived from the values on demand (r3d_bt.cu).
+//   * one scan's update (insertPointCloud) is a DELTA: a per-scan scratch hash table of bricks, each with a
+//     512-bit occupied mask and a 512-bit free mask, filled by the ray-casting kernel (K3) with atomicOr, then
+//     compacted to 136-byte records and applied to the store by the clamped log-odds kernel (K4).  Records are
+//     what multi-GPU runs exchange.
+#include "r3d_octree.cuh"
+
+namespace r3d {
+
+// ------------------------------------------------------------------ hash table primitives
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t* p) { return __ldcg(reinterpret_cast<const unsigned long long*>(p)); }
+
+// find-or-insert of a brick key; returns the slot, or kNoSlot when the table is full
+__device__ __forceinline__ uint64_t table_find_or_insert(uint64_t* keys, uint64_t cap, uint64_t bk, bool& inserted) {
+    const uint64_t mask = cap - 1;
+    uint64_t slot = hash64(bk) & mask;
+    inserted = false;
+    for (uint64_t probe = 0; probe < cap; ++probe) {
+        const uint64_t k = ld_cg_u64(keys + slot);
+        if (k == bk) return slot;
+        if (k == kEmptyKey) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(keys + slot), kEmptyKey, bk);
+            if (old == kEmptyKey) { inserted = true; return slot; }
+            if (old == bk) return slot;
+        }
+        slot = (slot + 1) & mask;
+    }
+    return kNoSlot;
+}
+__device__ __forceinline__ uint64_t table_find(const uint64_t* keys, uint64_t cap, uint64_t bk) {
+    const uint64_t mask = cap - 1;
+    uint64_t slot = hash64(bk) & mask;
+    for (uint64_t probe = 0; probe < cap; ++probe) {
+        const uint64_t k = ld_cg_u64(keys + slot);
+        if (k == bk) return slot;
+        if (k == kEmptyKey) return kNoSlot;
+        slot = (slot + 1) & mask;
+    }
+    return kNoSlot;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_point(const T* xyz, unsigned long long i, float& x, float& y, float& z) {
+    x = (float)xyz[3 * i]; y = (float)xyz[3 * i + 1]; z = (float)xyz[3 * i + 2];   // binding: point3d(float) cast
+}
+
+// ------------------------------------------------------------------ updateNode(point, ...) batches (a10)
+// pass 1: make sure every touched brick exists in the table and has a pool index
+template <typename T>
+__global__ void k_points_ensure(const T* __restrict__ xyz, unsigned long long n, double res_factor, uint64_t* tkeys,
+                                uint32_t* tvals, uint64_t tcap, uint32_t* counters) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float x, y, z;
+        load_point(xyz, i, x, y, z);
+        uint16_t kx, ky, kz;
+        if (!coord_to_key3(res_factor, x, y, z, kx, ky, kz)) { atomicAdd(&counters[CNT_DROPPED], 1u); continue; }
+        bool inserted;
+        const uint64_t slot = table_find_or_insert(tkeys, tcap, brick_key(kx, ky, kz), inserted);
+        if (slot == kNoSlot) { counters[CNT_OVERFLOW] = 1; continue; }
+        if (inserted) tvals[slot] = atomicAdd(&counters[CNT_POOL_USED], 1u);
+    }
+}
+
+// pass 2: clamped log-odds update; equal (brick, voxel) targets inside a warp are merged so that one lane applies
+// the update count times (the update function is the same for every point of the batch, so order is immaterial)
+template <typename T>
+__global__ void k_points_update(const T* __restrict__ xyz, unsigned long long n, double res_factor, const uint64_t* tkeys,
+                                const uint32_t* tvals, uint64_t tcap, float* values, uint32_t* known, float upd, float cmin,
+                                float cmax) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n_pad = (n + 31ull) & ~31ull;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        unsigned long long target = 0xffffffffffffff00ull + lane;   // unique per lane when invalid
+        bool valid = false;
+        if (i < n) {
+            float x, y, z;
+            load_point(xyz, i, x, y, z);
+            uint16_t kx, ky, kz;
+            if (coord_to_key3(res_factor, x, y, z, kx, ky, kz)) {
+                const uint64_t slot = table_find(tkeys, tcap, brick_key(kx, ky, kz));
+                if (slot != kNoSlot) {
+                    target = (unsigned long long)tvals[slot] * kBrickVoxels + brick_voxel_index(kx, ky, kz);
+                    valid = true;
+                }
+            }
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, target);
+        if (valid && lane == (unsigned)(__ffs(peers) - 1)) {
+            const int count = __popc(peers);
+            int* p = reinterpret_cast<int*>(values + target);
+            int old = *reinterpret_cast<volatile int*>(p);
+            for (;;) {
+                float v = __int_as_float(old);
+                for (int c = 0; c < count; ++c) {
+                    const float nv = clamped_add(v, upd, cmin, cmax);
+                    if (nv == v) break;   // saturated (upstream's early abort) or zero update
+                    v = nv;
+                }
+                if (__float_as_int(v) == old) break;
+                const int prev = atomicCAS(p, old, __float_as_int(v));
+                if (prev == old) break;
+                old = prev;
+            }
+            const unsigned vox = (unsigned)(target % kBrickVoxels);
+            uint32_t* kw = known + (target / kBrickVoxels) * 16 + (vox >> 5);
+            const uint32_t bit = 1u << (vox & 31u);
+            if (!(*reinterpret_cast<volatile uint32_t*>(kw) & bit)) atomicOr(kw, bit);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K3: per-scan ray casting into the delta table
+struct ScanArgs {
+    const float* xyz;
+    unsigned long long n;
+    float ox, oy, oz;
+    double maxrange, res, res_factor;
+    uint64_t* skeys;
+    uint32_t* smasks;   // per slot: 16 words occupied, 16 words free
+    uint64_t scap;
+    uint32_t* counters;
+};
+
+struct BrickCursor {
+    uint64_t bk = kEmptyKey;
+    uint64_t slot = kNoSlot;
+};
+
+__device__ __forceinline__ void delta_mark(const ScanArgs& a, int kx, int ky, int kz, int plane, BrickCursor& cur) {
+    const uint64_t bk = brick_key((uint32_t)kx, (uint32_t)ky, (uint32_t)kz);
+    if (bk != cur.bk) {
+        bool inserted;
+        cur.bk = bk;
+        cur.slot = table_find_or_insert(a.skeys, a.scap, bk, inserted);
+        if (inserted && atomicAdd(&a.counters[CNT_SCRATCH_USED], 1u) + 1u > (uint32_t)(a.scap / 2)) a.counters[CNT_OVERFLOW] = 1;
+        if (cur.slot == kNoSlot) a.counters[CNT_OVERFLOW] = 1;
+    }
+    if (cur.slot == kNoSlot) return;
+    const unsigned vox = brick_voxel_index((uint32_t)kx, (uint32_t)ky, (uint32_t)kz);
+    uint32_t* w = a.smasks + cur.slot * 32 + plane * 16 + (vox >> 5);
+    const uint32_t bit = 1u << (vox & 31u);
+    if (!(*w & bit)) atomicOr(w, bit);   // a stale (cached) 0 only costs a redundant atomic
+}
+
+// computeUpdate (OccupancyOcTreeBase): per point, free cells along the ray, endpoint occupied when in range
+__global__ void __launch_bounds__(256) k_scan_raycast(const ScanArgs a) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
+        float ex, ey, ez;
+        const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, ex, ey, ez);
+        BrickCursor occ_cur, free_cur;
+        if (in_range) {
+            uint16_t kx, ky, kz;
+            if (coord_to_key3(a.res_factor, px, py, pz, kx, ky, kz)) delta_mark(a, kx, ky, kz, 0, occ_cur);
+        }
+        Ray r;
+        if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, ex, ey, ez, r) == 1) {
+            delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur);
+            while (ray_step(r)) delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur);
+        }
+    }
+}
+
+// computeDiscreteUpdate's pre-pass: keep one voxel-centre point per distinct endpoint key
+__global__ void k_scan_discretize(const ScanArgs a, float* out_xyz) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        uint16_t kx, ky, kz;
+        if (!coord_to_key3(a.res_factor, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2], kx, ky, kz)) continue;
+        bool inserted;
+        const uint64_t slot = table_find_or_insert(a.skeys, a.scap, brick_key(kx, ky, kz), inserted);
+        if (slot == kNoSlot) { a.counters[CNT_OVERFLOW] = 1; continue; }
+        if (inserted && atomicAdd(&a.counters[CNT_SCRATCH_USED], 1u) + 1u > (uint32_t)(a.scap / 2)) a.counters[CNT_OVERFLOW] = 1;
+        const unsigned vox = brick_voxel_index(kx, ky, kz);
+        const uint32_t bit = 1u << (vox & 31u);
+        const uint32_t old = atomicOr(a.smasks + slot * 32 + (vox >> 5), bit);
+        if (!(old & bit)) {
+            const uint32_t q = atomicAdd(&a.counters[CNT_DISCRETE], 1u);
+            out_xyz[3 * q + 0] = (float)key_to_coord(a.res, kx);
+            out_xyz[3 * q + 1] = (float)key_to_coord(a.res, ky);
+            out_xyz[3 * q + 2] = (float)key_to_coord(a.res, kz);
+        }
+    }
+}
+
+// scratch table -> compact records (free already minus occupied); resets the slots it consumes.  One warp per slot.
+__global__ void __launch_bounds__(256) k_scan_compact(uint64_t* skeys, uint32_t* smasks, uint64_t scap, DeltaRecord* out,
+                                                      uint32_t* counters, uint32_t out_cap) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < scap; s += warps) {
+        const uint64_t k = skeys[s];
+        if (k == kEmptyKey) continue;
+        uint32_t w = smasks[s * 32 + lane];
+        const uint32_t occ_w = __shfl_sync(0xffffffffu, w, lane & 15u);
+        if (lane >= 16) w &= ~occ_w;   // occupied wins
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(&counters[CNT_DELTA], 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q < out_cap) {
+            if (lane == 0) out[q].key = k;
+            out[q].mask[lane] = w;
+        }
+        smasks[s * 32 + lane] = 0;
+        if (lane == 0) skeys[s] = kEmptyKey;
+    }
+}
+
+// ------------------------------------------------------------------ K4: clamped log-odds apply of one scan's delta
+// One warp per record.  Every brick appears once per delta, so the warp owns the brick's values for this launch.
+__global__ void __launch_bounds__(256) k_apply_delta(const DeltaRecord* __restrict__ recs, uint32_t n, uint64_t* tkeys,
+                                                     uint32_t* tvals, uint64_t tcap, float* values, uint32_t* known,
+                                                     uint32_t* counters, float hit, float miss, float cmin, float cmax) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        uint32_t idx = 0;
+        if (lane == 0) {
+            bool inserted;
+            const uint64_t slot = table_find_or_insert(tkeys, tcap, recs[r].key, inserted);
+            if (slot == kNoSlot) { counters[CNT_OVERFLOW] = 1; idx = 0xffffffffu; }
+            else if (inserted) { idx = atomicAdd(&counters[CNT_POOL_USED], 1u); tvals[slot] = idx; }
+            else idx = tvals[slot];
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx == 0xffffffffu) continue;
+        // lane handles voxels [16*lane, 16*lane+16): half of mask word lane/2
+        const uint32_t sh = (lane & 1u) * 16u;
+        const uint32_t occ = (recs[r].mask[lane >> 1] >> sh) & 0xffffu;
+        const uint32_t fre = (recs[r].mask[16 + (lane >> 1)] >> sh) & 0xffffu;
+        const uint32_t any = occ | fre;
+        if (any) {
+            float4* v4 = reinterpret_cast<float4*>(values + (size_t)idx * kBrickVoxels + lane * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t m = (any >> (4 * q)) & 0xfu;
+                if (!m) continue;
+                float4 v = v4[q];
+                float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t bit = 1u << (4 * q + b);
+                    if (occ & bit) e[b] = clamped_add(e[b], hit, cmin, cmax);
+                    else if (fre & bit) e[b] = clamped_add(e[b], miss, cmin, cmax);
+                }
+                v4[q] = v;
+            }
+        }
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, any, 1);
+        if (!(lane & 1u)) {
+            const uint32_t word = any | (other << 16);
+            if (word) known[(size_t)idx * 16 + (lane >> 1)] |= word;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ queries
+__global__ void k_search(const uint16_t* __restrict__ keys, unsigned long long n, const uint64_t* tkeys, const uint32_t* tvals,
+                         uint64_t tcap, const float* values, const uint32_t* known, float* out_v, uint8_t* out_f) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t kx = keys[3 * i], ky = keys[3 * i + 1], kz = keys[3 * i + 2];
+        const uint64_t slot = table_find(tkeys, tcap, brick_key(kx, ky, kz));
+        float v = 0.f;
+        uint8_t f = 0;
+        if (slot != kNoSlot) {
+            const uint32_t idx = tvals[slot];
+            const unsigned vox = brick_voxel_index(kx, ky, kz);
+            if (known[(size_t)idx * 16 + (vox >> 5)] & (1u << (vox & 31u))) { f = 1; v = values[(size_t)idx * kBrickVoxels + vox]; }
+        }
+        if (out_v) out_v[i] = v;
+        if (out_f) out_f[i] = f;
+    }
+}
+
+__global__ void k_coord_to_key(const float* __restrict__ xyz, unsigned long long n, double res_factor, uint16_t* keys, uint8_t* valid) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint16_t kx = 0, ky = 0, kz = 0;
+        const bool ok = coord_to_key3(res_factor, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], kx, ky, kz);
+        keys[3 * i] = kx; keys[3 * i + 1] = ky; keys[3 * i + 2] = kz;
+        if (valid) valid[i] = ok ? 1 : 0;
+    }
+}
+
+// table -> pool_keys[pool index] = brick key
+__global__ void k_table_to_pool_keys(const uint64_t* tkeys, const uint32_t* tvals, uint64_t tcap, uint64_t* pool_keys) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < tcap; s += stride) {
+        const uint64_t k = tkeys[s];
+        if (k != kEmptyKey) pool_keys[tvals[s]] = k;
+    }
+}
+
+__global__ void k_rehash(const uint64_t* okeys, const uint32_t* ovals, uint64_t ocap, uint64_t* nkeys, uint32_t* nvals, uint64_t ncap) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < ocap; s += stride) {
+        const uint64_t k = okeys[s];
+        if (k == kEmptyKey) continue;
+        bool inserted;
+        const uint64_t slot = table_find_or_insert(nkeys, ncap, k, inserted);
+        nvals[slot] = ovals[s];
+    }
+}
+
+__global__ void k_count_known(const uint32_t* known, uint64_t n_words, unsigned long long* out) {
+    unsigned long long c = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) c += __popc(known[i]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(out, c);
+}
+
+// every known voxel -> (key, value); order unspecified
+__global__ void k_export_voxels(const uint64_t* pool_keys, const float* values, const uint32_t* known, uint32_t n_bricks,
+                                uint16_t* out_keys, float* out_vals, unsigned long long cap, unsigned long long* counter) {
+    const uint64_t total = (uint64_t)n_bricks * kBrickVoxels;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t b = (uint32_t)(i / kBrickVoxels), vox = (uint32_t)(i % kBrickVoxels);
+        if (!(known[(size_t)b * 16 + (vox >> 5)] & (1u << (vox & 31u)))) continue;
+        const unsigned long long q = atomicAdd(counter, 1ull);
+        if (q >= cap) continue;
+        uint32_t bx, by, bz, x, y, z;
+        brick_key_unpack(pool_keys[b], bx, by, bz);
+        brick_voxel_coords(vox, x, y, z);
+        if (out_keys) { out_keys[3 * q] = (uint16_t)(bx * 8 + x); out_keys[3 * q + 1] = (uint16_t)(by * 8 + y); out_keys[3 * q + 2] = (uint16_t)(bz * 8 + z); }
+        if (out_vals) out_vals[q] = values[i];
+    }
+}
+
+__global__ void k_to_max_likelihood(float* values, const uint32_t* known, uint64_t total, float thres, float cmin, float cmax) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const uint32_t vox = (uint32_t)(i % kBrickVoxels);
+        if (known[(i / kBrickVoxels) * 16 + (vox >> 5)] & (1u << (vox & 31u))) values[i] = values[i] >= thres ? cmax : cmin;
+    }
+}
+
+// ------------------------------------------------------------------ host side: memory management
+static unsigned grid_for(r3d_ctx* ctx, unsigned long long items, int block = 256, int per_sm = 8) {
+    unsigned long long b = (items + block - 1) / block;
+    const unsigned long long cap = (unsigned long long)ctx->sm_count * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+int tree_sync_counters(r3d_tree* t) {
+    r3d_ctx* ctx = t->ctx;
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, t->counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(t->h_counters, ctx->pinned, CNT_COUNT * sizeof(uint32_t));
+    return R3D_OK;
+}
+
+static int tree_set_counter(r3d_tree* t, int which, uint32_t v) {
+    r3d_ctx* ctx = t->ctx;
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(t->counters + which, &v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
+    // v lives on the stack: the copy of 4 pageable bytes is staged before the call returns
+    return R3D_OK;
+}
+
+// hash table with at least `want_entries` * 2 slots
+static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
+    r3d_ctx* ctx = t->ctx;
+    uint64_t need = 1024;
+    while (need < want_entries * 2) need <<= 1;
+    if (need <= t->tcap) return R3D_OK;
+    uint64_t* nk = nullptr;
+    uint32_t* nv = nullptr;
+    R3D_CUDA_OK(ctx, cudaMalloc(&nk, need * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&nv, need * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(nk); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(hash values) failed: %s", cudaGetErrorString(e)); }
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(nk, 0xff, need * sizeof(uint64_t), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(nv, 0, need * sizeof(uint32_t), ctx->stream));
+    if (t->tcap) {
+        k_rehash<<<grid_for(ctx, t->tcap), 256, 0, ctx->stream>>>(t->tkeys, t->tvals, t->tcap, nk, nv, need);
+        ctx->launches++;
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(t->tkeys);
+        cudaFree(t->tvals);
+    }
+    t->tkeys = nk; t->tvals = nv; t->tcap = need;
+    return R3D_OK;
+}
+
+// brick pool with room for `want` bricks; new bricks are zero (log-odds 0 = a freshly created node, nothing known)
+static int tree_reserve_pool(r3d_tree* t, uint64_t want) {
+    r3d_ctx* ctx = t->ctx;
+    if (want <= t->pool_cap) return R3D_OK;
+    uint64_t ncap = t->pool_cap ? t->pool_cap : 1024;
+    while (ncap < want) ncap += ncap / 2 + 1024;
+    if (ncap > 0xfffffff0ull) return set_error(ctx, R3D_ERR_OOM, "brick pool would exceed 2^32 bricks");
+    float* nv = nullptr;
+    uint32_t* nk = nullptr;
+    cudaError_t e = cudaMalloc(&nv, ncap * kBrickVoxels * sizeof(float));
+    if (e != cudaSuccess) return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(%llu bricks of log-odds) failed: %s", (unsigned long long)ncap, cudaGetErrorString(e));
+    e = cudaMalloc(&nk, ncap * 16 * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(nv); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(known masks) failed: %s", cudaGetErrorString(e)); }
+    const uint64_t used = t->pool_cap;   // everything below the old capacity may hold data
+    if (used) {
+        R3D_CUDA_OK(ctx, cudaMemcpyAsync(nv, t->values, used * kBrickVoxels * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        R3D_CUDA_OK(ctx, cudaMemcpyAsync(nk, t->known, used * 16 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(nv + used * kBrickVoxels, 0, (ncap - used) * kBrickVoxels * sizeof(float), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(nk + used * 16, 0, (ncap - used) * 16 * sizeof(uint32_t), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(t->values);
+    cudaFree(t->known);
+    t->values = nv; t->known = nk; t->pool_cap = ncap;
+    return R3D_OK;
+}
+
+static int tree_reserve_scratch(r3d_tree* t, uint64_t want_slots) {
+    r3d_ctx* ctx = t->ctx;
+    uint64_t need = 1ull << 17;
+    while (need < want_slots) need <<= 1;
+    if (need <= t->scap) return R3D_OK;
+    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta);
+    t->skeys = nullptr; t->smasks = nullptr; t->delta = nullptr; t->scap = 0;
+    R3D_CUDA_OK(ctx, cudaMalloc(&t->skeys, need * sizeof(uint64_t)));
+    R3D_CUDA_OK(ctx, cudaMalloc(&t->smasks, need * 32 * sizeof(uint32_t)));
+    R3D_CUDA_OK(ctx, cudaMalloc(&t->delta, (need / 2 + 1) * sizeof(DeltaRecord)));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->skeys, 0xff, need * sizeof(uint64_t), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->smasks, 0, need * 32 * sizeof(uint32_t), ctx->stream));
+    t->scap = need;
+    t->delta_cap = need / 2 + 1;
+    return R3D_OK;
+}
+
+static int tree_reset_scratch(r3d_tree* t) {
+    r3d_ctx* ctx = t->ctx;
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->skeys, 0xff, t->scap * sizeof(uint64_t), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->smasks, 0, t->scap * 32 * sizeof(uint32_t), ctx->stream));
+    return R3D_OK;
+}
+
+// device copy of a host array (or the pointer itself when it already is device memory)
+template <typename T>
+static int stage_in(r3d_ctx* ctx, int slot, const T* p, size_t count, const T** out) {
+    if (is_device_ptr(p)) { *out = p; return R3D_OK; }
+    R3D_TRY(scratch_reserve(ctx, slot, count * sizeof(T) + 16));
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(ctx->scratch[slot], p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *out = reinterpret_cast<const T*>(ctx->scratch[slot]);
+    return R3D_OK;
+}
+
+int tree_refresh_pool_keys(r3d_tree* t) {
+    r3d_ctx* ctx = t->ctx;
+    if (t->pool_keys_cap < t->pool_cap) {
+        cudaFree(t->pool_keys);
+        t->pool_keys = nullptr;
+        R3D_CUDA_OK(ctx, cudaMalloc(&t->pool_keys, (t->pool_cap + 1) * sizeof(uint64_t)));
+        t->pool_keys_cap = t->pool_cap;
+    }
+    if (t->tcap) {
+        k_table_to_pool_keys<<<grid_for(ctx, t->tcap), 256, 0, ctx->stream>>>(t->tkeys, t->tvals, t->tcap, t->pool_keys);
+        ctx->launches++;
+    }
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    return R3D_OK;
+}
+
+template <typename T>
+static int update_points_impl(r3d_tree* t, const T* xyz, uint64_t n, float upd, uint64_t* n_dropped) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (!xyz && n) return set_error(ctx, R3D_ERR_ARG, "null points");
+    DeviceSetter ds(ctx->device);
+    uint64_t dropped_total = 0;
+    const uint64_t chunk = 1ull << 22;
+    const bool dev = n ? is_device_ptr(xyz) : true;
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint64_t m = (n - off < chunk) ? n - off : chunk;
+        const T* d = xyz + off * 3;
+        if (!dev) R3D_TRY(stage_in(ctx, SCR_IN0, xyz + off * 3, (size_t)m * 3, &d));
+        R3D_TRY(tree_reserve_table(t, (uint64_t)t->pool_used + m));
+        R3D_TRY(tree_set_counter(t, CNT_DROPPED, 0));
+        R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
+        k_points_ensure<T><<<grid_for(ctx, m), 256, 0, ctx->stream>>>(d, m, t->res_factor, t->tkeys, t->tvals, t->tcap, t->counters);
+        ctx->launches++;
+        R3D_TRY(tree_sync_counters(t));
+        if (t->h_counters[CNT_OVERFLOW]) return set_error(ctx, R3D_ERR_STATE, "brick table overflow (internal sizing error)");
+        t->pool_used = t->h_counters[CNT_POOL_USED];
+        dropped_total += t->h_counters[CNT_DROPPED];
+        R3D_TRY(tree_reserve_pool(t, t->pool_used));
+        k_points_update<T><<<grid_for(ctx, m), 256, 0, ctx->stream>>>(d, m, t->res_factor, t->tkeys, t->tvals, t->tcap, t->values,
+                                                                     t->known, upd, t->cmin, t->cmax);
+        ctx->launches++;
+        R3D_CUDA_OK(ctx, cudaGetLastError());
+        if (!dev) R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // staging buffer is reused by the next chunk
+    }
+    if (n_dropped) *n_dropped = dropped_total;
+    return finish(ctx);
+}
+
+// ray-cast one scan into the scratch table and compact it into t->delta (t->delta_n records)
+static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const float origin[3], double maxrange, int discretize) {
+    r3d_ctx* ctx = t->ctx;
+    if ((!xyz && n) || !origin) return set_error(ctx, R3D_ERR_ARG, "null scan buffer");
+    if (n > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "scan too large");
+    const float* d = xyz;
+    if (n) R3D_TRY(stage_in(ctx, SCR_IN0, xyz, (size_t)n * 3, &d));
+    R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        ScanArgs a;
+        a.xyz = d; a.n = n;
+        a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
+        a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
+        a.skeys = t->skeys; a.smasks = t->smasks; a.scap = t->scap; a.counters = t->counters;
+        R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
+        R3D_TRY(tree_set_counter(t, CNT_SCRATCH_USED, 0));
+        R3D_TRY(tree_set_counter(t, CNT_DELTA, 0));
+        R3D_TRY(tree_set_counter(t, CNT_DISCRETE, 0));
+        bool overflow = false;
+        if (discretize && n) {
+            R3D_TRY(scratch_reserve(ctx, SCR_IN1, (size_t)n * 12 + 16));
+            k_scan_discretize<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(a, (float*)ctx->scratch[SCR_IN1]);
+            ctx->launches++;
+            R3D_TRY(tree_sync_counters(t));
+            overflow = t->h_counters[CNT_OVERFLOW] != 0;
+            R3D_TRY(tree_reset_scratch(t));
+            R3D_TRY(tree_set_counter(t, CNT_SCRATCH_USED, 0));
+            a.xyz = (const float*)ctx->scratch[SCR_IN1];
+            a.n = t->h_counters[CNT_DISCRETE];
+        }
+        if (!overflow && a.n) {
+            k_scan_raycast<<<grid_for(ctx, a.n, 256, 8), 256, 0, ctx->stream>>>(a);
+            ctx->launches++;
+        }
+        if (!overflow) {
+            k_scan_compact<<<grid_for(ctx, t->scap * 32, 256, 8), 256, 0, ctx->stream>>>(t->skeys, t->smasks, t->scap, t->delta, t->counters,
+                                                                                      (uint32_t)t->delta_cap);
+            ctx->launches++;
+            R3D_CUDA_OK(ctx, cudaGetLastError());
+            R3D_TRY(tree_sync_counters(t));
+            overflow = t->h_counters[CNT_OVERFLOW] != 0 || t->h_counters[CNT_DELTA] > t->delta_cap;
+        }
+        if (!overflow) {
+            t->delta_n = t->h_counters[CNT_DELTA];
+            return R3D_OK;
+        }
+        // table too small for this scan: grow, wipe, cast again (ray casting is a pure function of the scan)
+        R3D_TRY(tree_reserve_scratch(t, t->scap * 4));
+        R3D_TRY(tree_reset_scratch(t));
+    }
+    return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the scratch table");
+}
+
+static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n) {
+    r3d_ctx* ctx = t->ctx;
+    if (n == 0) return R3D_OK;
+    R3D_TRY(tree_reserve_table(t, (uint64_t)t->pool_used + n));
+    R3D_TRY(tree_reserve_pool(t, (uint64_t)t->pool_used + n));
+    R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
+    k_apply_delta<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(d_recs, (uint32_t)n, t->tkeys, t->tvals, t->tcap, t->values, t->known,
+                                                                          t->counters, t->hit, t->miss, t->cmin, t->cmax);
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    R3D_TRY(tree_sync_counters(t));
+    if (t->h_counters[CNT_OVERFLOW]) return set_error(ctx, R3D_ERR_STATE, "brick table overflow while applying a delta");
+    t->pool_used = t->h_counters[CNT_POOL_USED];
+    return R3D_OK;
+}
+
+}  // namespace r3d
+
 using namespace r3d;
-#define R3D_TODO(ctxexpr) return set_error(ctxexpr, R3D_ERR_UNSUPPORTED, "%s: not implemented yet", __func__)
-struct r3d_tree { r3d_ctx* ctx; double res; };
-extern "C" int r3d_tree_create(r3d_ctx* ctx, double resolution, r3d_tree** tree) { (void)resolution; (void)tree; R3D_TODO(ctx); }
-extern "C" void r3d_tree_destroy(r3d_tree* tree) { delete tree; }
-extern "C" int r3d_tree_clear(r3d_tree* t) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_params(r3d_tree* t, float*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_update_points(r3d_tree* t, const float*, uint64_t, int, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_update_points_f64(r3d_tree* t, const double*, uint64_t, int, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_update_points_logodds(r3d_tree* t, const float*, uint64_t, float, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_insert_scan(r3d_tree* t, const float*, uint64_t, const float*, double, int) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_scan_delta_compute(r3d_tree* t, const float*, uint64_t, const float*, double, int, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_scan_delta_export(r3d_tree* t, void*, uint64_t, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_apply_delta(r3d_tree* t, const void*, uint64_t) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_delta_expand_keys(const void*, uint64_t, uint16_t*, uint64_t, uint64_t*, uint16_t*, uint64_t, uint64_t*) { R3D_TODO(nullptr); }
-extern "C" int r3d_tree_update_inner_occupancy(r3d_tree* t) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_write_bt(r3d_tree* t, const char*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_write_bt_mem(r3d_tree* t, uint8_t*, size_t, size_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_to_max_likelihood(r3d_tree* t) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_num_voxels(r3d_tree* t, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_size(r3d_tree* t, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_search(r3d_tree* t, const uint16_t*, uint64_t, float*, uint8_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_tree_export_voxels(r3d_tree* t, uint16_t*, float*, uint64_t, uint64_t*) { R3D_TODO(t ? t->ctx : nullptr); }
-extern "C" int r3d_coord_to_key(r3d_tree* t, const float*, uint64_t, uint16_t*, uint8_t*) { R3D_TODO(t ? t->ctx : nullptr); }
+
+// ------------------------------------------------------------------ C ABI
+static float logodds_f(double p) { return (float)log(p / (1 - p)); }
+
+extern "C" int r3d_tree_create(r3d_ctx* ctx, double resolution, r3d_tree** tree) {
+    if (!ctx) return set_error(nullptr, R3D_ERR_ARG, "null context");
+    if (!tree) return set_error(ctx, R3D_ERR_ARG, "null out pointer");
+    if (!(resolution > 0)) return set_error(ctx, R3D_ERR_ARG, "resolution must be positive");
+    DeviceSetter ds(ctx->device);
+    r3d_tree* t = new r3d_tree();
+    t->ctx = ctx;
+    t->res = resolution;
+    t->res_factor = 1.0 / resolution;
+    t->hit = logodds_f(0.7); t->miss = logodds_f(0.4);
+    t->cmin = logodds_f(0.1192); t->cmax = logodds_f(0.971);
+    t->occ_thres = logodds_f(0.5);
+    cudaError_t e = cudaMalloc(&t->counters, CNT_COUNT * sizeof(uint32_t));
+    if (e != cudaSuccess) { delete t; return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(counters): %s", cudaGetErrorString(e)); }
+    cudaMemsetAsync(t->counters, 0, CNT_COUNT * sizeof(uint32_t), ctx->stream);
+    int rc = tree_reserve_table(t, 1024);
+    if (rc == R3D_OK) rc = tree_reserve_pool(t, 1024);
+    if (rc != R3D_OK) { r3d_tree_destroy(t); return rc; }
+    *tree = t;
+    return finish(ctx);
+}
+
+extern "C" void r3d_tree_destroy(r3d_tree* t) {
+    if (!t) return;
+    DeviceSetter ds(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
+    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
+    delete t;
+}
+
+extern "C" int r3d_tree_clear(r3d_tree* t) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    DeviceSetter ds(ctx->device);
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->tkeys, 0xff, t->tcap * sizeof(uint64_t), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->values, 0, t->pool_cap * kBrickVoxels * sizeof(float), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->known, 0, t->pool_cap * 16 * sizeof(uint32_t), ctx->stream));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters, 0, CNT_COUNT * sizeof(uint32_t), ctx->stream));
+    t->pool_used = 0;
+    t->delta_n = 0;
+    return finish(ctx);
+}
+
+extern "C" int r3d_tree_params(r3d_tree* t, float out[5]) {
+    if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    out[0] = t->hit; out[1] = t->miss; out[2] = t->cmin; out[3] = t->cmax; out[4] = t->occ_thres;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_update_points(r3d_tree* t, const float* xyz, uint64_t n, int occupied, uint64_t* n_dropped) {
+    return update_points_impl<float>(t, xyz, n, t ? (occupied ? t->hit : t->miss) : 0.f, n_dropped);
+}
+extern "C" int r3d_tree_update_points_f64(r3d_tree* t, const double* xyz, uint64_t n, int occupied, uint64_t* n_dropped) {
+    return update_points_impl<double>(t, xyz, n, t ? (occupied ? t->hit : t->miss) : 0.f, n_dropped);
+}
+extern "C" int r3d_tree_update_points_logodds(r3d_tree* t, const float* xyz, uint64_t n, float upd, uint64_t* n_dropped) {
+    return update_points_impl<float>(t, xyz, n, upd, n_dropped);
+}
+
+extern "C" int r3d_scan_delta_compute(r3d_tree* t, const float* xyz, uint64_t n, const float origin[3], double maxrange,
+                                      int discretize, uint64_t* n_records) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    DeviceSetter ds(t->ctx->device);
+    R3D_TRY(scan_delta_impl(t, xyz, n, origin, maxrange, discretize));
+    if (n_records) *n_records = t->delta_n;
+    return finish(t->ctx);
+}
+
+extern "C" int r3d_scan_delta_export(r3d_tree* t, void* records, uint64_t capacity_records, uint64_t* n_records) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (n_records) *n_records = t->delta_n;
+    if (t->delta_n > capacity_records) return set_error(ctx, R3D_ERR_ARG, "delta has %llu records, buffer holds %llu", (unsigned long long)t->delta_n, (unsigned long long)capacity_records);
+    if (t->delta_n == 0) return R3D_OK;
+    if (!records) return set_error(ctx, R3D_ERR_ARG, "null record buffer");
+    DeviceSetter ds(ctx->device);
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(records, t->delta, t->delta_n * sizeof(DeltaRecord), cudaMemcpyDefault, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_apply_delta(r3d_tree* t, const void* records, uint64_t n_records) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (!records && n_records) return set_error(ctx, R3D_ERR_ARG, "null records");
+    if (n_records > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "too many records");
+    DeviceSetter ds(ctx->device);
+    const DeltaRecord* d = reinterpret_cast<const DeltaRecord*>(records);
+    if (n_records) R3D_TRY(stage_in(ctx, SCR_OUT0, reinterpret_cast<const DeltaRecord*>(records), (size_t)n_records, &d));
+    R3D_TRY(apply_delta_impl(t, d, n_records));
+    return finish(ctx);
+}
+
+extern "C" int r3d_tree_insert_scan(r3d_tree* t, const float* xyz, uint64_t n, const float origin[3], double maxrange, int discretize) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    DeviceSetter ds(t->ctx->device);
+    R3D_TRY(scan_delta_impl(t, xyz, n, origin, maxrange, discretize));
+    R3D_TRY(apply_delta_impl(t, t->delta, t->delta_n));
+    return finish(t->ctx);
+}
+
+extern "C" int r3d_delta_expand_keys(const void* records_host, uint64_t n_records, uint16_t* free_keys, uint64_t free_cap,
+                                     uint64_t* n_free, uint16_t* occ_keys, uint64_t occ_cap, uint64_t* n_occ) {
+    if (!records_host && n_records) return set_error(nullptr, R3D_ERR_ARG, "null records");
+    if (is_device_ptr(records_host)) return set_error(nullptr, R3D_ERR_ARG, "r3d_delta_expand_keys expects host memory");
+    const DeltaRecord* recs = reinterpret_cast<const DeltaRecord*>(records_host);
+    uint64_t nf = 0, no = 0;
+    for (uint64_t r = 0; r < n_records; ++r) {
+        uint32_t bx, by, bz;
+        brick_key_unpack(recs[r].key, bx, by, bz);
+        for (int plane = 0; plane < 2; ++plane) {
+            for (uint32_t vox = 0; vox < 512; ++vox) {
+                if (!(recs[r].mask[plane * 16 + (vox >> 5)] & (1u << (vox & 31u)))) continue;
+                uint32_t x, y, z;
+                brick_voxel_coords(vox, x, y, z);
+                uint16_t* dst = plane ? free_keys : occ_keys;
+                uint64_t& cnt = plane ? nf : no;
+                const uint64_t cap = plane ? free_cap : occ_cap;
+                if (dst && cnt < cap) { dst[3 * cnt] = (uint16_t)(bx * 8 + x); dst[3 * cnt + 1] = (uint16_t)(by * 8 + y); dst[3 * cnt + 2] = (uint16_t)(bz * 8 + z); }
+                cnt++;
+            }
+        }
+    }
+    if (n_free) *n_free = nf;
+    if (n_occ) *n_occ = no;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_update_inner_occupancy(r3d_tree* t) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    return R3D_OK;   // inner-node values are derived from the leaves when the tree shape is needed (a12)
+}
+
+extern "C" int r3d_tree_to_max_likelihood(r3d_tree* t) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    DeviceSetter ds(ctx->device);
+    const uint64_t total = (uint64_t)t->pool_used * kBrickVoxels;
+    if (total) {
+        k_to_max_likelihood<<<grid_for(ctx, total), 256, 0, ctx->stream>>>(t->values, t->known, total, t->occ_thres, t->cmin, t->cmax);
+        ctx->launches++;
+    }
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    return finish(ctx);
+}
+
+extern "C" int r3d_tree_num_voxels(r3d_tree* t, uint64_t* n) {
+    if (!t || !n) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    r3d_ctx* ctx = t->ctx;
+    DeviceSetter ds(ctx->device);
+    R3D_TRY(scratch_reserve(ctx, SCR_MISC, 64));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->scratch[SCR_MISC], 0, 8, ctx->stream));
+    const uint64_t words = (uint64_t)t->pool_used * 16;
+    if (words) {
+        k_count_known<<<grid_for(ctx, words), 256, 0, ctx->stream>>>(t->known, words, (unsigned long long*)ctx->scratch[SCR_MISC]);
+        ctx->launches++;
+    }
+    unsigned long long h = 0;
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(&h, ctx->scratch[SCR_MISC], 8, cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    *n = h;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_search(r3d_tree* t, const uint16_t* keys, uint64_t n, float* values, uint8_t* found) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (!keys && n) return set_error(ctx, R3D_ERR_ARG, "null keys");
+    if (n == 0) return R3D_OK;
+    DeviceSetter ds(ctx->device);
+    const uint16_t* dk = keys;
+    R3D_TRY(stage_in(ctx, SCR_IN0, keys, (size_t)n * 3, &dk));
+    const bool vdev = values && is_device_ptr(values), fdev = found && is_device_ptr(found);
+    R3D_TRY(scratch_reserve(ctx, SCR_OUT0, (size_t)n * 4 + 16));
+    R3D_TRY(scratch_reserve(ctx, SCR_OUT1, (size_t)n + 16));
+    float* dv = vdev ? values : (float*)ctx->scratch[SCR_OUT0];
+    uint8_t* df = fdev ? found : (uint8_t*)ctx->scratch[SCR_OUT1];
+    k_search<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(dk, n, t->tkeys, t->tvals, t->tcap, t->values, t->known, dv, df);
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    if (values && !vdev) R3D_CUDA_OK(ctx, cudaMemcpyAsync(values, dv, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (found && !fdev) R3D_CUDA_OK(ctx, cudaMemcpyAsync(found, df, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_export_voxels(r3d_tree* t, uint16_t* keys, float* values, uint64_t cap, uint64_t* n) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_refresh_pool_keys(t));
+    R3D_TRY(scratch_reserve(ctx, SCR_MISC, 64));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->scratch[SCR_MISC], 0, 8, ctx->stream));
+    uint16_t* dk = nullptr;
+    float* dv = nullptr;
+    if (keys && cap) { R3D_TRY(scratch_reserve(ctx, SCR_OUT0, (size_t)cap * 6 + 16)); dk = (uint16_t*)ctx->scratch[SCR_OUT0]; }
+    if (values && cap) { R3D_TRY(scratch_reserve(ctx, SCR_OUT1, (size_t)cap * 4 + 16)); dv = (float*)ctx->scratch[SCR_OUT1]; }
+    if (t->pool_used) {
+        k_export_voxels<<<grid_for(ctx, (uint64_t)t->pool_used * kBrickVoxels), 256, 0, ctx->stream>>>(
+            t->pool_keys, t->values, t->known, t->pool_used, dk, dv, cap, (unsigned long long*)ctx->scratch[SCR_MISC]);
+        ctx->launches++;
+    }
+    unsigned long long h = 0;
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(&h, ctx->scratch[SCR_MISC], 8, cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t m = h < cap ? h : cap;
+    if (dk && m) R3D_CUDA_OK(ctx, cudaMemcpy(keys, dk, (size_t)m * 6, cudaMemcpyDefault));
+    if (dv && m) R3D_CUDA_OK(ctx, cudaMemcpy(values, dv, (size_t)m * 4, cudaMemcpyDefault));
+    if (n) *n = h;
+    return R3D_OK;
+}
+
+extern "C" int r3d_coord_to_key(r3d_tree* t, const float* xyz, uint64_t n, uint16_t* keys, uint8_t* valid) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if ((!xyz || !keys) && n) return set_error(ctx, R3D_ERR_ARG, "null buffer");
+    if (n == 0) return R3D_OK;
+    DeviceSetter ds(ctx->device);
+    const float* d = xyz;
+    R3D_TRY(stage_in(ctx, SCR_IN0, xyz, (size_t)n * 3, &d));
+    const bool kdev = is_device_ptr(keys), vdev = valid && is_device_ptr(valid);
+    R3D_TRY(scratch_reserve(ctx, SCR_OUT0, (size_t)n * 6 + 16));
+    R3D_TRY(scratch_reserve(ctx, SCR_OUT1, (size_t)n + 16));
+    uint16_t* dk = kdev ? keys : (uint16_t*)ctx->scratch[SCR_OUT0];
+    uint8_t* dv = vdev ? valid : (uint8_t*)ctx->scratch[SCR_OUT1];
+    k_coord_to_key<<<grid_for(ctx, n), 256, 0, ctx->stream>>>(d, n, t->res_factor, dk, dv);
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    if (!kdev) R3D_CUDA_OK(ctx, cudaMemcpyAsync(keys, dk, (size_t)n * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    if (valid && !vdev) R3D_CUDA_OK(ctx, cudaMemcpyAsync(valid, dv, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return R3D_OK;
+}

@@ -1,0 +1,50 @@
+// r3d_octree.cuh -- the voxel store shared by the update kernels (r3d_octree.cu) and the .bt serialiser (r3d_bt.cu).
+#pragma once
+#include "r3d_common.cuh"
+
+namespace r3d {
+
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint64_t kNoSlot = ~0ull;
+constexpr uint32_t kBrickVoxels = 512;
+
+// one brick of a scan delta: see R3D_DELTA_RECORD_BYTES in r3d.h
+struct DeltaRecord {
+    uint64_t key;
+    uint32_t mask[32];   // [0,16): occupied, [16,32): free (already minus occupied)
+};
+static_assert(sizeof(DeltaRecord) == R3D_DELTA_RECORD_BYTES, "record layout is part of the ABI");
+
+// device counters of a tree
+enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_COUNT = 16 };
+
+}  // namespace r3d
+
+struct r3d_tree {
+    r3d_ctx* ctx = nullptr;
+    double res = 0.1, res_factor = 10.0;
+    float hit = 0, miss = 0, cmin = 0, cmax = 0, occ_thres = 0;
+    // persistent store: hash (brick key -> pool index) + brick pool
+    uint64_t* tkeys = nullptr;
+    uint32_t* tvals = nullptr;
+    uint64_t tcap = 0;
+    float* values = nullptr;      // [pool_cap][512] log-odds, Morton order inside the brick
+    uint32_t* known = nullptr;    // [pool_cap][16]  voxel was updated at least once (node exists)
+    uint64_t pool_cap = 0;
+    uint32_t pool_used = 0;       // host mirror of counters[CNT_POOL_USED]
+    uint64_t* pool_keys = nullptr; // [pool_cap] brick key per pool entry, rebuilt from the table on demand
+    uint64_t pool_keys_cap = 0;
+    // per-scan scratch table + compacted delta
+    uint64_t* skeys = nullptr;
+    uint32_t* smasks = nullptr;
+    uint64_t scap = 0;
+    r3d::DeltaRecord* delta = nullptr;
+    uint64_t delta_cap = 0, delta_n = 0;
+    uint32_t* counters = nullptr;
+    uint32_t h_counters[r3d::CNT_COUNT] = {0};
+};
+
+namespace r3d {
+int tree_sync_counters(r3d_tree* t);
+int tree_refresh_pool_keys(r3d_tree* t);
+}  // namespace r3d

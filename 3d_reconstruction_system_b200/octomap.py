@@ -1,0 +1,237 @@
+"""Drop-in for the subset of the `octomap` Python module the reference scripts use
+(octomap/txt_transfer_octomap.py:2,25,33-36; octomap/ply_transfer_octomap.py:2,33,45-48):
+
+    tree = octomap.OcTree(0.1)
+    tree.updateNode(point, True)          # per point, as the reference does
+    tree.updateInnerOccupancy()
+    tree.writeBinary(bytes(path, 'utf-8'))
+
+plus insertPointCloud(points, origin, maxrange=-1., lazy_eval=False, discretize=False) with the upstream binding's
+signature (named by BASELINE.json north_star).  Everything executes on the GPU through libr3d_b200.so.
+
+Per-point updateNode calls are queued on the host and flushed to the GPU in batches, in call order; a batch of
+updates with the same log-odds increment is order-independent per voxel, so runs of equal increments are applied
+as one kernel launch and runs are applied in sequence -- the result equals the one-by-one loop.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .runtime import _ptr, default_context
+
+_FLUSH_POINTS = 1 << 20
+
+
+class OcTree:
+    def __init__(self, resolution, device=0, ctx=None):
+        self._ctx = ctx if ctx is not None else default_context(device)
+        self._lib = self._ctx.lib
+        h = C.c_void_p()
+        check(self._lib.r3d_tree_create(self._ctx.handle, float(resolution), C.byref(h)), self._ctx.handle)
+        self._h = h
+        self._res = float(resolution)
+        self._pend_pts = []      # queued updateNode points (float64 triples)
+        self._pend_upd = []      # their log-odds increments (float32)
+        p = (C.c_float * 5)()
+        check(self._lib.r3d_tree_params(self._h, p), self._ctx.handle)
+        self._hit, self._miss, self._cmin, self._cmax, self._thres = (np.float32(v) for v in p)
+        self.n_dropped = 0       # out-of-range points silently ignored, as upstream does
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.r3d_tree_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ reference call surface
+    def updateNode(self, value, update, lazy_eval=False):
+        """updateNode(point, bool) / updateNode(point, float): dispatch on the Python type of `update` exactly like
+        the upstream binding; the point is cast to float32 and only elements 0..2 are used."""
+        if isinstance(update, (bool, np.bool_)):
+            upd = self._hit if update else self._miss
+        else:
+            upd = np.float32(update)
+        self._pend_pts.append((float(value[0]), float(value[1]), float(value[2])))
+        self._pend_upd.append(upd)
+        if len(self._pend_pts) >= _FLUSH_POINTS:
+            self._flush()
+
+    def updateNodes(self, points, occupied=True):
+        """Batched form of the reference's per-point loop: n points, one increment."""
+        self._flush()
+        dropped = C.c_uint64(0)
+        if isinstance(points, np.ndarray) and points.dtype == np.float32:
+            p = np.ascontiguousarray(points).reshape(-1, 3)
+            check(self._lib.r3d_tree_update_points(self._h, p.ctypes.data, p.shape[0], 1 if occupied else 0, C.byref(dropped)), self._ctx.handle)
+        elif isinstance(points, np.ndarray) or isinstance(points, (list, tuple)):
+            p = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+            check(self._lib.r3d_tree_update_points_f64(self._h, p.ctypes.data, p.shape[0], 1 if occupied else 0, C.byref(dropped)), self._ctx.handle)
+        else:   # device float32 buffer (n, 3)
+            n = int(points.shape[0])
+            check(self._lib.r3d_tree_update_points(self._h, _ptr(points), n, 1 if occupied else 0, C.byref(dropped)), self._ctx.handle)
+        self.n_dropped += int(dropped.value)
+
+    def insertPointCloud(self, pointcloud, origin, maxrange=-1.0, lazy_eval=False, discretize=False):
+        self._flush()
+        o = np.asarray(origin, dtype=np.float64).astype(np.float32)
+        oa = (C.c_float * 3)(float(o[0]), float(o[1]), float(o[2]))
+        if isinstance(pointcloud, np.ndarray) or isinstance(pointcloud, (list, tuple)):
+            p = np.ascontiguousarray(np.asarray(pointcloud, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+            ptr, n = p.ctypes.data, p.shape[0]
+        else:   # device float32 (n, 3)
+            ptr, n = _ptr(pointcloud), int(pointcloud.shape[0])
+        check(self._lib.r3d_tree_insert_scan(self._h, ptr, n, oa, float(maxrange), 1 if discretize else 0), self._ctx.handle)
+
+    def updateInnerOccupancy(self):
+        self._flush()
+        check(self._lib.r3d_tree_update_inner_occupancy(self._h), self._ctx.handle)
+
+    def writeBinary(self, filename=None):
+        """writeBinary(bytes path) -> bool; with no argument returns the .bt bytes (the binding's overload)."""
+        self._flush()
+        if filename is None:
+            n = C.c_size_t(0)
+            check(self._lib.r3d_tree_write_bt_mem(self._h, None, 0, C.byref(n)), self._ctx.handle)
+            buf = (C.c_uint8 * max(n.value, 1))()
+            check(self._lib.r3d_tree_write_bt_mem(self._h, buf, n.value, C.byref(n)), self._ctx.handle)
+            return bytes(buf[: n.value])
+        if isinstance(filename, str):
+            filename = filename.encode("utf-8")
+        rc = self._lib.r3d_tree_write_bt(self._h, filename)
+        if rc == -5:
+            return False
+        check(rc, self._ctx.handle)
+        return True
+
+    # ------------------------------------------------------------------ further binding methods
+    def getResolution(self):
+        return self._res
+
+    def size(self):
+        self._flush()
+        n = C.c_uint64(0)
+        check(self._lib.r3d_tree_size(self._h, C.byref(n)), self._ctx.handle)
+        return int(n.value)
+
+    def clear(self):
+        self._pend_pts, self._pend_upd = [], []
+        check(self._lib.r3d_tree_clear(self._h), self._ctx.handle)
+
+    def toMaxLikelihood(self):
+        self._flush()
+        check(self._lib.r3d_tree_to_max_likelihood(self._h), self._ctx.handle)
+
+    def coordToKey(self, point):
+        p = np.asarray(point, dtype=np.float64).astype(np.float32).reshape(1, 3)
+        k = np.zeros((1, 3), np.uint16)
+        v = np.zeros(1, np.uint8)
+        check(self._lib.r3d_coord_to_key(self._h, p.ctypes.data, 1, k.ctypes.data, v.ctypes.data), self._ctx.handle)
+        return (int(k[0, 0]), int(k[0, 1]), int(k[0, 2])) if v[0] else None
+
+    def coordsToKeys(self, points):
+        p = np.ascontiguousarray(np.asarray(points, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+        k = np.zeros((p.shape[0], 3), np.uint16)
+        v = np.zeros(p.shape[0], np.uint8)
+        check(self._lib.r3d_coord_to_key(self._h, p.ctypes.data, p.shape[0], k.ctypes.data, v.ctypes.data), self._ctx.handle)
+        return k, v.astype(bool)
+
+    def search(self, key):
+        """Log-odds of the depth-16 leaf at `key` (3 x uint16), or None when unknown."""
+        vals, found = self.searchKeys(np.asarray(key, dtype=np.uint16).reshape(1, 3))
+        return float(vals[0]) if found[0] else None
+
+    def searchKeys(self, keys):
+        self._flush()
+        k = np.ascontiguousarray(keys, dtype=np.uint16).reshape(-1, 3)
+        vals = np.zeros(k.shape[0], np.float32)
+        found = np.zeros(k.shape[0], np.uint8)
+        check(self._lib.r3d_tree_search(self._h, k.ctypes.data, k.shape[0], vals.ctypes.data, found.ctypes.data), self._ctx.handle)
+        return vals, found.astype(bool)
+
+    def isNodeOccupied(self, value):
+        return value is not None and np.float32(value) >= self._thres
+
+    def numVoxels(self):
+        self._flush()
+        n = C.c_uint64(0)
+        check(self._lib.r3d_tree_num_voxels(self._h, C.byref(n)), self._ctx.handle)
+        return int(n.value)
+
+    def voxels(self):
+        """Every depth-16 leaf ever updated: (keys (n,3) uint16, log-odds float32), sorted by packed key."""
+        n = self.numVoxels()
+        keys = np.zeros((max(n, 1), 3), np.uint16)
+        vals = np.zeros(max(n, 1), np.float32)
+        m = C.c_uint64(0)
+        check(self._lib.r3d_tree_export_voxels(self._h, keys.ctypes.data, vals.ctypes.data, n, C.byref(m)), self._ctx.handle)
+        keys, vals = keys[:n], vals[:n]
+        packed = keys[:, 0].astype(np.uint64) | (keys[:, 1].astype(np.uint64) << np.uint64(16)) | (keys[:, 2].astype(np.uint64) << np.uint64(32))
+        order = np.argsort(packed, kind="stable")
+        return keys[order], vals[order]
+
+    # ------------------------------------------------------------------ scan deltas (multi-GPU merge)
+    def computeScanDelta(self, pointcloud, origin, maxrange=-1.0, discretize=False):
+        """Ray-cast one scan WITHOUT touching the tree; returns the delta as a (n, 136) uint8 array of brick records."""
+        self._flush()
+        o = np.asarray(origin, dtype=np.float64).astype(np.float32)
+        oa = (C.c_float * 3)(float(o[0]), float(o[1]), float(o[2]))
+        if isinstance(pointcloud, np.ndarray) or isinstance(pointcloud, (list, tuple)):
+            p = np.ascontiguousarray(np.asarray(pointcloud, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+            ptr, n = p.ctypes.data, p.shape[0]
+        else:
+            ptr, n = _ptr(pointcloud), int(pointcloud.shape[0])
+        cnt = C.c_uint64(0)
+        check(self._lib.r3d_scan_delta_compute(self._h, ptr, n, oa, float(maxrange), 1 if discretize else 0, C.byref(cnt)), self._ctx.handle)
+        rec = np.zeros((max(cnt.value, 1), _lib.DELTA_RECORD_BYTES), np.uint8)
+        check(self._lib.r3d_scan_delta_export(self._h, rec.ctypes.data, cnt.value, C.byref(cnt)), self._ctx.handle)
+        return rec[: cnt.value]
+
+    def scanDeltaInto(self, buf, capacity_records):
+        """Export the last computed delta into a caller buffer (host array or device tensor); returns the record count."""
+        cnt = C.c_uint64(0)
+        check(self._lib.r3d_scan_delta_export(self._h, _ptr(buf), int(capacity_records), C.byref(cnt)), self._ctx.handle)
+        return int(cnt.value)
+
+    def applyDelta(self, records, n_records=None):
+        self._flush()
+        if isinstance(records, np.ndarray):
+            records = np.ascontiguousarray(records, dtype=np.uint8)
+            n = records.size // _lib.DELTA_RECORD_BYTES if n_records is None else int(n_records)
+            ptr = records.ctypes.data
+        else:
+            ptr, n = _ptr(records), int(n_records)
+        check(self._lib.r3d_tree_apply_delta(self._h, ptr, n), self._ctx.handle)
+
+    @staticmethod
+    def deltaKeys(records):
+        """Expand delta records to explicit OcTreeKeys: (free (n,3) uint16, occupied (m,3) uint16)."""
+        lib = _lib.load()
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        n = rec.size // _lib.DELTA_RECORD_BYTES
+        nf, no = C.c_uint64(0), C.c_uint64(0)
+        check(lib.r3d_delta_expand_keys(rec.ctypes.data, n, None, 0, C.byref(nf), None, 0, C.byref(no)))
+        fk = np.zeros((max(nf.value, 1), 3), np.uint16)
+        ok = np.zeros((max(no.value, 1), 3), np.uint16)
+        check(lib.r3d_delta_expand_keys(rec.ctypes.data, n, fk.ctypes.data, nf.value, C.byref(nf), ok.ctypes.data, no.value, C.byref(no)))
+        return fk[: nf.value], ok[: no.value]
+
+    # ------------------------------------------------------------------ internals
+    def _flush(self):
+        if not self._pend_pts:
+            return
+        pts = np.array(self._pend_pts, dtype=np.float64).reshape(-1, 3).astype(np.float32)
+        upd = np.array(self._pend_upd, dtype=np.float32)
+        self._pend_pts, self._pend_upd = [], []
+        # maximal runs of equal increments, applied in order
+        cuts = np.flatnonzero(upd[1:] != upd[:-1]) + 1
+        starts = np.concatenate([[0], cuts])
+        ends = np.concatenate([cuts, [upd.size]])
+        dropped = C.c_uint64(0)
+        for a, b in zip(starts, ends):
+            seg = np.ascontiguousarray(pts[a:b])
+            check(self._lib.r3d_tree_update_points_logodds(self._h, seg.ctypes.data, seg.shape[0], float(upd[a]), C.byref(dropped)), self._ctx.handle)
+            self.n_dropped += int(dropped.value)

@@ -1,0 +1,38 @@
+// Host build of 3d_reconstruction_system_b200/csrc/r3d_math.cuh -- TEST INFRASTRUCTURE ONLY.
+// The kernels' scalar arithmetic is written once for host and device; this wrapper lets the CPU test-suite check
+// those formulas against the oracle where no GPU exists.  It is never loaded by the product package.
+#include "../../3d_reconstruction_system_b200/csrc/r3d_math.cuh"
+#include <cstddef>
+using namespace r3d;
+extern "C" {
+int hm_coord_to_key(double res_factor, float x, float y, float z, uint16_t* k) {
+    return coord_to_key3(res_factor, x, y, z, k[0], k[1], k[2]) ? 1 : 0;
+}
+// returns -1 (out of bounds), else number of free keys written (origin key first), like computeRayKeys
+long hm_ray_keys(double res, const float* o, const float* e, uint16_t* out, long cap) {
+    Ray r;
+    const int st = ray_setup(res, 1.0 / res, o[0], o[1], o[2], e[0], e[1], e[2], r);
+    if (st < 0) return -1;
+    if (st == 0) return 0;
+    long n = 0;
+    do {
+        if (n < cap) { out[3 * n] = (uint16_t)r.kx; out[3 * n + 1] = (uint16_t)r.ky; out[3 * n + 2] = (uint16_t)r.kz; }
+        ++n;
+    } while (ray_step(r));
+    return n;
+}
+int hm_scan_point_end(const float* o, const float* p, double maxrange, float* e) {
+    return scan_point_end(o[0], o[1], o[2], p[0], p[1], p[2], maxrange, e[0], e[1], e[2]) ? 1 : 0;
+}
+void hm_pose_apply(const double* rt, const double* p, double* w) {
+    Pose ps; pose_load(rt, ps);
+    pose_apply(ps, p[0], p[1], p[2], w[0], w[1], w[2]);
+}
+double hm_pixel_coeff(int i, double c, double f) { return pixel_coeff(i, c, f); }
+double hm_decode_z(double raw, int mode, double scale, double fB, int* valid) { bool v; double z = decode_z(raw, mode, scale, fB, v); *valid = v; return z; }
+float hm_clamped_add(float v, float u, float lo, float hi) { return clamped_add(v, u, lo, hi); }
+uint32_t hm_brick_voxel_index(uint32_t x, uint32_t y, uint32_t z) { return brick_voxel_index(x, y, z); }
+void hm_brick_voxel_coords(uint32_t i, uint32_t* xyz) { brick_voxel_coords(i, xyz[0], xyz[1], xyz[2]); }
+uint64_t hm_brick_key(uint32_t x, uint32_t y, uint32_t z) { return brick_key(x, y, z); }
+uint64_t hm_brick_morton(uint64_t bk) { return brick_morton(bk); }
+}

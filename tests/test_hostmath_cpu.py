@@ -1,0 +1,137 @@
+"""The kernels' scalar arithmetic (csrc/r3d_math.cuh) is host/device code; here it is compiled for the host and
+checked against the oracle, so formula errors surface without a GPU.  (The GPU parity tests check the kernels.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import octomap_oracle as oo
+from oracle import points_oracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hm():
+    out = os.path.join(HERE, "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libhostmath.so")
+    src = os.path.join(HERE, "hostmath", "hostmath.cpp")
+    hdr = os.path.join(HERE, "..", "3d_reconstruction_system_b200", "csrc", "r3d_math.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", src, "-o", so])
+    L = C.CDLL(so)
+    L.hm_ray_keys.restype = C.c_long
+    L.hm_ray_keys.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+    L.hm_coord_to_key.argtypes = [C.c_double, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    L.hm_scan_point_end.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.hm_pose_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hm_pixel_coeff.restype = C.c_double
+    L.hm_pixel_coeff.argtypes = [C.c_int, C.c_double, C.c_double]
+    L.hm_clamped_add.restype = C.c_float
+    L.hm_clamped_add.argtypes = [C.c_float] * 4
+    L.hm_brick_key.restype = C.c_uint64
+    L.hm_brick_key.argtypes = [C.c_uint32] * 3
+    L.hm_brick_morton.restype = C.c_uint64
+    L.hm_brick_morton.argtypes = [C.c_uint64]
+    L.hm_brick_voxel_index.restype = C.c_uint32
+    L.hm_brick_voxel_index.argtypes = [C.c_uint32] * 3
+    L.hm_brick_voxel_coords.argtypes = [C.c_uint32, C.c_void_p]
+    return L
+
+
+def ray(hm, res, o, e):
+    o32, e32 = np.asarray(o, np.float32), np.asarray(e, np.float32)
+    buf = np.zeros((300000, 3), np.uint16)
+    n = hm.hm_ray_keys(res, o32.ctypes.data, e32.ctypes.data, buf.ctypes.data, buf.shape[0])
+    return None if n < 0 else buf[:n].copy()
+
+
+@pytest.mark.parametrize("res", [0.1, 0.05, 0.25])
+def test_dda_matches_oracle(hm, res):
+    rng = np.random.default_rng(3)
+    t = oo.OcTree(res)
+    cases = []
+    for _ in range(1500):
+        o = rng.uniform(-20, 20, 3)
+        cases.append((o, o + rng.normal(size=3) * rng.uniform(0, 60)))
+    o = np.array([0.05, 0.05, 0.05])
+    cases += [(o, o), (o, o + [3, 0, 0]), (o, o + [0, -3, 0]), (o, o + [0, 0, 3]), (o, o + [1, 1, 1]), (o, o + [1e-3, 0, 0]),
+              (o, [5000, 0, 0]), ([-5000, 0, 0], o), (o, o + [res, res, 0]), (np.zeros(3), [res * 10, res * 10, res * 10]),
+              (np.zeros(3), [-res * 7, res * 7, 0]), ([1600.0, -1600.0, 3.0], [1630.0, -1570.0, 9.0])]
+    for o, e in cases:
+        got = ray(hm, res, o, e)
+        want = t.computeRayKeys(np.float32(o), np.float32(e), 300000)
+        if want is None:
+            assert got is None
+        else:
+            assert np.array_equal(got, want), (o, e)
+
+
+def test_keys_and_maxrange_end(hm):
+    rng = np.random.default_rng(4)
+    t = oo.OcTree(0.1)
+    pts = np.concatenate([rng.uniform(-3300, 3300, size=(5000, 3)), (np.arange(-50, 50)[:, None] * 0.1 + np.zeros((1, 3)))])
+    k = (C.c_uint16 * 3)()
+    for p in pts.astype(np.float32):
+        ok = hm.hm_coord_to_key(10.0, float(p[0]), float(p[1]), float(p[2]), k)
+        want = t.coordToKey(p.astype(np.float64))
+        assert bool(ok) == (want is not None)
+        if want:
+            assert (k[0], k[1], k[2]) == want
+    # truncated ray end == the oracle's (checked through the free-key set of a single beyond-range point)
+    o = np.array([0.3, -0.2, 0.1], np.float32)
+    for _ in range(300):
+        p = (o + rng.normal(size=3) * 40).astype(np.float32)
+        e = np.zeros(3, np.float32)
+        inr = hm.hm_scan_point_end(o.ctypes.data, p.ctypes.data, 15.0, e.ctypes.data)
+        fr, oc = t.computeUpdate(p[None, :], o, 15.0)
+        assert bool(inr) == (len(oc) == 1)
+        got = ray(hm, 0.1, o, e)
+        keys = oo.pack_keys(got) if got is not None and len(got) else np.zeros(0, np.uint64)
+        if inr and len(oc):
+            keys = keys[keys != oc[0]]
+        assert np.array_equal(np.sort(np.unique(keys)), fr)
+
+
+def test_pose_tables_and_clamp(hm, golden_dir):
+    z = np.load(os.path.join(golden_dir, "ref_c2w_small.npz"))
+    for i in (0, 5, 319, 320, 321, 1241):
+        assert hm.hm_pixel_coeff(i, 320.0, 600.391) == (i - 320) / 600.391
+        assert hm.hm_pixel_coeff(i, 607.1928, 718.856) == (i - 607.1928) / 718.856
+    k = 2
+    cam, world = po.depth_to_world(z["depths"][k], po.REF_INTRINSICS, z["rinv"][k], z["trans"][k])
+    rt = np.concatenate([z["rinv"][k].reshape(9), z["trans"][k]])
+    w = np.zeros(3)
+    for i in range(cam.shape[0]):
+        p = np.ascontiguousarray(cam[i])
+        hm.hm_pose_apply(rt.ctypes.data, p.ctypes.data, w.ctypes.data)
+        assert np.array_equal(w, world[i])
+    v = np.float32(0)
+    for _ in range(8):
+        v = np.float32(hm.hm_clamped_add(v, np.float32(0.84729785), np.float32(-2.0000279), np.float32(3.5110307)))
+    assert v == np.float32(3.5110307)
+
+
+def test_brick_indexing_roundtrip(hm):
+    seen = set()
+    xyz = (C.c_uint32 * 3)()
+    for x in range(8):
+        for y in range(8):
+            for z in range(8):
+                i = hm.hm_brick_voxel_index(x + 8 * 5, y + 8 * 9, z)
+                assert i == (x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | ((x >> 1 & 1) << 3) | ((y >> 1 & 1) << 4) | ((z >> 1 & 1) << 5) | \
+                    ((x >> 2) << 6) | ((y >> 2) << 7) | ((z >> 2) << 8)
+                hm.hm_brick_voxel_coords(i, xyz)
+                assert (xyz[0], xyz[1], xyz[2]) == (x, y, z)
+                seen.add(i)
+    assert len(seen) == 512
+    bk = hm.hm_brick_key(65535, 8, 32768)
+    assert bk == (8191 | (1 << 13) | (4096 << 26))
+    m = hm.hm_brick_morton(bk)
+    want = 0
+    for b in range(13):
+        want |= ((8191 >> b) & 1) << (3 * b) | ((1 >> b) & 1) << (3 * b + 1) | ((4096 >> b) & 1) << (3 * b + 2)
+    assert m == want

@@ -1,0 +1,296 @@
+"""Parity of the GPU occupancy path (updateNode / insertPointCloud / writeBinary) with the OctoMap restatement
+in oracle/octomap_oracle.c, through the drop-in octomap.OcTree class (which calls the C ABI).
+
+Bars: voxel key sets and occupancy bits bit-exact, log-odds bit-exact (stricter than the 1e-6 of BASELINE.json),
+.bt byte-identical.  PARITY UNPINNED vs real OctoMap (not installable here): the oracle is the spec."""
+import importlib
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import octomap_oracle as oo
+from oracle import points_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+HDR = (b"# Octomap OcTree binary file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n"
+       b"id OcTree\nsize %d\nres %s\ndata\n")
+
+
+@pytest.fixture(scope="module")
+def octomap(r3d):
+    return importlib.import_module("3d_reconstruction_system_b200.octomap")
+
+
+def f32bits(v):
+    return struct.unpack("<I", struct.pack("<f", float(v)))[0]
+
+
+def assert_same_tree(gpu, ref, check_size=True):
+    """Every GPU voxel has the oracle's log-odds bit for bit, the voxel counts agree, and the .bt bytes agree."""
+    keys, vals = gpu.voxels()
+    rk, rv, rd = ref.leaves()
+    # expand the oracle's (possibly pruned) leaves to depth-16 voxel count
+    n_ref = int(np.sum(8 ** (16 - rd.astype(np.int64))))
+    assert keys.shape[0] == n_ref
+    step = max(1, keys.shape[0] // 4000)
+    for k, v in zip(keys[::step], vals[::step]):
+        assert f32bits(ref.search(k)) == f32bits(v), (k, v, ref.search(k))
+    if check_size:
+        assert gpu.size() == ref.size()
+    assert gpu.writeBinary() == ref.write_binary_bytes()   # oracle call last: it mutates the oracle tree
+
+
+def test_params_and_keys(octomap):
+    t = octomap.OcTree(0.1)
+    r = oo.OcTree(0.1)
+    assert [f32bits(v) for v in (t._hit, t._miss, t._cmin, t._cmax)] == [0x3F58E883, 0xBECF991F, 0xC0000075, 0x4060B4BA]
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([rng.uniform(-3300, 3300, size=(20000, 3)),
+                          np.array([[0, 0, 0], [-1e-9, 0.05, 0.1], [0.3, 0.7, -0.3], [3276.75, 0, 0], [3276.8, 0, 0], [-3276.8, 0, 0],
+                                    [np.nan, 0, 0], [np.inf, 1, 1], [1e30, 0, 0]])])
+    k = np.arange(-40, 40)[:, None] * 0.1 + np.array([0.0, 1e-7, -1e-7])[None, :]
+    pts = np.concatenate([pts, np.stack([k.ravel(), k.ravel(), k.ravel()], axis=1)])
+    keys, valid = t.coordsToKeys(pts)
+    for p, kk, v in zip(pts, keys, valid):
+        want = r.coordToKey(np.float32(p).astype(np.float64))
+        assert (want is not None) == bool(v)
+        if want is not None:
+            assert tuple(int(x) for x in kk) == want
+    t5 = octomap.OcTree(0.05)
+    assert t5.coordToKey([1638.39, 0, 0])[0] == 65535 and t5.coordToKey([1638.41, 0, 0]) is None
+
+
+def test_logodds_ladder_and_float_update(octomap):
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    p = np.array([1.0, 2.0, 3.0])
+    k = r.coordToKey(p)
+    for i in range(7):
+        t.updateNode(p, True)
+        r.updateNode(p, True)
+        assert f32bits(t.search(k)) == f32bits(r.search(k))
+    for i in range(20):
+        t.updateNode(p, False)
+        r.updateNode(p, False)
+        if i % 3 == 0:
+            assert f32bits(t.search(k)) == f32bits(r.search(k))
+    assert f32bits(t.search(k)) == 0xC0000075
+    t.updateNode(p, 1.0)
+    r.updateNode(p, 1.0)
+    t.updateNode(p, -0.25)
+    r.updateNode(p, -0.25)
+    assert f32bits(t.search(k)) == f32bits(r.search(k))
+    assert t.search((1, 2, 3)) is None
+    # many hits on one voxel in ONE batch (warp-aggregated path)
+    t2, r2 = octomap.OcTree(0.1), oo.OcTree(0.1)
+    for n in (1, 2, 3, 4, 5, 33, 1000):
+        t2.clear()
+        r2 = oo.OcTree(0.1)
+        pts = np.tile(p, (n, 1))
+        t2.updateNodes(pts, True)
+        r2.updateNodes(pts, True)
+        assert f32bits(t2.search(k)) == f32bits(r2.search(k))
+
+
+def test_bt_known_answers(octomap):
+    t = octomap.OcTree(0.1)
+    assert t.writeBinary() == HDR % (0, b"0.1")
+    assert t.size() == 0
+    t.updateNode(np.array([0.05, 0.05, 0.05]), True)
+    t.updateInnerOccupancy()
+    assert t.size() == 17
+    assert t.writeBinary() == HDR % (17, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 14 + b"\x02\x00"
+    t = octomap.OcTree(0.05)
+    t.updateNode(np.array([-0.01, -0.01, -0.01]), False)
+    assert t.writeBinary() == HDR % (17, b"0.05") + b"\x03\x00" + b"\x00\xc0" * 14 + b"\x00\x40"
+    t = octomap.OcTree(0.1)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                t.updateNode(np.array([0.05 + 0.1 * dx, 0.05 + 0.1 * dy, 0.05 + 0.1 * dz]), True)
+    assert t.size() == 16
+    assert t.writeBinary() == HDR % (16, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 13 + b"\x02\x00"
+    t = octomap.OcTree(0.1)
+    t.updateNode(np.array([0.05, 0.05, 0.05]), True)
+    t.updateNode(np.array([0.15, 0.05, 0.05]), False)
+    t.updateNode(np.array([0.05, 0.15, 0.15]), True)
+    assert t.writeBinary() == HDR % (19, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 14 + bytes([0x02 | 0x04, 0x20])
+
+
+def test_prune_early_break_quirk(octomap):
+    t, t2 = octomap.OcTree(0.1), octomap.OcTree(0.1)
+    for ix in range(4):
+        for iy in range(4):
+            for iz in range(4):
+                p = np.array([0.05 + 0.1 * ix, 0.05 + 0.1 * iy, 0.05 + 0.1 * iz])
+                t.updateNode(p, True)
+                t2.updateNode(p, True)
+                if not (ix < 2 and iy < 2 and iz < 2):
+                    t.updateNode(p, True)
+                if ix % 2 == 0:
+                    t2.updateNode(p, True)
+    assert t.size() == 1 + 14 + 8
+    assert t.writeBinary() == HDR % (23, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 13 + b"\xaa\xaa"
+    assert t2.writeBinary() == HDR % (15, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 12 + b"\x02\x00"
+
+
+@pytest.mark.parametrize("res,n,spread,seed", [(0.1, 3000, 2.0, 1), (0.1, 60000, 1.2, 2), (0.05, 40000, 30.0, 3), (0.1, 20000, 3000.0, 4)])
+def test_update_node_clouds_match_oracle(octomap, res, n, spread, seed):
+    """The reference scripts' mode: updateNode(p, True) per point, then writeBinary."""
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-spread, spread, size=(n, 3))
+    pts[: n // 10] = np.round(pts[: n // 10], 1)     # duplicates / voxel-boundary values
+    t, r = octomap.OcTree(res), oo.OcTree(res)
+    t.updateNodes(pts, True)
+    r.updateNodes(pts, True)
+    assert_same_tree(t, r)
+
+
+def test_dense_block_prunes_across_levels(octomap):
+    """A solid 32^3 block (4 bricks per axis... all saturated) collapses many levels; plus a shell of mixed values."""
+    g = (np.arange(32) + 0.5) * 0.1
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    for _ in range(6):   # saturate
+        t.updateNodes(pts, True)
+        r.updateNodes(pts, True)
+    t.updateNodes(pts[::7], False)
+    r.updateNodes(pts[::7], False)
+    assert_same_tree(t, r)
+    t2, r2 = octomap.OcTree(0.1), oo.OcTree(0.1)
+    for _ in range(6):
+        t2.updateNodes(pts, True)
+        r2.updateNodes(pts, True)
+    assert_same_tree(t2, r2)
+
+
+def test_per_point_api_mixed_sequence(octomap):
+    rng = np.random.default_rng(11)
+    pts = np.round(rng.uniform(-0.6, 0.6, size=(4000, 3)), 2)
+    occ = rng.random(4000) < 0.6
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    for p, o in zip(pts, occ):
+        t.updateNode(p, bool(o))
+        r.updateNode(p, bool(o))
+    assert_same_tree(t, r)
+
+
+def _scan(rng, n, origin, far=30.0):
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return origin + d * rng.uniform(0.0, far, size=(n, 1))
+
+
+@pytest.mark.parametrize("maxrange", [-1.0, 12.0])
+@pytest.mark.parametrize("res", [0.1, 0.05])
+def test_scan_delta_keys_bit_exact(octomap, maxrange, res):
+    rng = np.random.default_rng(21)
+    origin = np.array([0.31, -1.27, 0.55])
+    pts = _scan(rng, 3000, origin)
+    pts[:5] = origin                                     # zero-length rays
+    pts[5] = origin + [3.0, 0, 0]                         # axis aligned
+    pts[6] = origin + [0, -2.0, 0]
+    pts[7] = origin + [1e-4, 1e-4, 1e-4]
+    pts[8] = [5000.0, 0, 0]                               # out of bounds endpoint
+    t, r = octomap.OcTree(res), oo.OcTree(res)
+    rec = t.computeScanDelta(pts, origin, maxrange)
+    fk, ok = octomap.OcTree.deltaKeys(rec)
+    rf, ro = r.computeUpdate(pts.astype(np.float32), origin, maxrange)
+    assert np.array_equal(np.sort(oo.pack_keys(fk)), rf)
+    assert np.array_equal(np.sort(oo.pack_keys(ok)), ro)
+    assert t.numVoxels() == 0                             # computing a delta does not touch the tree
+
+
+def test_insert_point_cloud_sequence_matches_oracle(octomap):
+    rng = np.random.default_rng(22)
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    for s in range(8):
+        origin = np.array([0.4 * s, 0.1 * s, -0.05 * s])
+        pts = _scan(rng, 1500, origin, far=10.0)
+        mr = -1.0 if s % 2 else 6.0
+        t.insertPointCloud(pts, origin, maxrange=mr)
+        r.insertPointCloud(pts, origin, maxrange=mr)
+    assert_same_tree(t, r)
+
+
+def test_insert_point_cloud_discretize_and_oob_origin(octomap):
+    rng = np.random.default_rng(23)
+    origin = np.array([1.0, 1.0, 1.0])
+    pts = np.round(_scan(rng, 2000, origin, far=4.0), 1)
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    t.insertPointCloud(pts, origin, maxrange=-1.0, discretize=True)
+    r.insertPointCloud(pts, origin, maxrange=-1.0, discretize=True)
+    # sensor outside the map: no free cells, endpoints still occupied
+    t.insertPointCloud(pts[:100], np.array([9000.0, 0, 0]), maxrange=-1.0)
+    r.insertPointCloud(pts[:100], np.array([9000.0, 0, 0]), maxrange=-1.0)
+    t.insertPointCloud(np.zeros((0, 3)), origin)
+    assert_same_tree(t, r)
+
+
+def test_delta_export_apply_equals_insert(octomap):
+    rng = np.random.default_rng(24)
+    a, b, r = octomap.OcTree(0.1), octomap.OcTree(0.1), oo.OcTree(0.1)
+    for s in range(3):
+        origin = np.array([0.2 * s, 0.0, 0.0])
+        pts = _scan(rng, 2000, origin, far=8.0)
+        a.insertPointCloud(pts, origin, maxrange=5.0)
+        rec = b.computeScanDelta(pts, origin, maxrange=5.0)
+        b.applyDelta(rec)
+        r.insertPointCloud(pts, origin, maxrange=5.0)
+    assert a.writeBinary() == b.writeBinary()
+    ka, va = a.voxels()
+    kb, vb = b.voxels()
+    assert np.array_equal(ka, kb) and np.array_equal(va.view(np.uint32), vb.view(np.uint32))
+    assert_same_tree(b, r)
+
+
+def test_kitti_shape_scan_from_fused_points(octomap, r3d):
+    """Config-3 shape: one 1242x375 street frame -> K1 world points (float32) -> insertPointCloud @0.1 m / 80 m."""
+    ctx = r3d.default_context(0)
+    intr = po.KITTI_INTRINSICS
+    depth = po.synth_depth_u16(1242, 375, intr, 20261018 + 3, "street")
+    q, tr = po.synth_pose(2250, 4500)
+    rt = ctx.pose_to_rt(q, tr)
+    world, _ = ctx.backproject(depth, intr, rt=rt, depth_scale=1 / 256.0)
+    world = world[::3]                                   # keep the oracle run short (~1.5 s)
+    origin = po.camera_centre(rt[0, :9].reshape(3, 3), rt[0, 9:])
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    rec = t.computeScanDelta(world, origin, 80.0)
+    fk, ok = octomap.OcTree.deltaKeys(rec)
+    rf, ro = r.computeUpdate(world, origin, 80.0)
+    assert np.array_equal(np.sort(oo.pack_keys(fk)), rf)
+    assert np.array_equal(np.sort(oo.pack_keys(ok)), ro)
+    t.insertPointCloud(world, origin, maxrange=80.0)
+    r.insertPointCloud_f32(world, origin, 80.0)
+    assert_same_tree(t, r)
+
+
+def test_scratch_growth_on_wide_scan(octomap):
+    """A scan whose free space covers far more bricks than the initial scratch table: the table grows and re-casts."""
+    rng = np.random.default_rng(25)
+    origin = np.zeros(3)
+    pts = _scan(rng, 60000, origin, far=120.0)
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    rec = t.computeScanDelta(pts, origin, -1.0)
+    fk, ok = octomap.OcTree.deltaKeys(rec)
+    rf, ro = r.computeUpdate(pts.astype(np.float32), origin, -1.0)
+    assert np.array_equal(np.sort(oo.pack_keys(fk)), rf)
+    assert np.array_equal(np.sort(oo.pack_keys(ok)), ro)
+
+
+def test_dropped_points_and_device_buffers(octomap):
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(26)
+    pts = rng.uniform(-5, 5, size=(5000, 3)).astype(np.float32)
+    pts[:17, 0] = 4000.0
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    d = torch.from_numpy(pts).cuda()
+    t.updateNodes(d, True)
+    assert t.n_dropped == 17
+    r.updateNodes_f32(pts, True)
+    origin = np.array([0.0, 0.0, 0.0])
+    t.insertPointCloud(d[100:2000], origin, maxrange=4.0)
+    r.insertPointCloud_f32(pts[100:2000], origin, 4.0)
+    assert_same_tree(t, r)
