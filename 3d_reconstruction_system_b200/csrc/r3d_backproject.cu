@@ -408,7 +408,7 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
     }
     unsigned long long done = 0;
     if (bulk_ok && total >= K1_TILE) {
-        constexpr int kOutBufs = sizeof(OutT) == 4 ? 3 : 2;
+        constexpr int kOutBufs = 2;   // 2 x 12 KB (float): 46 KB per CTA -> 4 CTAs per SM
         a.n_tiles = total / K1_TILE;
         const size_t smem = 128 + table_bytes + (size_t)K1_STAGES * K1_TILE * sizeof(DepthT) +
                             (size_t)kOutBufs * K1_TILE * 3 * sizeof(OutT);
