@@ -157,6 +157,7 @@ __device__ __forceinline__ void delta_mark(const ScanArgs& a, int kx, int ky, in
 // computeUpdate (OccupancyOcTreeBase): per point, free cells along the ray, endpoint occupied when in range
 __global__ void __launch_bounds__(256) k_scan_raycast(const ScanArgs a) {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long steps = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
         float ex, ey, ez;
@@ -169,9 +170,14 @@ __global__ void __launch_bounds__(256) k_scan_raycast(const ScanArgs a) {
         Ray r;
         if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, ex, ey, ez, r) == 1) {
             delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur);
-            while (ray_step(r)) delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur);
+            ++steps;
+            while (ray_step(r)) { delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur); ++steps; }
         }
     }
+    // statistics only: free-cell visits of this scan
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+    if ((threadIdx.x & 31u) == 0 && steps)
+        atomicAdd(reinterpret_cast<unsigned long long*>(&a.counters[CNT_STEPS_LO]), steps);
 }
 
 // computeDiscreteUpdate's pre-pass: keep one voxel-centre point per distinct endpoint key
@@ -526,6 +532,8 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
         R3D_TRY(tree_set_counter(t, CNT_SCRATCH_USED, 0));
         R3D_TRY(tree_set_counter(t, CNT_DELTA, 0));
         R3D_TRY(tree_set_counter(t, CNT_DISCRETE, 0));
+        R3D_TRY(tree_set_counter(t, CNT_STEPS_LO, 0));
+        R3D_TRY(tree_set_counter(t, CNT_STEPS_HI, 0));
         bool overflow = false;
         if (discretize && n) {
             R3D_TRY(scratch_reserve(ctx, SCR_IN1, (size_t)n * 12 + 16));
@@ -552,6 +560,8 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
         }
         if (!overflow) {
             t->delta_n = t->h_counters[CNT_DELTA];
+            t->last_scan_rays = a.n;
+            t->last_scan_steps = (uint64_t)t->h_counters[CNT_STEPS_LO] | ((uint64_t)t->h_counters[CNT_STEPS_HI] << 32);
             return R3D_OK;
         }
         // table too small for this scan: grow, wipe, cast again (ray casting is a pure function of the scan)
@@ -710,6 +720,12 @@ extern "C" int r3d_delta_expand_keys(const void* records_host, uint64_t n_record
     }
     if (n_free) *n_free = nf;
     if (n_occ) *n_occ = no;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_last_scan_stats(r3d_tree* t, uint64_t out[4]) {
+    if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    out[0] = t->last_scan_rays; out[1] = t->last_scan_steps; out[2] = t->delta_n; out[3] = t->pool_used;
     return R3D_OK;
 }
 

@@ -16,7 +16,7 @@ struct DeltaRecord {
 static_assert(sizeof(DeltaRecord) == R3D_DELTA_RECORD_BYTES, "record layout is part of the ABI");
 
 // device counters of a tree
-enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_COUNT = 16 };
+enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_STEPS_LO, CNT_STEPS_HI, CNT_COUNT = 16 };
 
 }  // namespace r3d
 
@@ -40,6 +40,7 @@ struct r3d_tree {
     uint64_t scap = 0;
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
+    uint64_t last_scan_rays = 0, last_scan_steps = 0;
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};
 };

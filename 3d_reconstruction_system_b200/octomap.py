@@ -86,6 +86,12 @@ class OcTree:
             ptr, n = _ptr(pointcloud), int(pointcloud.shape[0])
         check(self._lib.r3d_tree_insert_scan(self._h, ptr, n, oa, float(maxrange), 1 if discretize else 0), self._ctx.handle)
 
+    def lastScanStats(self):
+        """dict(rays, steps, records, bricks) of the most recent insertPointCloud / computeScanDelta."""
+        a = (C.c_uint64 * 4)()
+        check(self._lib.r3d_tree_last_scan_stats(self._h, a), self._ctx.handle)
+        return {"rays": int(a[0]), "steps": int(a[1]), "records": int(a[2]), "bricks": int(a[3])}
+
     def updateInnerOccupancy(self):
         self._flush()
         check(self._lib.r3d_tree_update_inner_occupancy(self._h), self._ctx.handle)

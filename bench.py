@@ -197,6 +197,75 @@ def synth_on_device(torch, n_frames, rank, dev):
     return out.reshape(n_frames, H, W), q, t
 
 
+def octomap_cpu_baseline(world_pts, origin, maxrange, res):
+    """OctoMap scans/s on one host core: the C restatement (oracle/octomap_oracle.c) inserting one scan."""
+    from oracle import octomap_oracle as oo
+    tree = oo.OcTree(res)
+    t0 = time.perf_counter()
+    tree.insertPointCloud_f32(world_pts, origin, maxrange)
+    sec = time.perf_counter() - t0
+    return {"value": 1.0 / sec, "unit": "scans/s", "cores": 1, "kind": "port",
+            "sample": "1 scan of %d rays, C restatement of insertPointCloud (key sets + tree update), %.1f s" % (world_pts.shape[0], sec)}
+
+
+def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cpu):
+    """Second half of BASELINE.json's metric: OctoMap scans/s @0.1 m, max range 80 m (config 3).  Scans are the
+    world points of consecutive frames of the same sequence (K1 output, device resident); each scan is ray-cast
+    into a brick delta and applied in order.  Timed with CUDA events on the context stream."""
+    from oracle import points_oracle as po
+    octomap = importlib.import_module("3d_reconstruction_system_b200.octomap")
+    n_scans = min(n_scans, depth.shape[0])
+    f0 = depth.shape[0] // 2 - n_scans // 2          # middle of the trajectory: every key in range
+    world = torch.empty((n_scans * H * W, 3), dtype=torch.float32, device=dev)
+    rt = torch.from_numpy(rt_host[f0:f0 + n_scans].copy()).to(dev)
+    ctx.backproject(depth[f0:f0 + n_scans], po.KITTI_INTRINSICS, rt=rt, depth_scale=DEPTH_SCALE, out=world, shape=(n_scans, H, W),
+                    counts=np.zeros(n_scans, np.uint64))
+    origins = [po.camera_centre(rt_host[f0 + i, :9].reshape(3, 3), rt_host[f0 + i, 9:]) for i in range(n_scans)]
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    res, maxrange = 0.1, 80.0
+
+    def run(tree, count):
+        steps = rays = 0
+        for i in range(count):
+            tree.insertPointCloud(world[i * H * W:(i + 1) * H * W], origins[i], maxrange=maxrange)
+            st = tree.lastScanStats()
+            steps += st["steps"]
+            rays += st["rays"]
+        return steps, rays
+
+    warm = octomap.OcTree(res, ctx=ctx)
+    run(warm, min(3, n_scans))
+    del warm
+    tree = octomap.OcTree(res, ctx=ctx)
+    ctx.synchronize()
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    steps, rays = run(tree, n_scans)
+    e1.record(stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1)
+    t0 = time.perf_counter()
+    bt = tree.writeBinary()
+    bt_s = time.perf_counter() - t0
+    out = {"metric": "OctoMap scans/s @0.1 m (insertPointCloud, max range 80 m)", "value": n_scans / (ms * 1e-3), "unit": "scans/s",
+           "scans": n_scans, "rays_per_scan": rays // n_scans, "dda_steps_per_scan": steps // n_scans,
+           "rays_per_s": rays / (ms * 1e-3), "dda_steps_per_s": steps / (ms * 1e-3), "ms_per_scan": ms / n_scans,
+           "voxels": tree.numVoxels(), "bricks": tree.lastScanStats()["bricks"], "bt_bytes": len(bt), "bt_write_s": bt_s,
+           "gpu_launches": ctx.launch_count() - launches0,
+           "workload": "C3: %d consecutive KITTI-shape street scans (1242x375 rays each, Z=0 sky pixels included as rays to the sensor origin)" % n_scans}
+    if with_cpu:
+        w0 = world[:H * W].cpu().numpy()
+        out["cpu_baseline"] = octomap_cpu_baseline(w0, origins[0], maxrange, res)
+        # parity of what was timed: first scan's tree against the oracle
+        from oracle import octomap_oracle as oo
+        chk, ref = octomap.OcTree(res, ctx=ctx), oo.OcTree(res)
+        chk.insertPointCloud(world[:H * W], origins[0], maxrange=maxrange)
+        ref.insertPointCloud_f32(w0, origins[0], maxrange)
+        out["parity_bt_ok"] = bool(chk.writeBinary() == ref.write_binary_bytes())
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     r3d = importlib.import_module("3d_reconstruction_system_b200")
@@ -307,6 +376,12 @@ def run_gpu_arm(args):
     lib.r3d_host_free(h_in)
     lib.r3d_host_free(h_out)
 
+    octo = None
+    if world == 1 and args.octomap_scans > 0:
+        del out
+        torch.cuda.empty_cache()
+        octo = octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, args.octomap_scans, with_cpu=not args.no_cpu_baseline)
+
     if rank == 0:
         peak, peak_src = load_peaks()
         kernel_ms = float(np.mean(per_step))
@@ -328,7 +403,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k1_bulk<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
                          "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -344,6 +419,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--octomap-scans", type=int, default=32, help="scans for the OctoMap scans/s section (0 = skip)")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the 4500 of BASELINE config 2)")
     args = ap.parse_args()
     if args.impl == "reference":

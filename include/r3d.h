@@ -167,6 +167,10 @@ int r3d_tree_apply_delta(r3d_tree *tree, const void *records, uint64_t n_records
 int r3d_delta_expand_keys(const void *records_host, uint64_t n_records, uint16_t *free_keys, uint64_t free_cap,
                           uint64_t *n_free, uint16_t *occ_keys, uint64_t occ_cap, uint64_t *n_occ);
 
+/* Statistics of the last scan delta: out[0] rays cast, out[1] free-cell visits (DDA steps), out[2] delta records,
+ * out[3] bricks in the map. */
+int r3d_tree_last_scan_stats(r3d_tree *tree, uint64_t out[4]);
+
 /* tree.updateInnerOccupancy() (octomap/txt_transfer_octomap.py:35): inner values are derived on demand. */
 int r3d_tree_update_inner_occupancy(r3d_tree *tree);
 
