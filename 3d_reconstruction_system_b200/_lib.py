@@ -14,6 +14,7 @@ U8, U16, F32 = 0, 1, 2
 MODE_DEPTH, MODE_DISPARITY = 0, 1
 OUT_F32, OUT_F64 = 0, 1
 DELTA_RECORD_BYTES = 136
+BRICK_RECORD_BYTES = 2120
 
 _vp, _sz, _u64, _dbl, _flt, _i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_double, C.c_float, C.c_int
 _u64p = C.POINTER(C.c_uint64)
@@ -32,6 +33,9 @@ SIGNATURES = {
     "r3d_last_kernel_ms": (_flt, [_vp]),
     "r3d_host_alloc": (_vp, [_sz]),
     "r3d_host_free": (None, [_vp]),
+    "r3d_device_alloc": (_vp, [_vp, _sz]),
+    "r3d_device_free": (None, [_vp, _vp]),
+    "r3d_memcpy": (_i32, [_vp, _vp, _vp, _sz]),
     "r3d_pose_to_rt": (_i32, [_vp, _i32, _dbl, _vp]),
     "r3d_backproject_rt": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _vp, _vp]),
     "r3d_backproject": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _vp, _vp]),
@@ -48,6 +52,10 @@ SIGNATURES = {
     "r3d_scan_delta_compute": (_i32, [_vp, _vp, _u64, _vp, _dbl, _i32, _u64p]),
     "r3d_scan_delta_export": (_i32, [_vp, _vp, _u64, _u64p]),
     "r3d_tree_apply_delta": (_i32, [_vp, _vp, _u64]),
+    "r3d_tree_apply_delta_owned": (_i32, [_vp, _vp, _u64, C.c_uint32, C.c_uint32]),
+    "r3d_tree_num_bricks": (_i32, [_vp, _u64p]),
+    "r3d_tree_export_bricks": (_i32, [_vp, _vp, _u64, _u64p]),
+    "r3d_tree_import_bricks": (_i32, [_vp, _vp, _u64]),
     "r3d_delta_expand_keys": (_i32, [_vp, _u64, _vp, _u64, _u64p, _vp, _u64, _u64p]),
     "r3d_tree_last_scan_stats": (_i32, [_vp, _vp]),
     "r3d_tree_update_inner_occupancy": (_i32, [_vp]),

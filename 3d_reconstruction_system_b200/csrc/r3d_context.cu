@@ -156,3 +156,32 @@ extern "C" void* r3d_host_alloc(size_t bytes) {
 extern "C" void r3d_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+
+
+extern "C" void* r3d_device_alloc(r3d_ctx* ctx, size_t bytes) {
+    if (!ctx) { set_error(nullptr, R3D_ERR_ARG, "null context"); return nullptr; }
+    DeviceSetter ds(ctx->device);
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error(ctx, R3D_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void r3d_device_free(r3d_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    DeviceSetter ds(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+extern "C" int r3d_memcpy(r3d_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return set_error(nullptr, R3D_ERR_ARG, "null context");
+    if ((!dst || !src) && bytes) return set_error(ctx, R3D_ERR_ARG, "r3d_memcpy: null buffer");
+    if (!bytes) return R3D_OK;
+    DeviceSetter ds(ctx->device);
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return R3D_OK;
+}

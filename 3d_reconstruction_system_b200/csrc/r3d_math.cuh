@@ -171,6 +171,9 @@ R3D_HD uint64_t hash64(uint64_t x) {
     return x;
 }
 
+// which of `nparts` GPUs owns a brick (multi-GPU apply); high hash bits, the table slots use the low ones
+R3D_HD uint32_t brick_owner(uint64_t bk, uint32_t nparts) { return (uint32_t)((hash64(bk) >> 32) % nparts); }
+
 // ---------------------------------------------------------------- 3-D DDA (a11: computeRayKeys)
 // Mixed float / double exactly as upstream: direction, length, origin are float; tMax, tDelta and the voxel
 // border are double; the half-voxel offset is rounded through float.

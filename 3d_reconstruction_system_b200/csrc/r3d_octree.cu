@@ -229,10 +229,12 @@ __global__ void __launch_bounds__(256) k_scan_compact(uint64_t* skeys, uint32_t*
 // One warp per record.  Every brick appears once per delta, so the warp owns the brick's values for this launch.
 __global__ void __launch_bounds__(256) k_apply_delta(const DeltaRecord* __restrict__ recs, uint32_t n, uint64_t* tkeys,
                                                      uint32_t* tvals, uint64_t tcap, float* values, uint32_t* known,
-                                                     uint32_t* counters, float hit, float miss, float cmin, float cmax) {
+                                                     uint32_t* counters, float hit, float miss, float cmin, float cmax,
+                                                     uint32_t part, uint32_t nparts) {
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        if (nparts > 1 && brick_owner(recs[r].key, nparts) != part) continue;   // another GPU owns this brick
         uint32_t idx = 0;
         if (lane == 0) {
             bool inserted;
@@ -353,6 +355,41 @@ __global__ void k_to_max_likelihood(float* values, const uint32_t* known, uint64
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const uint32_t vox = (uint32_t)(i % kBrickVoxels);
         if (known[(i / kBrickVoxels) * 16 + (vox >> 5)] & (1u << (vox & 31u))) values[i] = values[i] >= thres ? cmax : cmin;
+    }
+}
+
+// pool -> brick records (key, 512 log-odds, 16 known words); one warp per brick
+__global__ void __launch_bounds__(256) k_export_bricks(const uint64_t* pool_keys, const float* values, const uint32_t* known,
+                                                       uint32_t n_bricks, BrickRecord* out) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_bricks; b += warps) {
+        if (lane == 0) out[b].key = pool_keys[b];
+        if (lane < 16) out[b].known[lane] = known[(size_t)b * 16 + lane];
+        for (uint32_t v = lane; v < kBrickVoxels; v += 32) out[b].value[v] = values[(size_t)b * kBrickVoxels + v];
+    }
+}
+
+// brick records -> store (known voxels of the record overwrite / create the local ones); one warp per record
+__global__ void __launch_bounds__(256) k_import_bricks(const BrickRecord* __restrict__ recs, uint32_t n, uint64_t* tkeys,
+                                                       uint32_t* tvals, uint64_t tcap, float* values, uint32_t* known,
+                                                       uint32_t* counters) {
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        uint32_t idx = 0;
+        if (lane == 0) {
+            bool inserted;
+            const uint64_t slot = table_find_or_insert(tkeys, tcap, recs[r].key, inserted);
+            if (slot == kNoSlot) { counters[CNT_OVERFLOW] = 1; idx = 0xffffffffu; }
+            else if (inserted) { idx = atomicAdd(&counters[CNT_POOL_USED], 1u); tvals[slot] = idx; }
+            else idx = tvals[slot];
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx == 0xffffffffu) continue;
+        for (uint32_t v = lane; v < kBrickVoxels; v += 32)
+            if (recs[r].known[v >> 5] & (1u << (v & 31u))) values[(size_t)idx * kBrickVoxels + v] = recs[r].value[v];
+        if (lane < 16) known[(size_t)idx * 16 + lane] |= recs[r].known[lane];
     }
 }
 
@@ -571,14 +608,14 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
     return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the scratch table");
 }
 
-static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n) {
+static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1) {
     r3d_ctx* ctx = t->ctx;
     if (n == 0) return R3D_OK;
     R3D_TRY(tree_reserve_table(t, (uint64_t)t->pool_used + n));
     R3D_TRY(tree_reserve_pool(t, (uint64_t)t->pool_used + n));
     R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
     k_apply_delta<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(d_recs, (uint32_t)n, t->tkeys, t->tvals, t->tcap, t->values, t->known,
-                                                                          t->counters, t->hit, t->miss, t->cmin, t->cmax);
+                                                                          t->counters, t->hit, t->miss, t->cmin, t->cmax, part, nparts);
     ctx->launches++;
     R3D_CUDA_OK(ctx, cudaGetLastError());
     R3D_TRY(tree_sync_counters(t));
@@ -685,6 +722,67 @@ extern "C" int r3d_tree_apply_delta(r3d_tree* t, const void* records, uint64_t n
     const DeltaRecord* d = reinterpret_cast<const DeltaRecord*>(records);
     if (n_records) R3D_TRY(stage_in(ctx, SCR_OUT0, reinterpret_cast<const DeltaRecord*>(records), (size_t)n_records, &d));
     R3D_TRY(apply_delta_impl(t, d, n_records));
+    return finish(ctx);
+}
+
+extern "C" int r3d_tree_apply_delta_owned(r3d_tree* t, const void* records, uint64_t n_records, uint32_t part, uint32_t nparts) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (!records && n_records) return set_error(ctx, R3D_ERR_ARG, "null records");
+    if (n_records > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "too many records");
+    if (nparts == 0 || part >= nparts) return set_error(ctx, R3D_ERR_ARG, "bad partition %u of %u", part, nparts);
+    DeviceSetter ds(ctx->device);
+    const DeltaRecord* d = reinterpret_cast<const DeltaRecord*>(records);
+    if (n_records) R3D_TRY(stage_in(ctx, SCR_OUT0, reinterpret_cast<const DeltaRecord*>(records), (size_t)n_records, &d));
+    R3D_TRY(apply_delta_impl(t, d, n_records, part, nparts));
+    return finish(ctx);
+}
+
+extern "C" int r3d_tree_num_bricks(r3d_tree* t, uint64_t* n) {
+    if (!t || !n) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    *n = t->pool_used;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_export_bricks(r3d_tree* t, void* records, uint64_t capacity, uint64_t* n) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (n) *n = t->pool_used;
+    if (t->pool_used > capacity) return set_error(ctx, R3D_ERR_ARG, "map has %u bricks, buffer holds %llu", t->pool_used, (unsigned long long)capacity);
+    if (t->pool_used == 0) return R3D_OK;
+    if (!records) return set_error(ctx, R3D_ERR_ARG, "null brick buffer");
+    DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_refresh_pool_keys(t));
+    const bool dev = is_device_ptr(records);
+    BrickRecord* d = reinterpret_cast<BrickRecord*>(records);
+    if (!dev) { R3D_TRY(scratch_reserve(ctx, SCR_OUT0, (size_t)t->pool_used * sizeof(BrickRecord))); d = (BrickRecord*)ctx->scratch[SCR_OUT0]; }
+    k_export_bricks<<<grid_for(ctx, (uint64_t)t->pool_used * 32, 256, 8), 256, 0, ctx->stream>>>(t->pool_keys, t->values, t->known, t->pool_used, d);
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    if (!dev) R3D_CUDA_OK(ctx, cudaMemcpyAsync(records, d, (size_t)t->pool_used * sizeof(BrickRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_import_bricks(r3d_tree* t, const void* records, uint64_t n_records) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (!records && n_records) return set_error(ctx, R3D_ERR_ARG, "null records");
+    if (n_records > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "too many records");
+    if (n_records == 0) return R3D_OK;
+    DeviceSetter ds(ctx->device);
+    const BrickRecord* d = reinterpret_cast<const BrickRecord*>(records);
+    R3D_TRY(stage_in(ctx, SCR_OUT0, reinterpret_cast<const BrickRecord*>(records), (size_t)n_records, &d));
+    R3D_TRY(tree_reserve_table(t, (uint64_t)t->pool_used + n_records));
+    R3D_TRY(tree_reserve_pool(t, (uint64_t)t->pool_used + n_records));
+    R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
+    k_import_bricks<<<grid_for(ctx, n_records * 32, 256, 8), 256, 0, ctx->stream>>>(d, (uint32_t)n_records, t->tkeys, t->tvals, t->tcap, t->values,
+                                                                               t->known, t->counters);
+    ctx->launches++;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    R3D_TRY(tree_sync_counters(t));
+    if (t->h_counters[CNT_OVERFLOW]) return set_error(ctx, R3D_ERR_STATE, "brick table overflow while importing bricks");
+    t->pool_used = t->h_counters[CNT_POOL_USED];
     return finish(ctx);
 }
 

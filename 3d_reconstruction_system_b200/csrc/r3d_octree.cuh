@@ -15,6 +15,14 @@ struct DeltaRecord {
 };
 static_assert(sizeof(DeltaRecord) == R3D_DELTA_RECORD_BYTES, "record layout is part of the ABI");
 
+// one whole brick of the map: see R3D_BRICK_RECORD_BYTES in r3d.h
+struct BrickRecord {
+    uint64_t key;
+    float value[512];
+    uint32_t known[16];
+};
+static_assert(sizeof(BrickRecord) == R3D_BRICK_RECORD_BYTES, "record layout is part of the ABI");
+
 // device counters of a tree
 enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_STEPS_LO, CNT_STEPS_HI, CNT_COUNT = 16 };
 

@@ -196,6 +196,21 @@ class OcTree:
         check(self._lib.r3d_scan_delta_export(self._h, rec.ctypes.data, cnt.value, C.byref(cnt)), self._ctx.handle)
         return rec[: cnt.value]
 
+    def computeScanDeltaOnDevice(self, pointcloud, origin, maxrange=-1.0, discretize=False):
+        """Ray-cast one scan into the tree's device-side delta buffer (no host copy); returns the record count.
+        Follow with scanDeltaInto(device_buffer, n)."""
+        self._flush()
+        o = np.asarray(origin, dtype=np.float64).astype(np.float32)
+        oa = (C.c_float * 3)(float(o[0]), float(o[1]), float(o[2]))
+        if isinstance(pointcloud, np.ndarray) or isinstance(pointcloud, (list, tuple)):
+            p = np.ascontiguousarray(np.asarray(pointcloud, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+            ptr, n = p.ctypes.data, p.shape[0]
+        else:
+            ptr, n = _ptr(pointcloud), int(pointcloud.shape[0])
+        cnt = C.c_uint64(0)
+        check(self._lib.r3d_scan_delta_compute(self._h, ptr, n, oa, float(maxrange), 1 if discretize else 0, C.byref(cnt)), self._ctx.handle)
+        return int(cnt.value)
+
     def scanDeltaInto(self, buf, capacity_records):
         """Export the last computed delta into a caller buffer (host array or device tensor); returns the record count."""
         cnt = C.c_uint64(0)
@@ -211,6 +226,46 @@ class OcTree:
         else:
             ptr, n = _ptr(records), int(n_records)
         check(self._lib.r3d_tree_apply_delta(self._h, ptr, n), self._ctx.handle)
+
+    def applyDeltaOwned(self, records, n_records, part, nparts):
+        """applyDelta restricted to the bricks owned by partition `part` of `nparts` (multi-GPU partitioned map)."""
+        self._flush()
+        if isinstance(records, np.ndarray):
+            records = np.ascontiguousarray(records, dtype=np.uint8)
+            ptr = records.ctypes.data
+        else:
+            ptr = _ptr(records)
+        check(self._lib.r3d_tree_apply_delta_owned(self._h, ptr, int(n_records), int(part), int(nparts)), self._ctx.handle)
+
+    BRICK_RECORD_BYTES = _lib.BRICK_RECORD_BYTES
+
+    def numBricks(self):
+        self._flush()
+        n = C.c_uint64(0)
+        check(self._lib.r3d_tree_num_bricks(self._h, C.byref(n)), self._ctx.handle)
+        return int(n.value)
+
+    def exportBricks(self, buf=None, capacity=None):
+        """Every brick of the map as 2120-byte records.  With no buffer: returns a (n, 2120) uint8 host array."""
+        self._flush()
+        n = self.numBricks()
+        cnt = C.c_uint64(0)
+        if buf is None:
+            rec = np.zeros((max(n, 1), _lib.BRICK_RECORD_BYTES), np.uint8)
+            check(self._lib.r3d_tree_export_bricks(self._h, rec.ctypes.data, n, C.byref(cnt)), self._ctx.handle)
+            return rec[:n]
+        check(self._lib.r3d_tree_export_bricks(self._h, _ptr(buf), int(n if capacity is None else capacity), C.byref(cnt)), self._ctx.handle)
+        return int(cnt.value)
+
+    def importBricks(self, records, n_records=None):
+        self._flush()
+        if isinstance(records, np.ndarray):
+            records = np.ascontiguousarray(records, dtype=np.uint8)
+            n = records.size // _lib.BRICK_RECORD_BYTES if n_records is None else int(n_records)
+            ptr = records.ctypes.data
+        else:
+            ptr, n = _ptr(records), int(n_records)
+        check(self._lib.r3d_tree_import_bricks(self._h, ptr, n), self._ctx.handle)
 
     @staticmethod
     def deltaKeys(records):

@@ -41,6 +41,80 @@ def _depth_code(x):
     raise TypeError("cannot infer depth dtype from %r" % name)
 
 
+class DeviceBuffer:
+    """A block of device memory owned by a Context (r3d_device_alloc): shape / dtype bookkeeping plus data_ptr(), so it
+    can be passed wherever the wrappers accept a device buffer.  Slicing along axis 0 gives a view."""
+
+    def __init__(self, ctx, shape, dtype, _base=None, _ptr=None):
+        self.ctx = ctx
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._base = _base
+        if _base is None:
+            self._p = ctx.lib.r3d_device_alloc(ctx.handle, self.nbytes)
+            if not self._p:
+                msg = ctx.lib.r3d_last_error(ctx.handle)
+                raise _lib.R3DError("r3d_device_alloc(%d) failed: %s" % (self.nbytes, msg.decode() if msg else "?"))
+        else:
+            self._p = _ptr
+
+    def data_ptr(self):
+        return self._p
+
+    def __getitem__(self, key):
+        if not isinstance(key, slice):
+            key = slice(int(key), int(key) + 1)
+            squeeze = True
+        else:
+            squeeze = False
+        a, b, step = key.indices(self.shape[0])
+        if step != 1:
+            raise ValueError("DeviceBuffer views are contiguous")
+        b = max(a, b)
+        row = self.nbytes // max(self.shape[0], 1)
+        shape = (b - a,) + self.shape[1:]
+        if squeeze:
+            shape = self.shape[1:]
+        return DeviceBuffer(self.ctx, shape, self.dtype, _base=self._base or self, _ptr=self._p + a * row)
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        n = int(np.prod(self.shape, dtype=np.int64))
+        shape = list(shape)
+        if -1 in shape:
+            i = shape.index(-1)
+            rest = int(np.prod([v for v in shape if v != -1], dtype=np.int64))
+            shape[i] = n // max(rest, 1)
+        if int(np.prod(shape, dtype=np.int64)) != n:
+            raise ValueError("cannot reshape %r to %r" % (self.shape, tuple(shape)))
+        return DeviceBuffer(self.ctx, shape, self.dtype, _base=self._base or self, _ptr=self._p)
+
+    def numpy(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        check(self.ctx.lib.r3d_memcpy(self.ctx.handle, out.ctypes.data, self._p, self.nbytes), self.ctx.handle)
+        return out
+
+    def copy_from(self, host):
+        h = np.ascontiguousarray(host, dtype=self.dtype)
+        if h.nbytes != self.nbytes:
+            raise ValueError("size mismatch")
+        check(self.ctx.lib.r3d_memcpy(self.ctx.handle, self._p, h.ctypes.data, self.nbytes), self.ctx.handle)
+        return self
+
+    def free(self):
+        if self._base is None and getattr(self, "_p", None) and getattr(self.ctx, "_h", None):
+            self.ctx.lib.r3d_device_free(self.ctx.handle, self._p)
+        self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Context:
     """r3d_ctx: one per GPU; not thread-safe (the reference is single-threaded, synchronous)."""
 
@@ -83,6 +157,13 @@ class Context:
     def last_kernel_ms(self):
         return float(self.lib.r3d_last_kernel_ms(self._h))
 
+    def device_empty(self, shape, dtype):
+        return DeviceBuffer(self, shape, dtype)
+
+    def to_device(self, host):
+        h = np.ascontiguousarray(host)
+        return DeviceBuffer(self, h.shape, h.dtype).copy_from(h)
+
     # ---- poses (scipy_transfer, transfer/camera_to_world.py:53-55)
     def pose_to_rt(self, quats, trans, t_scale=1.0):
         q = np.asarray(quats, dtype=np.float64).reshape(-1, 4)
@@ -112,6 +193,8 @@ class Context:
             depth = np.ascontiguousarray(depth)
         code = _depth_code(depth)
         out_np = np.dtype(out_dtype)
+        if out is not None and str(getattr(out, "dtype", "")).endswith("float64"):
+            out_np = np.dtype(np.float64)
         ocode = OUT_F32 if out_np == np.dtype(np.float32) else OUT_F64
         if rt is not None and _is_host(rt):
             rt = np.ascontiguousarray(rt, dtype=np.float64).reshape(n, 12)

@@ -66,6 +66,12 @@ float r3d_last_kernel_ms(r3d_ctx *ctx);
 /* Pinned host memory helpers (so callers can hand the library page-locked buffers). */
 void *r3d_host_alloc(size_t bytes);
 void r3d_host_free(void *p);
+/* Device memory of the context's GPU, for callers that keep intermediate results (e.g. the world points of a frame
+ * batch between back-projection and insertPointCloud) on the GPU.  r3d_memcpy copies between any two of host / device
+ * buffers on the context stream and blocks until done. */
+void *r3d_device_alloc(r3d_ctx *ctx, size_t bytes);
+void r3d_device_free(r3d_ctx *ctx, void *p);
+int r3d_memcpy(r3d_ctx *ctx, void *dst, const void *src, size_t bytes);
 
 /* ------------------------------------------------------------------ poses ------ */
 /*
@@ -163,6 +169,19 @@ int r3d_scan_delta_compute(r3d_tree *tree, const float *xyz, uint64_t n, const f
                            int discretize, uint64_t *n_records);
 int r3d_scan_delta_export(r3d_tree *tree, void *records, uint64_t capacity_records, uint64_t *n_records);
 int r3d_tree_apply_delta(r3d_tree *tree, const void *records, uint64_t n_records);
+/* Multi-GPU apply with the map partitioned by brick: only the records whose brick is owned by `part` of `nparts`
+ * (owner = (hash64(brick key) >> 32) mod nparts, hash64 = the murmur3 finaliser) are applied; the others are skipped. */
+int r3d_tree_apply_delta_owned(r3d_tree *tree, const void *records, uint64_t n_records, uint32_t part, uint32_t nparts);
+/*
+ * Whole-brick transfer between maps (merging the per-GPU pieces of a partitioned map, checkpointing):
+ * record layout (R3D_BRICK_RECORD_BYTES = 2120): uint64 brick key, 512 float32 log-odds (Morton order inside the
+ * brick, as in the delta masks), 16 x uint32 "known" mask.  Import creates missing bricks; voxels known in the record
+ * replace the local value.  Buffers may be host or device memory.
+ */
+#define R3D_BRICK_RECORD_BYTES 2120
+int r3d_tree_num_bricks(r3d_tree *tree, uint64_t *n);
+int r3d_tree_export_bricks(r3d_tree *tree, void *records, uint64_t capacity_records, uint64_t *n_records);
+int r3d_tree_import_bricks(r3d_tree *tree, const void *records, uint64_t n_records);
 /* Expand delta records to explicit OcTreeKeys (n x 3 uint16) for inspection / parity tests (host buffers). */
 int r3d_delta_expand_keys(const void *records_host, uint64_t n_records, uint16_t *free_keys, uint64_t free_cap,
                           uint64_t *n_free, uint16_t *occ_keys, uint64_t occ_cap, uint64_t *n_occ);
