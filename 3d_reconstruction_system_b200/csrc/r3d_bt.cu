@@ -332,6 +332,7 @@ static int tree_shape(r3d_tree* t, bool ml, uint64_t* n_nodes, std::vector<uint8
     r3d_ctx* ctx = t->ctx;
     *n_nodes = 0;
     if (payload) payload->clear();
+    R3D_TRY(tree_settle(t));
     const uint32_t nb = t->pool_used;
     if (nb == 0) return R3D_OK;
     R3D_TRY(tree_refresh_pool_keys(t));

@@ -225,6 +225,28 @@ R3D_HD bool ray_step(Ray& r) {
     if (dist > (double)r.length) return false;
     return true;
 }
+// The same walk in branch-free form for the ray-casting kernel (lanes of a warp pick different axes every step, so
+// per-axis branches would serialise).  ray_select picks the axis of the next step with upstream's comparison chain and
+// returns tMax of that axis, which IS min(tMax) -- the value upstream compares with the ray length after each step.
+//   first:  a = ray_select(r, t)                      (after ray_setup returned 1 and the origin key was recorded)
+//   loop:   ray_advance(r, a); if (ray_at_end(r)) stop; a = ray_select(r, t); if (t > length) stop; record key
+R3D_HD int ray_select(const Ray& r, double& tsel) {
+    const bool xy = r.tmx < r.tmy, xz = r.tmx < r.tmz, yz = r.tmy < r.tmz;
+    const bool selx = xy & xz, sely = (!xy) & yz;
+    tsel = selx ? r.tmx : (sely ? r.tmy : r.tmz);
+    return selx ? 0 : (sely ? 1 : 2);
+}
+R3D_HD void ray_advance(Ray& r, int axis) {
+    const double nx = dadd(r.tmx, r.tdx), ny = dadd(r.tmy, r.tdy), nz = dadd(r.tmz, r.tdz);
+    r.kx = (r.kx + (axis == 0 ? r.sx : 0)) & 0xffff;   // key_type is uint16: wraps like upstream
+    r.ky = (r.ky + (axis == 1 ? r.sy : 0)) & 0xffff;
+    r.kz = (r.kz + (axis == 2 ? r.sz : 0)) & 0xffff;
+    r.tmx = axis == 0 ? nx : r.tmx;
+    r.tmy = axis == 1 ? ny : r.tmy;
+    r.tmz = axis == 2 ? nz : r.tmz;
+}
+R3D_HD bool ray_at_end(const Ray& r) { return ((r.kx ^ r.ex) | (r.ky ^ r.ey) | (r.kz ^ r.ez)) == 0; }
+
 // computeUpdate's per-point prologue: decides whether the endpoint is an occupied cell and where the ray ends.
 // maxrange < 0: unlimited.  Returns true when the endpoint (px,py,pz) is within range (occupied candidate);
 // (ex,ey,ez) receives the ray end (the point itself, or origin + dir * maxrange).

@@ -127,57 +127,203 @@ struct ScanArgs {
     unsigned long long n;
     float ox, oy, oz;
     double maxrange, res, res_factor;
-    uint64_t* skeys;
+    uint64_t* skeys;    // hash mode: open-addressing table of brick keys (slot = table position)
+                        // dense mode: brick key of every allocated slot (slots handed out by a counter)
     uint32_t* smasks;   // per slot: 16 words occupied, 16 words free
     uint64_t scap;
     uint32_t* counters;
+    // dense mode: brick -> slot through a 3-D grid of (epoch << 24 | slot) words centred on the sensor origin
+    uint32_t* grid;
+    int gx0, gy0, gz0;  // brick coordinates of grid cell (0,0,0)
+    uint32_t gdim;      // cells per axis
+    uint32_t epoch;     // 1..255, bumped per scan: cells of older epochs read as empty, so the grid is never cleared
 };
 
-struct BrickCursor {
-    uint64_t bk = kEmptyKey;
-    uint64_t slot = kNoSlot;
-};
+// computeUpdate (OccupancyOcTreeBase): per point, free cells along the ray, endpoint occupied when in range.
+//
+// Persistent warps; every lane walks one ray at a time and idle lanes are re-filled from a global ray counter as soon
+// as K3_REFILL_MIN of them are idle (rays of one image differ in length by orders of magnitude: sky pixels walk 0
+// cells, far ground pixels ~1000).  The walk is the branch-free form of computeRayKeys (r3d_math.cuh).  Free cells are
+// collected in a 64-bit register mask per 4x4x4 sub-block (the depth-14 node: 64 consecutive Morton voxels = one
+// aligned 64-bit word of the brick's free mask) and written with ONE red.or when the ray leaves the sub-block; the
+// word's current value is fetched (L2) when the ray enters the sub-block and only consulted when it leaves, so the load
+// latency overlaps the walk, and the atomic is skipped when every bit is already set (128 M visits -> 10 M distinct
+// cells per scan).  Different lanes cross sub-block and brick borders at different steps, so that bookkeeping is
+// written with PREDICATED memory instructions instead of branches: some lane needs it on almost every iteration and a
+// divergent path would be executed by the whole warp every time.
+//
+// kDense: brick -> slot is one load from the epoch-tagged grid (bounded maxrange); otherwise the scratch hash table.
+constexpr int K3_THREADS = 256;
+constexpr int K3_REFILL_MIN = 8;
+constexpr uint32_t kSlotMask = 0xffffffu;
 
-__device__ __forceinline__ void delta_mark(const ScanArgs& a, int kx, int ky, int kz, int plane, BrickCursor& cur) {
-    const uint64_t bk = brick_key((uint32_t)kx, (uint32_t)ky, (uint32_t)kz);
-    if (bk != cur.bk) {
-        bool inserted;
-        cur.bk = bk;
-        cur.slot = table_find_or_insert(a.skeys, a.scap, bk, inserted);
-        if (inserted && atomicAdd(&a.counters[CNT_SCRATCH_USED], 1u) + 1u > (uint32_t)(a.scap / 2)) a.counters[CNT_OVERFLOW] = 1;
-        if (cur.slot == kNoSlot) a.counters[CNT_OVERFLOW] = 1;
-    }
-    if (cur.slot == kNoSlot) return;
-    const unsigned vox = brick_voxel_index((uint32_t)kx, (uint32_t)ky, (uint32_t)kz);
-    uint32_t* w = a.smasks + cur.slot * 32 + plane * 16 + (vox >> 5);
-    const uint32_t bit = 1u << (vox & 31u);
-    if (!(*w & bit)) atomicOr(w, bit);   // a stale (cached) 0 only costs a redundant atomic
+__device__ __forceinline__ void red_or_u64_if(uint64_t* p, uint64_t v, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.global.or.b64 [%0], %1;\n\t}" ::"l"(p), "l"(v), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ uint64_t ldcg_u64_if(const uint64_t* p, uint64_t otherwise, bool pred) {
+    uint64_t v = otherwise;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cg.u64 %0, [%1];\n\t}" : "+l"(v) : "l"(p), "r"((unsigned)pred) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ldcg_u32_if(const uint32_t* p, uint32_t otherwise, bool pred) {
+    uint32_t v = otherwise;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cg.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((unsigned)pred) : "memory");
+    return v;
 }
 
-// computeUpdate (OccupancyOcTreeBase): per point, free cells along the ray, endpoint occupied when in range
-__global__ void __launch_bounds__(256) k_scan_raycast(const ScanArgs a) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+// hash mode: slot of a brick in the scratch table (bounded probe length; a too-full table is grown by the host)
+// (arguments by value: taking the address of the kernel-parameter struct would spill it to local memory)
+__device__ __noinline__ uint32_t scratch_slot_hash(uint64_t* skeys, uint64_t scap, uint32_t* counters, uint64_t bk) {
+    const uint64_t mask = scap - 1;
+    uint64_t slot = hash64(bk) & mask;
+    for (int probe = 0; probe < 128; ++probe) {
+        const uint64_t k = ld_cg_u64(skeys + slot);
+        if (k == bk) return (uint32_t)slot;
+        if (k == kEmptyKey) {
+            const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(skeys + slot), kEmptyKey, bk);
+            if (old == kEmptyKey) {
+                if (atomicAdd(&counters[CNT_SCRATCH_USED], 1u) + 1u > (uint32_t)(scap / 2)) counters[CNT_OVERFLOW] = 1;
+                return (uint32_t)slot;
+            }
+            if (old == bk) return (uint32_t)slot;
+        }
+        slot = (slot + 1) & mask;
+    }
+    counters[CNT_OVERFLOW] = 1;
+    return 0xffffffffu;
+}
+
+// dense mode, first touch of a brick in this scan: take the next slot and publish it in the grid cell.  Losing the
+// publication race wastes the slot (its key stays empty and its masks zero, so compaction skips it).
+__device__ __noinline__ uint32_t scratch_slot_alloc(uint64_t* skeys, uint64_t scap, uint32_t* counters, uint32_t epoch, uint32_t* cell,
+                                                    uint32_t seen_entry, uint64_t bk) {
+    const uint32_t s = atomicAdd(&counters[CNT_SCRATCH_USED], 1u);
+    if (s >= scap || s > kSlotMask) { counters[CNT_OVERFLOW] = 1; return 0xffffffffu; }
+    skeys[s] = bk;
+    const uint32_t mine = (epoch << 24) | s;
+    const uint32_t old = atomicCAS(cell, seen_entry, mine);
+    if (old == seen_entry) return s;
+    skeys[s] = kEmptyKey;              // somebody else published first (only current-epoch values are ever written)
+    if ((old >> 24) == epoch) return old & kSlotMask;
+    counters[CNT_OVERFLOW] = 1;        // unreachable; forces a clean re-cast instead of a wrong map
+    return 0xffffffffu;
+}
+
+template <bool kDense>
+__device__ __forceinline__ uint32_t brick_slot(const ScanArgs& a, int kx, int ky, int kz, bool wanted) {
+    // `wanted` false: the caller keeps its old slot; nothing is touched
+    if (kDense) {
+        const uint32_t ux = (uint32_t)((kx >> 3) - a.gx0), uy = (uint32_t)((ky >> 3) - a.gy0), uz = (uint32_t)((kz >> 3) - a.gz0);
+        const bool inside = (ux < a.gdim) & (uy < a.gdim) & (uz < a.gdim);
+        uint32_t* cell = a.grid + ((size_t)uz * a.gdim + uy) * a.gdim + ux;
+        const uint32_t e = ldcg_u32_if(cell, a.epoch << 24, wanted & inside);
+        uint32_t slot = e & kSlotMask;
+        if (wanted && (!inside || (e >> 24) != a.epoch)) {          // rare: first touch of the brick, or outside the grid
+            if (!inside) { a.counters[CNT_GRID_MISS] = 1; slot = 0xffffffffu; }
+            else slot = scratch_slot_alloc(a.skeys, a.scap, a.counters, a.epoch, cell, e, brick_key((uint32_t)kx, (uint32_t)ky, (uint32_t)kz));
+        }
+        return slot;
+    } else {
+        uint32_t slot = 0xffffffffu;
+        if (wanted) slot = scratch_slot_hash(a.skeys, a.scap, a.counters, brick_key((uint32_t)kx, (uint32_t)ky, (uint32_t)kz));
+        return slot;
+    }
+}
+
+__device__ __forceinline__ uint64_t* free_word(const ScanArgs& a, uint32_t slot, int kx, int ky, int kz) {
+    const unsigned sub = (unsigned)((kx >> 2) & 1) | ((unsigned)((ky >> 2) & 1) << 1) | ((unsigned)((kz >> 2) & 1) << 2);
+    return reinterpret_cast<uint64_t*>(a.smasks + (size_t)slot * 32 + 16) + sub;
+}
+__device__ __forceinline__ uint64_t sub_bit(int kx, int ky, int kz) {
+    const unsigned x = kx & 3, y = ky & 3, z = kz & 3;
+    const unsigned bit = (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3) | ((z & 2u) << 4);
+    return 1ull << bit;
+}
+
+template <bool kDense>
+__global__ void __launch_bounds__(K3_THREADS) k_scan_raycast(const ScanArgs a, unsigned long long* ray_counter) {
+    const unsigned lane = threadIdx.x & 31u;
+    bool active = false, exhausted = false;
+    Ray r;
+    int axis = 0;
+    double length = 0.0;
+    // cursor: 64-bit free-mask word of the current sub-block
+    uint64_t* word = nullptr;
+    uint64_t seen = 0, mask = 0;
+    uint32_t slot = 0xffffffffu;
     unsigned long long steps = 0;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
-        float ex, ey, ez;
-        const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, ex, ey, ez);
-        BrickCursor occ_cur, free_cur;
-        if (in_range) {
-            uint16_t kx, ky, kz;
-            if (coord_to_key3(a.res_factor, px, py, pz, kx, ky, kz)) delta_mark(a, kx, ky, kz, 0, occ_cur);
+    for (;;) {
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const unsigned idle = ~act;
+        if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(idle) >= a.n) exhausted = true;
+            const unsigned long long i = base + __popc(idle & ((1u << lane) - 1u));
+            if (!active && i < a.n) {
+                const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
+                float ex, ey, ez;
+                const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, ex, ey, ez);
+                if (in_range) {
+                    uint16_t kx, ky, kz;
+                    if (coord_to_key3(a.res_factor, px, py, pz, kx, ky, kz)) {
+                        const uint32_t s = brick_slot<kDense>(a, kx, ky, kz, true);
+                        if (s != 0xffffffffu) {
+                            const unsigned vox = brick_voxel_index(kx, ky, kz);
+                            uint32_t* w = a.smasks + (size_t)s * 32 + (vox >> 5);
+                            const uint32_t bit = 1u << (vox & 31u);
+                            if (!(__ldcg(w) & bit)) atomicOr(w, bit);
+                        }
+                    }
+                }
+                if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, ex, ey, ez, r) == 1) {
+                    active = true;
+                    length = (double)r.length;
+                    // the origin cell is the first free cell
+                    slot = brick_slot<kDense>(a, r.kx, r.ky, r.kz, true);
+                    const bool ok = slot != 0xffffffffu;
+                    word = free_word(a, ok ? slot : 0u, r.kx, r.ky, r.kz);
+                    seen = ldcg_u64_if(word, ~0ull, ok);
+                    mask = sub_bit(r.kx, r.ky, r.kz);
+                    ++steps;
+                    double t;
+                    axis = ray_select(r, t);
+                }
+            }
+            continue;
         }
-        Ray r;
-        if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, ex, ey, ez, r) == 1) {
-            delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur);
-            ++steps;
-            while (ray_step(r)) { delta_mark(a, r.kx, r.ky, r.kz, 1, free_cur); ++steps; }
-        }
+        if (act == 0) break;   // no ray left anywhere in this warp
+        const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
+        do {
+            if (active) {
+                const int px = r.kx, py = r.ky, pz = r.kz;
+                ray_advance(r, axis);
+                double t;
+                axis = ray_select(r, t);
+                const bool done = ray_at_end(r) | (t > length);
+                const int diff = (r.kx ^ px) | (r.ky ^ py) | (r.kz ^ pz);
+                const bool new_sub = (diff >> 2) != 0;
+                // leave the sub-block (or the ray): publish its cells unless all of them were already set
+                red_or_u64_if(word, mask, (done | new_sub) & ((mask & ~seen) != 0));
+                const bool enter = new_sub & !done;
+                const uint32_t ns = brick_slot<kDense>(a, r.kx, r.ky, r.kz, enter & ((diff >> 3) != 0));
+                if (enter & ((diff >> 3) != 0)) slot = ns;
+                const bool ok = slot != 0xffffffffu;
+                if (enter) {
+                    word = free_word(a, ok ? slot : 0u, r.kx, r.ky, r.kz);
+                    mask = 0;
+                }
+                seen = ldcg_u64_if(word, enter ? ~0ull : seen, enter & ok);
+                mask |= sub_bit(r.kx, r.ky, r.kz);
+                steps += done ? 0u : 1u;
+                active = !done;
+            }
+        } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
     }
     // statistics only: free-cell visits of this scan
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
-    if ((threadIdx.x & 31u) == 0 && steps)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&a.counters[CNT_STEPS_LO]), steps);
+    if (lane == 0 && steps) atomicAdd(reinterpret_cast<unsigned long long*>(&a.counters[CNT_STEPS_LO]), steps);
 }
 
 // computeDiscreteUpdate's pre-pass: keep one voxel-centre point per distinct endpoint key
@@ -203,10 +349,12 @@ __global__ void k_scan_discretize(const ScanArgs a, float* out_xyz) {
 }
 
 // scratch table -> compact records (free already minus occupied); resets the slots it consumes.  One warp per slot.
+// dense: only the slots handed out by the counter are visited.
 __global__ void __launch_bounds__(256) k_scan_compact(uint64_t* skeys, uint32_t* smasks, uint64_t scap, DeltaRecord* out,
-                                                      uint32_t* counters, uint32_t out_cap) {
+                                                      uint32_t* counters, uint32_t out_cap, int dense) {
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (dense) { const uint64_t used = counters[CNT_SCRATCH_USED]; if (used < scap) scap = used; }
     for (uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < scap; s += warps) {
         const uint64_t k = skeys[s];
         if (k == kEmptyKey) continue;
@@ -239,7 +387,7 @@ __global__ void __launch_bounds__(256) k_apply_delta(const DeltaRecord* __restri
         if (lane == 0) {
             bool inserted;
             const uint64_t slot = table_find_or_insert(tkeys, tcap, recs[r].key, inserted);
-            if (slot == kNoSlot) { counters[CNT_OVERFLOW] = 1; idx = 0xffffffffu; }
+            if (slot == kNoSlot) { counters[CNT_APPLY_OVERFLOW] = 1; idx = 0xffffffffu; }
             else if (inserted) { idx = atomicAdd(&counters[CNT_POOL_USED], 1u); tvals[slot] = idx; }
             else idx = tvals[slot];
         }
@@ -407,6 +555,23 @@ int tree_sync_counters(r3d_tree* t) {
     R3D_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, t->counters, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(t->h_counters, ctx->pinned, CNT_COUNT * sizeof(uint32_t));
+    // the read-back is ordered after every queued kernel of the stream, so the mirror is exact again
+    t->pool_used = t->h_counters[CNT_POOL_USED];
+    t->pool_bound = t->pool_used;
+    t->pool_dirty = false;
+    if (t->h_counters[CNT_APPLY_OVERFLOW]) return set_error(ctx, R3D_ERR_STATE, "brick table overflow while applying a delta (internal sizing error)");
+    return R3D_OK;
+}
+
+int tree_settle(r3d_tree* t) {
+    if (!t->pool_dirty) return R3D_OK;
+    return tree_sync_counters(t);
+}
+
+// zero every per-scan counter with one memset (everything but the pool cursor and the sticky apply-overflow flag)
+static int tree_reset_scan_counters(r3d_tree* t) {
+    r3d_ctx* ctx = t->ctx;
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + 1, 0, (CNT_APPLY_OVERFLOW - 1) * sizeof(uint32_t), ctx->stream));
     return R3D_OK;
 }
 
@@ -524,6 +689,7 @@ static int update_points_impl(r3d_tree* t, const T* xyz, uint64_t n, float upd, 
     r3d_ctx* ctx = t->ctx;
     if (!xyz && n) return set_error(ctx, R3D_ERR_ARG, "null points");
     DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_settle(t));
     uint64_t dropped_total = 0;
     const uint64_t chunk = 1ull << 22;
     const bool dev = n ? is_device_ptr(xyz) : true;
@@ -551,6 +717,43 @@ static int update_points_impl(r3d_tree* t, const T* xyz, uint64_t n, float upd, 
     return finish(ctx);
 }
 
+// Grid geometry for the dense brick lookup.  Returns non-zero when the scan cannot use it (reach too large, origin not
+// finite): the hash table serves those.
+static int discretize_blocks_dense(r3d_tree* t, const float origin[3], double maxrange, int* gx0, int* gy0, int* gz0, uint32_t* gdim) {
+    const double reach_vox = ceil(maxrange * t->res_factor) + 4.0;     // the DDA may overshoot the range by a cell or two
+    if (!(reach_vox < 8.0 * 400.0)) return 1;
+    const int reach = (int)(reach_vox / 8.0) + 2;
+    int o[3];
+    for (int i = 0; i < 3; ++i) {
+        const double f = floor(t->res_factor * (double)origin[i]);
+        if (!(f > -1e9 && f < 1e9)) return 1;
+        o[i] = (((int)f + r3d::kTreeMaxVal) >> 3) - reach;
+    }
+    *gx0 = o[0]; *gy0 = o[1]; *gz0 = o[2];
+    *gdim = (uint32_t)(2 * reach + 1);
+    return 0;
+}
+
+// grid storage for `gdim`^3 cells and a fresh epoch (cells written in older epochs read as empty)
+static int tree_grid_prepare(r3d_tree* t, uint32_t gdim) {
+    r3d_ctx* ctx = t->ctx;
+    const uint64_t cells = (uint64_t)gdim * gdim * gdim;
+    if (cells > t->sgrid_cells) {
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(t->sgrid);
+        t->sgrid = nullptr; t->sgrid_cells = 0;
+        R3D_CUDA_OK(ctx, cudaMalloc(&t->sgrid, cells * sizeof(uint32_t)));
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->sgrid, 0, cells * sizeof(uint32_t), ctx->stream));
+        t->sgrid_cells = cells;
+        t->epoch = 0;
+    }
+    if (++t->epoch > 255u) {
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->sgrid, 0, t->sgrid_cells * sizeof(uint32_t), ctx->stream));
+        t->epoch = 1;
+    }
+    return R3D_OK;
+}
+
 // ray-cast one scan into the scratch table and compact it into t->delta (t->delta_n records)
 static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const float origin[3], double maxrange, int discretize) {
     r3d_ctx* ctx = t->ctx;
@@ -559,18 +762,19 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
     const float* d = xyz;
     if (n) R3D_TRY(stage_in(ctx, SCR_IN0, xyz, (size_t)n * 3, &d));
     R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
-    for (int attempt = 0; attempt < 12; ++attempt) {
+    // dense brick lookup when the scan's reach is bounded: grid of (2*reach+1)^3 cells centred on the origin's brick
+    bool dense = false;
+    int gx0 = 0, gy0 = 0, gz0 = 0;
+    uint32_t gdim = 0;
+    if (maxrange >= 0.0 && !discretize_blocks_dense(t, origin, maxrange, &gx0, &gy0, &gz0, &gdim)) dense = true;
+    for (int attempt = 0; attempt < 14; ++attempt) {
         ScanArgs a;
         a.xyz = d; a.n = n;
         a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
         a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
         a.skeys = t->skeys; a.smasks = t->smasks; a.scap = t->scap; a.counters = t->counters;
-        R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
-        R3D_TRY(tree_set_counter(t, CNT_SCRATCH_USED, 0));
-        R3D_TRY(tree_set_counter(t, CNT_DELTA, 0));
-        R3D_TRY(tree_set_counter(t, CNT_DISCRETE, 0));
-        R3D_TRY(tree_set_counter(t, CNT_STEPS_LO, 0));
-        R3D_TRY(tree_set_counter(t, CNT_STEPS_HI, 0));
+        a.grid = nullptr; a.gx0 = gx0; a.gy0 = gy0; a.gz0 = gz0; a.gdim = gdim; a.epoch = 0;
+        R3D_TRY(tree_reset_scan_counters(t));
         bool overflow = false;
         if (discretize && n) {
             R3D_TRY(scratch_reserve(ctx, SCR_IN1, (size_t)n * 12 + 16));
@@ -583,17 +787,35 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
             a.xyz = (const float*)ctx->scratch[SCR_IN1];
             a.n = t->h_counters[CNT_DISCRETE];
         }
+        if (!overflow && dense) {
+            R3D_TRY(tree_grid_prepare(t, gdim));
+            a.grid = t->sgrid;
+            a.epoch = t->epoch;
+        }
         if (!overflow && a.n) {
-            k_scan_raycast<<<grid_for(ctx, a.n, 256, 8), 256, 0, ctx->stream>>>(a);
+            // persistent warps pulling rays from a counter (slot CNT_RAY_LO/HI of the tree's counter block, zeroed above)
+            unsigned long long* ray_counter = reinterpret_cast<unsigned long long*>(&t->counters[CNT_RAY_LO]);
+            if (t->raycast_blocks_per_sm == 0) {
+                int per_sm = 0;
+                R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_raycast<true>, K3_THREADS, 0));
+                t->raycast_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
+            }
+            unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
+            const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
+            if (blocks > need) blocks = need;
+            if (dense) k_scan_raycast<true><<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
+            else k_scan_raycast<false><<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
             ctx->launches++;
         }
+        bool grid_miss = false;
         if (!overflow) {
             k_scan_compact<<<grid_for(ctx, t->scap * 32, 256, 8), 256, 0, ctx->stream>>>(t->skeys, t->smasks, t->scap, t->delta, t->counters,
-                                                                                      (uint32_t)t->delta_cap);
+                                                                                      (uint32_t)t->delta_cap, dense ? 1 : 0);
             ctx->launches++;
             R3D_CUDA_OK(ctx, cudaGetLastError());
             R3D_TRY(tree_sync_counters(t));
-            overflow = t->h_counters[CNT_OVERFLOW] != 0 || t->h_counters[CNT_DELTA] > t->delta_cap;
+            grid_miss = dense && t->h_counters[CNT_GRID_MISS] != 0;
+            overflow = t->h_counters[CNT_OVERFLOW] != 0 || t->h_counters[CNT_DELTA] > t->delta_cap || grid_miss;
         }
         if (!overflow) {
             t->delta_n = t->h_counters[CNT_DELTA];
@@ -601,8 +823,10 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
             t->last_scan_steps = (uint64_t)t->h_counters[CNT_STEPS_LO] | ((uint64_t)t->h_counters[CNT_STEPS_HI] << 32);
             return R3D_OK;
         }
-        // table too small for this scan: grow, wipe, cast again (ray casting is a pure function of the scan)
-        R3D_TRY(tree_reserve_scratch(t, t->scap * 4));
+        // table too small for this scan (or a ray left the grid): grow / switch to the hash table, wipe, cast again
+        // (ray casting is a pure function of the scan)
+        if (grid_miss) dense = false;
+        else R3D_TRY(tree_reserve_scratch(t, t->scap * 4));
         R3D_TRY(tree_reset_scratch(t));
     }
     return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the scratch table");
@@ -611,16 +835,15 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
 static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1) {
     r3d_ctx* ctx = t->ctx;
     if (n == 0) return R3D_OK;
-    R3D_TRY(tree_reserve_table(t, (uint64_t)t->pool_used + n));
-    R3D_TRY(tree_reserve_pool(t, (uint64_t)t->pool_used + n));
-    R3D_TRY(tree_set_counter(t, CNT_OVERFLOW, 0));
+    // sized from the host-side upper bound of the pool cursor: no read-back between a scan's apply and the next scan
+    R3D_TRY(tree_reserve_table(t, t->pool_bound + n));
+    R3D_TRY(tree_reserve_pool(t, t->pool_bound + n));
     k_apply_delta<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(d_recs, (uint32_t)n, t->tkeys, t->tvals, t->tcap, t->values, t->known,
                                                                           t->counters, t->hit, t->miss, t->cmin, t->cmax, part, nparts);
     ctx->launches++;
     R3D_CUDA_OK(ctx, cudaGetLastError());
-    R3D_TRY(tree_sync_counters(t));
-    if (t->h_counters[CNT_OVERFLOW]) return set_error(ctx, R3D_ERR_STATE, "brick table overflow while applying a delta");
-    t->pool_used = t->h_counters[CNT_POOL_USED];
+    t->pool_bound += n;
+    t->pool_dirty = true;
     return R3D_OK;
 }
 
@@ -658,7 +881,7 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     DeviceSetter ds(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
-    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
+    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters); cudaFree(t->sgrid);
     delete t;
 }
 
@@ -671,6 +894,8 @@ extern "C" int r3d_tree_clear(r3d_tree* t) {
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->known, 0, t->pool_cap * 16 * sizeof(uint32_t), ctx->stream));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters, 0, CNT_COUNT * sizeof(uint32_t), ctx->stream));
     t->pool_used = 0;
+    t->pool_bound = 0;
+    t->pool_dirty = false;
     t->delta_n = 0;
     return finish(ctx);
 }
@@ -740,6 +965,8 @@ extern "C" int r3d_tree_apply_delta_owned(r3d_tree* t, const void* records, uint
 
 extern "C" int r3d_tree_num_bricks(r3d_tree* t, uint64_t* n) {
     if (!t || !n) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    DeviceSetter ds(t->ctx->device);
+    R3D_TRY(tree_settle(t));
     *n = t->pool_used;
     return R3D_OK;
 }
@@ -747,6 +974,7 @@ extern "C" int r3d_tree_num_bricks(r3d_tree* t, uint64_t* n) {
 extern "C" int r3d_tree_export_bricks(r3d_tree* t, void* records, uint64_t capacity, uint64_t* n) {
     if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
     r3d_ctx* ctx = t->ctx;
+    { DeviceSetter ds0(ctx->device); R3D_TRY(tree_settle(t)); }
     if (n) *n = t->pool_used;
     if (t->pool_used > capacity) return set_error(ctx, R3D_ERR_ARG, "map has %u bricks, buffer holds %llu", t->pool_used, (unsigned long long)capacity);
     if (t->pool_used == 0) return R3D_OK;
@@ -772,6 +1000,7 @@ extern "C" int r3d_tree_import_bricks(r3d_tree* t, const void* records, uint64_t
     if (n_records == 0) return R3D_OK;
     DeviceSetter ds(ctx->device);
     const BrickRecord* d = reinterpret_cast<const BrickRecord*>(records);
+    R3D_TRY(tree_settle(t));
     R3D_TRY(stage_in(ctx, SCR_OUT0, reinterpret_cast<const BrickRecord*>(records), (size_t)n_records, &d));
     R3D_TRY(tree_reserve_table(t, (uint64_t)t->pool_used + n_records));
     R3D_TRY(tree_reserve_pool(t, (uint64_t)t->pool_used + n_records));
@@ -836,6 +1065,7 @@ extern "C" int r3d_tree_to_max_likelihood(r3d_tree* t) {
     if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
     r3d_ctx* ctx = t->ctx;
     DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_settle(t));
     const uint64_t total = (uint64_t)t->pool_used * kBrickVoxels;
     if (total) {
         k_to_max_likelihood<<<grid_for(ctx, total), 256, 0, ctx->stream>>>(t->values, t->known, total, t->occ_thres, t->cmin, t->cmax);
@@ -849,6 +1079,7 @@ extern "C" int r3d_tree_num_voxels(r3d_tree* t, uint64_t* n) {
     if (!t || !n) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
     r3d_ctx* ctx = t->ctx;
     DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_settle(t));
     R3D_TRY(scratch_reserve(ctx, SCR_MISC, 64));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->scratch[SCR_MISC], 0, 8, ctx->stream));
     const uint64_t words = (uint64_t)t->pool_used * 16;
@@ -889,6 +1120,7 @@ extern "C" int r3d_tree_export_voxels(r3d_tree* t, uint16_t* keys, float* values
     if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
     r3d_ctx* ctx = t->ctx;
     DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_settle(t));
     R3D_TRY(tree_refresh_pool_keys(t));
     R3D_TRY(scratch_reserve(ctx, SCR_MISC, 64));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->scratch[SCR_MISC], 0, 8, ctx->stream));

@@ -24,7 +24,8 @@ struct BrickRecord {
 static_assert(sizeof(BrickRecord) == R3D_BRICK_RECORD_BYTES, "record layout is part of the ABI");
 
 // device counters of a tree
-enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_STEPS_LO, CNT_STEPS_HI, CNT_COUNT = 16 };
+enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_STEPS_LO, CNT_STEPS_HI, CNT_RAY_LO, CNT_RAY_HI, CNT_GRID_MISS,
+       CNT_APPLY_OVERFLOW = 15 /* sticky, outside the per-scan reset range */, CNT_COUNT = 16 };
 
 }  // namespace r3d
 
@@ -39,13 +40,19 @@ struct r3d_tree {
     float* values = nullptr;      // [pool_cap][512] log-odds, Morton order inside the brick
     uint32_t* known = nullptr;    // [pool_cap][16]  voxel was updated at least once (node exists)
     uint64_t pool_cap = 0;
-    uint32_t pool_used = 0;       // host mirror of counters[CNT_POOL_USED]
+    uint32_t pool_used = 0;       // host mirror of counters[CNT_POOL_USED] as of the last counter read-back
+    uint64_t pool_bound = 0;      // upper bound of the device value once every queued apply has run
+    bool pool_dirty = false;      // applies were queued since the last read-back: call tree_settle before using pool_used
+    int raycast_blocks_per_sm = 0;
     uint64_t* pool_keys = nullptr; // [pool_cap] brick key per pool entry, rebuilt from the table on demand
     uint64_t pool_keys_cap = 0;
     // per-scan scratch table + compacted delta
     uint64_t* skeys = nullptr;
     uint32_t* smasks = nullptr;
     uint64_t scap = 0;
+    uint32_t* sgrid = nullptr;    // dense brick -> slot lookup of the ray caster: (epoch << 24 | slot) per cell
+    uint64_t sgrid_cells = 0;
+    uint32_t epoch = 0;
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
@@ -55,5 +62,6 @@ struct r3d_tree {
 
 namespace r3d {
 int tree_sync_counters(r3d_tree* t);
+int tree_settle(r3d_tree* t);   // pool_used exact again (reads the counters back if applies are pending)
 int tree_refresh_pool_keys(r3d_tree* t);
 }  // namespace r3d

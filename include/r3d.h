@@ -187,7 +187,7 @@ int r3d_delta_expand_keys(const void *records_host, uint64_t n_records, uint16_t
                           uint64_t *n_free, uint16_t *occ_keys, uint64_t occ_cap, uint64_t *n_occ);
 
 /* Statistics of the last scan delta: out[0] rays cast, out[1] free-cell visits (DDA steps), out[2] delta records,
- * out[3] bricks in the map. */
+ * out[3] bricks in the map as of the last counter read-back (r3d_tree_num_bricks is exact). */
 int r3d_tree_last_scan_stats(r3d_tree *tree, uint64_t out[4]);
 
 /* tree.updateInnerOccupancy() (octomap/txt_transfer_octomap.py:35): inner values are derived on demand. */

@@ -21,6 +21,27 @@ long hm_ray_keys(double res, const float* o, const float* e, uint16_t* out, long
     } while (ray_step(r));
     return n;
 }
+// the branch-free walk the ray-casting kernel uses (ray_select / ray_advance): must list the same keys
+long hm_ray_keys_predicated(double res, const float* o, const float* e, uint16_t* out, long cap) {
+    Ray r;
+    const int st = ray_setup(res, 1.0 / res, o[0], o[1], o[2], e[0], e[1], e[2], r);
+    if (st < 0) return -1;
+    if (st == 0) return 0;
+    long n = 0;
+    if (n < cap) { out[0] = (uint16_t)r.kx; out[1] = (uint16_t)r.ky; out[2] = (uint16_t)r.kz; }
+    ++n;
+    double t;
+    int a = ray_select(r, t);
+    for (;;) {
+        ray_advance(r, a);
+        if (ray_at_end(r)) break;
+        a = ray_select(r, t);
+        if (t > (double)r.length) break;
+        if (n < cap) { out[3 * n] = (uint16_t)r.kx; out[3 * n + 1] = (uint16_t)r.ky; out[3 * n + 2] = (uint16_t)r.kz; }
+        ++n;
+    }
+    return n;
+}
 int hm_scan_point_end(const float* o, const float* p, double maxrange, float* e) {
     return scan_point_end(o[0], o[1], o[2], p[0], p[1], p[2], maxrange, e[0], e[1], e[2]) ? 1 : 0;
 }
