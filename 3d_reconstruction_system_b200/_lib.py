@@ -44,6 +44,7 @@ SIGNATURES = {
     "r3d_tree_create": (_i32, [_vp, _dbl, C.POINTER(_vp)]),
     "r3d_tree_destroy": (None, [_vp]),
     "r3d_tree_clear": (_i32, [_vp]),
+    "r3d_tree_reserve": (_i32, [_vp, _u64]),
     "r3d_tree_params": (_i32, [_vp, _vp]),
     "r3d_tree_update_points": (_i32, [_vp, _vp, _u64, _i32, _u64p]),
     "r3d_tree_update_points_f64": (_i32, [_vp, _vp, _u64, _i32, _u64p]),

@@ -23,6 +23,12 @@ struct r3d_ctx {
     // reusable device scratch (grown on demand, freed in r3d_destroy)
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // direct-mapped scratch of the ray caster (dense mode): 32 mask words per brick cell + touched bitmap; zero between scans
+    uint32_t* cell_masks = nullptr;
+    uint32_t* cell_touched = nullptr;
+    uint64_t cell_cap = 0;
+    bool cells_dirty = false;
+    uint64_t cell_budget_bytes = 16ull << 30;   // larger grids use the hash table (R3D_SCAN_SCRATCH_GB overrides)
     void* pinned = nullptr;          // small pinned mailbox for counters read back from the device
     size_t pinned_bytes = 0;
 };

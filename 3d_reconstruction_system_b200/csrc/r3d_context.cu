@@ -1,4 +1,6 @@
 // r3d_context.cu -- context lifetime, error text, scratch memory, pointer classification.
+#include <stdlib.h>
+
 #include "r3d_common.cuh"
 
 namespace r3d {
@@ -97,6 +99,10 @@ extern "C" r3d_ctx* r3d_create(int device) {
              cudaEventCreateWithFlags(&ctx->stage_done[s], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
+    if (const char* gb = getenv("R3D_SCAN_SCRATCH_GB")) {
+        const double v = atof(gb);
+        if (v >= 0) ctx->cell_budget_bytes = (uint64_t)(v * (double)(1ull << 30));
+    }
     ctx->pinned_bytes = 4096;
     ok = ok && cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault) == cudaSuccess;
     if (!ok) {
@@ -112,6 +118,8 @@ extern "C" void r3d_destroy(r3d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < SCR_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    if (ctx->cell_masks) cudaFree(ctx->cell_masks);
+    if (ctx->cell_touched) cudaFree(ctx->cell_touched);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

@@ -121,22 +121,25 @@ __global__ void k_points_update(const T* __restrict__ xyz, unsigned long long n,
     }
 }
 
-// ------------------------------------------------------------------ K3: per-scan ray casting into the delta table
+// ------------------------------------------------------------------ K3: per-scan ray casting into the scan delta
 struct ScanArgs {
     const float* xyz;
     unsigned long long n;
     float ox, oy, oz;
     double maxrange, res, res_factor;
-    uint64_t* skeys;    // hash mode: open-addressing table of brick keys (slot = table position)
-                        // dense mode: brick key of every allocated slot (slots handed out by a counter)
+    // hash mode (unbounded reach): open-addressing table of brick keys; the masks of a brick sit at its table position
+    uint64_t* skeys;
     uint32_t* smasks;   // per slot: 16 words occupied, 16 words free
     uint64_t scap;
     uint32_t* counters;
-    // dense mode: brick -> slot through a 3-D grid of (epoch << 24 | slot) words centred on the sensor origin
-    uint32_t* grid;
-    int gx0, gy0, gz0;  // brick coordinates of grid cell (0,0,0)
+    // dense mode (bounded reach): the masks are direct-mapped -- cell (cx, cy, cz) of a gdim^3 grid of bricks centred on
+    // the sensor origin owns words [32 * cell, 32 * cell + 32) of `cmasks`; `ctouched` has one bit per cell that holds
+    // anything, so that only touched cells are read back.  No lookup structure, no allocation, no dependent loads.
+    uint32_t* cmasks;
+    uint32_t* ctouched;
+    int gx0, gy0, gz0;  // brick coordinates of cell (0,0,0)
     uint32_t gdim;      // cells per axis
-    uint32_t epoch;     // 1..255, bumped per scan: cells of older epochs read as empty, so the grid is never cleared
+    uint32_t gcells;    // gdim^3
 };
 
 // computeUpdate (OccupancyOcTreeBase): per point, free cells along the ray, endpoint occupied when in range.
@@ -149,29 +152,208 @@ struct ScanArgs {
 // word's current value is fetched (L2) when the ray enters the sub-block and only consulted when it leaves, so the load
 // latency overlaps the walk, and the atomic is skipped when every bit is already set (128 M visits -> 10 M distinct
 // cells per scan).  Different lanes cross sub-block and brick borders at different steps, so that bookkeeping is
-// written with PREDICATED memory instructions instead of branches: some lane needs it on almost every iteration and a
-// divergent path would be executed by the whole warp every time.
-//
-// kDense: brick -> slot is one load from the epoch-tagged grid (bounded maxrange); otherwise the scratch hash table.
+// written without divergent slow paths: some lane needs it on almost every iteration.
 constexpr int K3_THREADS = 256;
 constexpr int K3_REFILL_MIN = 8;
-constexpr uint32_t kSlotMask = 0xffffffu;
 
-__device__ __forceinline__ void red_or_u64_if(uint64_t* p, uint64_t v, bool pred) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.global.or.b64 [%0], %1;\n\t}" ::"l"(p), "l"(v), "r"((unsigned)pred) : "memory");
-}
 __device__ __forceinline__ uint64_t ldcg_u64_if(const uint64_t* p, uint64_t otherwise, bool pred) {
     uint64_t v = otherwise;
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cg.u64 %0, [%1];\n\t}" : "+l"(v) : "l"(p), "r"((unsigned)pred) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t ldcg_u32_if(const uint32_t* p, uint32_t otherwise, bool pred) {
-    uint32_t v = otherwise;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.cg.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"((unsigned)pred) : "memory");
-    return v;
+__device__ __forceinline__ unsigned sub_index(int kx, int ky, int kz) {
+    return (unsigned)((kx >> 2) & 1) | ((unsigned)((ky >> 2) & 1) << 1) | ((unsigned)((kz >> 2) & 1) << 2);
+}
+__device__ __forceinline__ uint64_t sub_bit(int kx, int ky, int kz) {
+    const unsigned x = kx & 3, y = ky & 3, z = kz & 3;
+    const unsigned bit = (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3) | ((z & 2u) << 4);
+    return 1ull << bit;
 }
 
-// hash mode: slot of a brick in the scratch table (bounded probe length; a too-full table is grown by the host)
+// ---- dense mode
+__device__ __forceinline__ bool cell_of_key(const ScanArgs& a, int kx, int ky, int kz, uint32_t& cell) {
+    const uint32_t ux = (uint32_t)((kx >> 3) - a.gx0), uy = (uint32_t)((ky >> 3) - a.gy0), uz = (uint32_t)((kz >> 3) - a.gz0);
+    cell = (uz * a.gdim + uy) * a.gdim + ux;
+    return (ux < a.gdim) & (uy < a.gdim) & (uz < a.gdim);
+}
+
+// Per-lane state of the dense walker.
+struct DenseLane {
+    int kx, ky, kz, ex, ey, ez, sx, sy, sz;
+    double tmx, tmy, tmz, tdx, tdy, tdz, length;
+    int csx, csy, csz;   // cell-index change of one brick step along each axis
+    int axis;
+    uint32_t cell;       // grid cell of the current brick
+    uint32_t widx;       // index of the current sub-block's free word in the 64-bit view of cmasks
+    uint64_t mask;       // cells of that sub-block visited by this ray
+    uint64_t seen;       // what the word held when the ray entered the sub-block; 0 = not known (yet)
+    unsigned age;        // iterations since the ray entered the sub-block (saturates at 3)
+    unsigned steps;
+};
+
+// One iteration of the walk for an active lane.  `stage` is the register the word fetched on entering a sub-block
+// lands in; the caller alternates between two of them, and a fetched word is moved into `seen` two iterations after
+// it was requested.  The warp therefore never waits on the load it has just issued (a scoreboard wait is warp-wide:
+// with ~28 active lanes some lane enters a sub-block on nearly every iteration), only on the one from two iterations
+// ago.  A ray that leaves a sub-block earlier publishes its cells without knowing the word (a redundant red.or).
+__device__ __forceinline__ bool dense_step(const ScanArgs& a, uint64_t* masks64, uint8_t* touched, DenseLane& L, uint64_t& stage) {
+    if (L.age == 1) L.seen = stage;      // requested two iterations ago, into this same register
+    // ---- one DDA step along `axis` (ray_advance), then pick the next axis (ray_select)
+    const bool ax = L.axis == 0, ay = L.axis == 1, az = L.axis == 2;
+    const double nx = dadd(L.tmx, L.tdx), ny = dadd(L.tmy, L.tdy), nz = dadd(L.tmz, L.tdz);
+    const int kold = ax ? L.kx : (ay ? L.ky : L.kz);
+    const int knew = kold + (ax ? L.sx : (ay ? L.sy : L.sz));
+    L.kx = ax ? knew : L.kx; L.ky = ay ? knew : L.ky; L.kz = az ? knew : L.kz;
+    L.tmx = ax ? nx : L.tmx; L.tmy = ay ? ny : L.tmy; L.tmz = az ? nz : L.tmz;
+    const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
+    const bool selx = xy & xz, sely = (!xy) & yz;
+    const double tsel = selx ? L.tmx : (sely ? L.tmy : L.tmz);
+    const int cstep = ax ? L.csx : (ay ? L.csy : L.csz);
+    L.axis = selx ? 0 : (sely ? 1 : 2);
+    const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | (tsel > L.length);
+    const int diff = knew ^ kold;            // only one coordinate moved
+    const bool new_sub = (diff >> 2) != 0;
+    // ---- leaving the sub-block (or the ray): publish its cells unless all of them are known to be set
+    if ((done | new_sub) && (L.mask & ~L.seen) != 0) {
+        atomicOr(reinterpret_cast<unsigned long long*>(masks64 + L.widx), (unsigned long long)L.mask);
+        touched[L.widx >> 4] = 1;
+    }
+    // ---- entering the next one
+    const bool enter = new_sub & !done;
+    L.cell += (enter & ((diff >> 3) != 0)) ? (uint32_t)cstep : 0u;
+    if (enter) {
+        if (L.cell >= a.gcells) {          // memory-safety guard; the grid is sized so that it never trips
+            a.counters[CNT_GRID_MISS] = 1;
+            L.cell = 0;
+        }
+        L.widx = L.cell * 16u + 8u + sub_index(L.kx, L.ky, L.kz);
+        L.mask = 0;
+        L.seen = 0;
+    }
+    stage = ldcg_u64_if(masks64 + L.widx, stage, enter);
+    L.age = enter ? 0u : (L.age < 3u ? L.age + 1u : 3u);
+    L.mask |= sub_bit(L.kx, L.ky, L.kz);
+    L.steps += done ? 0u : 1u;
+    return !done;
+}
+
+__global__ void __launch_bounds__(K3_THREADS, 3) k_scan_raycast_dense(const ScanArgs a, unsigned long long* ray_counter) {
+    const unsigned lane = threadIdx.x & 31u;
+    uint64_t* const masks64 = reinterpret_cast<uint64_t*>(a.cmasks);
+    uint8_t* const touched = reinterpret_cast<uint8_t*>(a.ctouched);
+    bool active = false, exhausted = false;
+    // (keys never wrap here: the host only picks this kernel when the whole grid lies inside the key range)
+    DenseLane L;
+    memset(&L, 0, sizeof L);
+    L.age = 3;
+    uint64_t stage_a = 0, stage_b = 0;
+    for (;;) {
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        const unsigned idle = ~act;
+        if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + __popc(idle) >= a.n) exhausted = true;
+            const unsigned long long i = base + __popc(idle & ((1u << lane) - 1u));
+            if (!active && i < a.n) {
+                const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
+                float fx, fy, fz;
+                const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, fx, fy, fz);
+                if (in_range) {
+                    uint16_t qx, qy, qz;
+                    if (coord_to_key3(a.res_factor, px, py, pz, qx, qy, qz)) {
+                        uint32_t c;
+                        if (cell_of_key(a, qx, qy, qz, c)) {
+                            const unsigned vox = brick_voxel_index(qx, qy, qz);
+                            uint32_t* w = a.cmasks + (size_t)c * 32 + (vox >> 5);
+                            const uint32_t bit = 1u << (vox & 31u);
+                            if (!(__ldcg(w) & bit)) {
+                                atomicOr(w, bit);
+                                touched[c] = 1;
+                            }
+                        } else {
+                            a.counters[CNT_GRID_MISS] = 1;
+                        }
+                    }
+                }
+                Ray r;
+                if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, fx, fy, fz, r) == 1) {
+                    L.kx = r.kx; L.ky = r.ky; L.kz = r.kz; L.ex = r.ex; L.ey = r.ey; L.ez = r.ez; L.sx = r.sx; L.sy = r.sy; L.sz = r.sz;
+                    L.tmx = r.tmx; L.tmy = r.tmy; L.tmz = r.tmz; L.tdx = r.tdx; L.tdy = r.tdy; L.tdz = r.tdz;
+                    L.length = (double)r.length;
+                    L.csx = r.sx; L.csy = r.sy * (int)a.gdim; L.csz = r.sz * (int)(a.gdim * a.gdim);
+                    const bool ok = cell_of_key(a, L.kx, L.ky, L.kz, L.cell);
+                    if (!ok) a.counters[CNT_GRID_MISS] = 1;
+                    active = ok;
+                    // the origin cell is the first free cell; its word is read here (this path is long anyway)
+                    L.widx = (ok ? L.cell : 0u) * 16u + 8u + sub_index(L.kx, L.ky, L.kz);
+                    L.seen = ld_cg_u64(masks64 + L.widx);
+                    L.age = 3;
+                    L.mask = sub_bit(L.kx, L.ky, L.kz);
+                    ++L.steps;
+                    double t;
+                    L.axis = ray_select(r, t);
+                }
+            }
+            continue;
+        }
+        if (act == 0) break;   // no ray left anywhere in this warp
+        const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
+        do {
+            if (active) active = dense_step(a, masks64, touched, L, stage_a);
+            if (active) active = dense_step(a, masks64, touched, L, stage_b);
+        } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
+        // fetched words still on their way are dropped (their rays publish without them): the next round may start
+        // with either staging register
+        if (L.age < 2) L.age = 3;
+    }
+    // statistics only: free-cell visits of this scan
+    unsigned long long total = L.steps;
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(&a.counters[CNT_STEPS_LO]), total);
+}
+
+// dense mode read-back, step 1: list the touched cells (one byte per cell, four cells per thread and load)
+__global__ void k_cells_list(const uint32_t* __restrict__ touched, uint32_t n_words, uint32_t* list, uint32_t cap, uint32_t* counters) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
+        const uint32_t w = touched[i];
+        if (!w) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if ((w >> (8 * b)) & 0xffu) {
+                const uint32_t q = atomicAdd(&counters[CNT_DELTA], 1u);
+                if (q < cap) list[q] = i * 4u + (uint32_t)b;
+            }
+        }
+    }
+}
+// step 2: one warp per listed cell -> record (free already minus occupied); clears the cell and its bit.  Does nothing
+// when the list overflowed (the host grows the buffers and runs both steps again: the masks are still intact).
+__global__ void __launch_bounds__(256) k_cells_emit(uint32_t* cmasks, uint8_t* touched, const uint32_t* __restrict__ list, uint32_t cap,
+                                                    const uint32_t* counters, DeltaRecord* out, int gx0, int gy0, int gz0, uint32_t gdim) {
+    const uint32_t n = counters[CNT_DELTA];
+    if (n > cap) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += warps) {
+        const uint32_t cell = list[q];
+        uint32_t w = cmasks[(size_t)cell * 32 + lane];
+        const uint32_t occ_w = __shfl_sync(0xffffffffu, w, lane & 15u);
+        if (lane >= 16) w &= ~occ_w;   // occupied wins
+        if (lane == 0) {
+            const uint32_t cx = cell % gdim, cy = (cell / gdim) % gdim, cz = cell / (gdim * gdim);
+            out[q].key = (uint64_t)(uint32_t)(gx0 + (int)cx) | ((uint64_t)(uint32_t)(gy0 + (int)cy) << 13) | ((uint64_t)(uint32_t)(gz0 + (int)cz) << 26);
+            touched[cell] = 0;
+        }
+        out[q].mask[lane] = w;
+        cmasks[(size_t)cell * 32 + lane] = 0;
+    }
+}
+
+// ---- hash mode
+// slot of a brick in the scratch table (bounded probe length; a too-full table is grown by the host)
 // (arguments by value: taking the address of the kernel-parameter struct would spill it to local memory)
 __device__ __noinline__ uint32_t scratch_slot_hash(uint64_t* skeys, uint64_t scap, uint32_t* counters, uint64_t bk) {
     const uint64_t mask = scap - 1;
@@ -193,63 +375,14 @@ __device__ __noinline__ uint32_t scratch_slot_hash(uint64_t* skeys, uint64_t sca
     return 0xffffffffu;
 }
 
-// dense mode, first touch of a brick in this scan: take the next slot and publish it in the grid cell.  Losing the
-// publication race wastes the slot (its key stays empty and its masks zero, so compaction skips it).
-__device__ __noinline__ uint32_t scratch_slot_alloc(uint64_t* skeys, uint64_t scap, uint32_t* counters, uint32_t epoch, uint32_t* cell,
-                                                    uint32_t seen_entry, uint64_t bk) {
-    const uint32_t s = atomicAdd(&counters[CNT_SCRATCH_USED], 1u);
-    if (s >= scap || s > kSlotMask) { counters[CNT_OVERFLOW] = 1; return 0xffffffffu; }
-    skeys[s] = bk;
-    const uint32_t mine = (epoch << 24) | s;
-    const uint32_t old = atomicCAS(cell, seen_entry, mine);
-    if (old == seen_entry) return s;
-    skeys[s] = kEmptyKey;              // somebody else published first (only current-epoch values are ever written)
-    if ((old >> 24) == epoch) return old & kSlotMask;
-    counters[CNT_OVERFLOW] = 1;        // unreachable; forces a clean re-cast instead of a wrong map
-    return 0xffffffffu;
-}
-
-template <bool kDense>
-__device__ __forceinline__ uint32_t brick_slot(const ScanArgs& a, int kx, int ky, int kz, bool wanted) {
-    // `wanted` false: the caller keeps its old slot; nothing is touched
-    if (kDense) {
-        const uint32_t ux = (uint32_t)((kx >> 3) - a.gx0), uy = (uint32_t)((ky >> 3) - a.gy0), uz = (uint32_t)((kz >> 3) - a.gz0);
-        const bool inside = (ux < a.gdim) & (uy < a.gdim) & (uz < a.gdim);
-        uint32_t* cell = a.grid + ((size_t)uz * a.gdim + uy) * a.gdim + ux;
-        const uint32_t e = ldcg_u32_if(cell, a.epoch << 24, wanted & inside);
-        uint32_t slot = e & kSlotMask;
-        if (wanted && (!inside || (e >> 24) != a.epoch)) {          // rare: first touch of the brick, or outside the grid
-            if (!inside) { a.counters[CNT_GRID_MISS] = 1; slot = 0xffffffffu; }
-            else slot = scratch_slot_alloc(a.skeys, a.scap, a.counters, a.epoch, cell, e, brick_key((uint32_t)kx, (uint32_t)ky, (uint32_t)kz));
-        }
-        return slot;
-    } else {
-        uint32_t slot = 0xffffffffu;
-        if (wanted) slot = scratch_slot_hash(a.skeys, a.scap, a.counters, brick_key((uint32_t)kx, (uint32_t)ky, (uint32_t)kz));
-        return slot;
-    }
-}
-
-__device__ __forceinline__ uint64_t* free_word(const ScanArgs& a, uint32_t slot, int kx, int ky, int kz) {
-    const unsigned sub = (unsigned)((kx >> 2) & 1) | ((unsigned)((ky >> 2) & 1) << 1) | ((unsigned)((kz >> 2) & 1) << 2);
-    return reinterpret_cast<uint64_t*>(a.smasks + (size_t)slot * 32 + 16) + sub;
-}
-__device__ __forceinline__ uint64_t sub_bit(int kx, int ky, int kz) {
-    const unsigned x = kx & 3, y = ky & 3, z = kz & 3;
-    const unsigned bit = (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3) | ((z & 2u) << 4);
-    return 1ull << bit;
-}
-
-template <bool kDense>
-__global__ void __launch_bounds__(K3_THREADS) k_scan_raycast(const ScanArgs a, unsigned long long* ray_counter) {
+__global__ void __launch_bounds__(K3_THREADS) k_scan_raycast_hash(const ScanArgs a, unsigned long long* ray_counter) {
     const unsigned lane = threadIdx.x & 31u;
     bool active = false, exhausted = false;
     Ray r;
     int axis = 0;
     double length = 0.0;
-    // cursor: 64-bit free-mask word of the current sub-block
-    uint64_t* word = nullptr;
-    uint64_t seen = 0, mask = 0;
+    uint64_t* word = nullptr;      // 64-bit free-mask word of the current sub-block
+    uint64_t seen = ~0ull, mask = 0;
     uint32_t slot = 0xffffffffu;
     unsigned long long steps = 0;
     for (;;) {
@@ -263,27 +396,26 @@ __global__ void __launch_bounds__(K3_THREADS) k_scan_raycast(const ScanArgs a, u
             const unsigned long long i = base + __popc(idle & ((1u << lane) - 1u));
             if (!active && i < a.n) {
                 const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
-                float ex, ey, ez;
-                const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, ex, ey, ez);
+                float fx, fy, fz;
+                const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, fx, fy, fz);
                 if (in_range) {
-                    uint16_t kx, ky, kz;
-                    if (coord_to_key3(a.res_factor, px, py, pz, kx, ky, kz)) {
-                        const uint32_t s = brick_slot<kDense>(a, kx, ky, kz, true);
+                    uint16_t qx, qy, qz;
+                    if (coord_to_key3(a.res_factor, px, py, pz, qx, qy, qz)) {
+                        const uint32_t s = scratch_slot_hash(a.skeys, a.scap, a.counters, brick_key(qx, qy, qz));
                         if (s != 0xffffffffu) {
-                            const unsigned vox = brick_voxel_index(kx, ky, kz);
+                            const unsigned vox = brick_voxel_index(qx, qy, qz);
                             uint32_t* w = a.smasks + (size_t)s * 32 + (vox >> 5);
                             const uint32_t bit = 1u << (vox & 31u);
                             if (!(__ldcg(w) & bit)) atomicOr(w, bit);
                         }
                     }
                 }
-                if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, ex, ey, ez, r) == 1) {
+                if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, fx, fy, fz, r) == 1) {
                     active = true;
                     length = (double)r.length;
-                    // the origin cell is the first free cell
-                    slot = brick_slot<kDense>(a, r.kx, r.ky, r.kz, true);
+                    slot = scratch_slot_hash(a.skeys, a.scap, a.counters, brick_key((uint32_t)r.kx, (uint32_t)r.ky, (uint32_t)r.kz));
                     const bool ok = slot != 0xffffffffu;
-                    word = free_word(a, ok ? slot : 0u, r.kx, r.ky, r.kz);
+                    word = reinterpret_cast<uint64_t*>(a.smasks + (size_t)(ok ? slot : 0u) * 32 + 16) + sub_index(r.kx, r.ky, r.kz);
                     seen = ldcg_u64_if(word, ~0ull, ok);
                     mask = sub_bit(r.kx, r.ky, r.kz);
                     ++steps;
@@ -293,7 +425,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_scan_raycast(const ScanArgs a, u
             }
             continue;
         }
-        if (act == 0) break;   // no ray left anywhere in this warp
+        if (act == 0) break;
         const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
         do {
             if (active) {
@@ -304,24 +436,21 @@ __global__ void __launch_bounds__(K3_THREADS) k_scan_raycast(const ScanArgs a, u
                 const bool done = ray_at_end(r) | (t > length);
                 const int diff = (r.kx ^ px) | (r.ky ^ py) | (r.kz ^ pz);
                 const bool new_sub = (diff >> 2) != 0;
-                // leave the sub-block (or the ray): publish its cells unless all of them were already set
-                red_or_u64_if(word, mask, (done | new_sub) & ((mask & ~seen) != 0));
+                if ((done | new_sub) && (mask & ~seen) != 0) atomicOr(reinterpret_cast<unsigned long long*>(word), (unsigned long long)mask);
                 const bool enter = new_sub & !done;
-                const uint32_t ns = brick_slot<kDense>(a, r.kx, r.ky, r.kz, enter & ((diff >> 3) != 0));
-                if (enter & ((diff >> 3) != 0)) slot = ns;
-                const bool ok = slot != 0xffffffffu;
                 if (enter) {
-                    word = free_word(a, ok ? slot : 0u, r.kx, r.ky, r.kz);
+                    if ((diff >> 3) != 0) slot = scratch_slot_hash(a.skeys, a.scap, a.counters, brick_key((uint32_t)r.kx, (uint32_t)r.ky, (uint32_t)r.kz));
+                    const bool ok = slot != 0xffffffffu;
+                    word = reinterpret_cast<uint64_t*>(a.smasks + (size_t)(ok ? slot : 0u) * 32 + 16) + sub_index(r.kx, r.ky, r.kz);
+                    seen = ldcg_u64_if(word, ~0ull, ok);
                     mask = 0;
                 }
-                seen = ldcg_u64_if(word, enter ? ~0ull : seen, enter & ok);
                 mask |= sub_bit(r.kx, r.ky, r.kz);
                 steps += done ? 0u : 1u;
                 active = !done;
             }
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
     }
-    // statistics only: free-cell visits of this scan
     for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
     if (lane == 0 && steps) atomicAdd(reinterpret_cast<unsigned long long*>(&a.counters[CNT_STEPS_LO]), steps);
 }
@@ -349,12 +478,10 @@ __global__ void k_scan_discretize(const ScanArgs a, float* out_xyz) {
 }
 
 // scratch table -> compact records (free already minus occupied); resets the slots it consumes.  One warp per slot.
-// dense: only the slots handed out by the counter are visited.
 __global__ void __launch_bounds__(256) k_scan_compact(uint64_t* skeys, uint32_t* smasks, uint64_t scap, DeltaRecord* out,
-                                                      uint32_t* counters, uint32_t out_cap, int dense) {
+                                                      uint32_t* counters, uint32_t out_cap) {
     const unsigned lane = threadIdx.x & 31u;
     const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    if (dense) { const uint64_t used = counters[CNT_SCRATCH_USED]; if (used < scap) scap = used; }
     for (uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < scap; s += warps) {
         const uint64_t k = skeys[s];
         if (k == kEmptyKey) continue;
@@ -610,8 +737,9 @@ static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
 static int tree_reserve_pool(r3d_tree* t, uint64_t want) {
     r3d_ctx* ctx = t->ctx;
     if (want <= t->pool_cap) return R3D_OK;
-    uint64_t ncap = t->pool_cap ? t->pool_cap : 1024;
-    while (ncap < want) ncap += ncap / 2 + 1024;
+    // geometric growth from 4096 bricks (8.6 MB): a growth step costs a device allocation, a copy and a sync
+    uint64_t ncap = t->pool_cap ? t->pool_cap : 4096;
+    while (ncap < want) ncap *= 2;
     if (ncap > 0xfffffff0ull) return set_error(ctx, R3D_ERR_OOM, "brick pool would exceed 2^32 bricks");
     float* nv = nullptr;
     uint32_t* nk = nullptr;
@@ -717,41 +845,122 @@ static int update_points_impl(r3d_tree* t, const T* xyz, uint64_t n, float upd, 
     return finish(ctx);
 }
 
-// Grid geometry for the dense brick lookup.  Returns non-zero when the scan cannot use it (reach too large, origin not
-// finite): the hash table serves those.
-static int discretize_blocks_dense(r3d_tree* t, const float origin[3], double maxrange, int* gx0, int* gy0, int* gz0, uint32_t* gdim) {
-    const double reach_vox = ceil(maxrange * t->res_factor) + 4.0;     // the DDA may overshoot the range by a cell or two
-    if (!(reach_vox < 8.0 * 400.0)) return 1;
+// Grid geometry of the dense mode: a cube of (2*reach+1)^3 bricks centred on the origin's brick, reach = maxrange plus
+// a margin (every visited voxel contains a point of the ray no farther than the ray length from the origin; the margin
+// is 4 voxels + 2 bricks).  Returns non-zero when the scan cannot use it -- unbounded range, scratch over budget, origin
+// not finite, or the cube not completely inside the key range (keys would wrap like upstream's uint16) -- and the hash
+// table serves those.
+static int dense_grid_geometry(r3d_tree* t, const float origin[3], double maxrange, int* gx0, int* gy0, int* gz0, uint32_t* gdim) {
+    if (!(maxrange >= 0.0)) return 1;
+    const double reach_vox = ceil(maxrange * t->res_factor) + 4.0;
+    if (!(reach_vox < 8.0 * 4000.0)) return 1;
     const int reach = (int)(reach_vox / 8.0) + 2;
+    const uint64_t g = (uint64_t)(2 * reach + 1);
+    if (g * g * g * 128ull > t->ctx->cell_budget_bytes || g * g * g > (1ull << 27)) return 1;
     int o[3];
     for (int i = 0; i < 3; ++i) {
         const double f = floor(t->res_factor * (double)origin[i]);
-        if (!(f > -1e9 && f < 1e9)) return 1;
+        if (!(f >= -32768.0 && f < 32768.0)) return 1;
         o[i] = (((int)f + r3d::kTreeMaxVal) >> 3) - reach;
+        if (o[i] < 0 || o[i] + (int)g > 8192) return 1;
     }
     *gx0 = o[0]; *gy0 = o[1]; *gz0 = o[2];
-    *gdim = (uint32_t)(2 * reach + 1);
+    *gdim = (uint32_t)g;
     return 0;
 }
 
-// grid storage for `gdim`^3 cells and a fresh epoch (cells written in older epochs read as empty)
-static int tree_grid_prepare(r3d_tree* t, uint32_t gdim) {
-    r3d_ctx* ctx = t->ctx;
-    const uint64_t cells = (uint64_t)gdim * gdim * gdim;
-    if (cells > t->sgrid_cells) {
-        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(t->sgrid);
-        t->sgrid = nullptr; t->sgrid_cells = 0;
-        R3D_CUDA_OK(ctx, cudaMalloc(&t->sgrid, cells * sizeof(uint32_t)));
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->sgrid, 0, cells * sizeof(uint32_t), ctx->stream));
-        t->sgrid_cells = cells;
-        t->epoch = 0;
+// direct-mapped scan scratch of the context: `cells` x (32 mask words) + touched bitmap, all zero between scans
+static int ctx_reserve_cells(r3d_ctx* ctx, uint64_t cells) {
+    if (cells <= ctx->cell_cap && !ctx->cells_dirty) return R3D_OK;
+    if (cells > ctx->cell_cap) {
+        R3D_CUDA_OK(ctx, cudaDeviceSynchronize());
+        cudaFree(ctx->cell_masks); cudaFree(ctx->cell_touched);
+        ctx->cell_masks = nullptr; ctx->cell_touched = nullptr; ctx->cell_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->cell_masks, cells * 128);
+        if (e == cudaSuccess) e = cudaMalloc(&ctx->cell_touched, (cells / 4 + 1) * 4);   // one byte per cell
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(ctx->cell_masks); ctx->cell_masks = nullptr;
+            return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(%llu MB of scan scratch) failed: %s", (unsigned long long)(cells * 128 >> 20), cudaGetErrorString(e));
+        }
+        ctx->cell_cap = cells;
+        ctx->cells_dirty = true;
     }
-    if (++t->epoch > 255u) {
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->sgrid, 0, t->sgrid_cells * sizeof(uint32_t), ctx->stream));
-        t->epoch = 1;
+    if (ctx->cells_dirty) {   // fresh memory, or a scan that was abandoned half-way
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->cell_masks, 0, ctx->cell_cap * 128, ctx->stream));
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->cell_touched, 0, (ctx->cell_cap / 4 + 1) * 4, ctx->stream));
+        ctx->cells_dirty = false;
     }
     return R3D_OK;
+}
+
+static int tree_reserve_delta(r3d_tree* t, uint64_t want) {
+    r3d_ctx* ctx = t->ctx;
+    if (want <= t->delta_cap) return R3D_OK;
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(t->delta);
+    t->delta = nullptr; t->delta_cap = 0;
+    R3D_CUDA_OK(ctx, cudaMalloc(&t->delta, want * sizeof(DeltaRecord)));
+    t->delta_cap = want;
+    return R3D_OK;
+}
+
+static unsigned raycast_blocks(r3d_tree* t, unsigned long long n_rays) {
+    r3d_ctx* ctx = t->ctx;
+    if (t->raycast_blocks_per_sm == 0) {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_scan_raycast_dense, K3_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_scan_raycast_hash, K3_THREADS, 0);
+        t->raycast_blocks_per_sm = a < 1 ? 1 : a;
+        t->raycast_blocks_per_sm_hash = b < 1 ? 1 : b;
+    }
+    (void)ctx;
+    return 0;
+}
+
+// dense mode: rays -> direct-mapped masks -> records.  Returns R3D_OK with *fallback = true when the hash path must
+// take over (a ray left the grid: cannot happen by construction, kept as a safety net).
+static int scan_delta_dense(r3d_tree* t, const ScanArgs& a0, bool* fallback) {
+    r3d_ctx* ctx = t->ctx;
+    ScanArgs a = a0;
+    *fallback = false;
+    R3D_TRY(ctx_reserve_cells(ctx, a.gcells));
+    a.cmasks = ctx->cell_masks;
+    a.ctouched = ctx->cell_touched;
+    if (t->delta_cap < (1u << 16)) R3D_TRY(tree_reserve_delta(t, 1u << 16));
+    ctx->cells_dirty = true;     // until the read-back below has cleaned up
+    if (a.n) {
+        unsigned long long* ray_counter = reinterpret_cast<unsigned long long*>(&t->counters[CNT_RAY_LO]);   // zeroed by the caller
+        raycast_blocks(t, a.n);
+        unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
+        const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
+        if (blocks > need) blocks = need;
+        cudaEventRecord(ctx->ev_a, ctx->stream);
+        k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
+        cudaEventRecord(ctx->ev_b, ctx->stream);
+        ctx->launches++;
+    }
+    const uint32_t n_words = a.gcells / 4 + 1;
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)t->delta_cap * 4 + 256));
+        if (attempt) R3D_TRY(tree_set_counter(t, CNT_DELTA, 0));
+        k_cells_list<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(a.ctouched, n_words, (uint32_t*)ctx->scratch[SCR_TILE],
+                                                                              (uint32_t)t->delta_cap, t->counters);
+        k_cells_emit<<<grid_for(ctx, (uint64_t)t->delta_cap * 32, 256, 8), 256, 0, ctx->stream>>>(
+            a.cmasks, reinterpret_cast<uint8_t*>(a.ctouched), (const uint32_t*)ctx->scratch[SCR_TILE], (uint32_t)t->delta_cap, t->counters, t->delta, a.gx0, a.gy0, a.gz0, a.gdim);
+        ctx->launches += 2;
+        R3D_CUDA_OK(ctx, cudaGetLastError());
+        R3D_TRY(tree_sync_counters(t));
+        if (t->h_counters[CNT_DELTA] <= t->delta_cap) {
+            ctx->cells_dirty = false;
+            if (a.n && attempt == 0) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);   // the read-back above fenced both
+            if (t->h_counters[CNT_GRID_MISS]) { *fallback = true; return R3D_OK; }   // records discarded, scratch clean
+            t->delta_n = t->h_counters[CNT_DELTA];
+            return R3D_OK;
+        }
+        R3D_TRY(tree_reserve_delta(t, (uint64_t)t->h_counters[CNT_DELTA] * 2));   // list overflow: masks untouched, list again
+    }
+    return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the record buffer");
 }
 
 // ray-cast one scan into the scratch table and compact it into t->delta (t->delta_n records)
@@ -761,19 +970,19 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
     if (n > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "scan too large");
     const float* d = xyz;
     if (n) R3D_TRY(stage_in(ctx, SCR_IN0, xyz, (size_t)n * 3, &d));
-    R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
-    // dense brick lookup when the scan's reach is bounded: grid of (2*reach+1)^3 cells centred on the origin's brick
-    bool dense = false;
+    ScanArgs a;
+    memset(&a, 0, sizeof a);
+    a.xyz = d; a.n = n;
+    a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
+    a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
+    a.counters = t->counters;
     int gx0 = 0, gy0 = 0, gz0 = 0;
     uint32_t gdim = 0;
-    if (maxrange >= 0.0 && !discretize_blocks_dense(t, origin, maxrange, &gx0, &gy0, &gz0, &gdim)) dense = true;
+    bool dense = dense_grid_geometry(t, origin, maxrange, &gx0, &gy0, &gz0, &gdim) == 0;
+    if (!dense || discretize) R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
     for (int attempt = 0; attempt < 14; ++attempt) {
-        ScanArgs a;
         a.xyz = d; a.n = n;
-        a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
-        a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
-        a.skeys = t->skeys; a.smasks = t->smasks; a.scap = t->scap; a.counters = t->counters;
-        a.grid = nullptr; a.gx0 = gx0; a.gy0 = gy0; a.gz0 = gz0; a.gdim = gdim; a.epoch = 0;
+        a.skeys = t->skeys; a.smasks = t->smasks; a.scap = t->scap;
         R3D_TRY(tree_reset_scan_counters(t));
         bool overflow = false;
         if (discretize && n) {
@@ -788,34 +997,35 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
             a.n = t->h_counters[CNT_DISCRETE];
         }
         if (!overflow && dense) {
-            R3D_TRY(tree_grid_prepare(t, gdim));
-            a.grid = t->sgrid;
-            a.epoch = t->epoch;
+            a.gx0 = gx0; a.gy0 = gy0; a.gz0 = gz0; a.gdim = gdim; a.gcells = gdim * gdim * gdim;
+            bool fallback = false;
+            R3D_TRY(scan_delta_dense(t, a, &fallback));
+            if (!fallback) {
+                t->last_scan_rays = a.n;
+                t->last_scan_steps = (uint64_t)t->h_counters[CNT_STEPS_LO] | ((uint64_t)t->h_counters[CNT_STEPS_HI] << 32);
+                return R3D_OK;
+            }
+            dense = false;
+            R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
+            continue;
         }
         if (!overflow && a.n) {
             // persistent warps pulling rays from a counter (slot CNT_RAY_LO/HI of the tree's counter block, zeroed above)
             unsigned long long* ray_counter = reinterpret_cast<unsigned long long*>(&t->counters[CNT_RAY_LO]);
-            if (t->raycast_blocks_per_sm == 0) {
-                int per_sm = 0;
-                R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_raycast<true>, K3_THREADS, 0));
-                t->raycast_blocks_per_sm = per_sm < 1 ? 1 : per_sm;
-            }
-            unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
+            raycast_blocks(t, a.n);
+            unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm_hash;
             const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
             if (blocks > need) blocks = need;
-            if (dense) k_scan_raycast<true><<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
-            else k_scan_raycast<false><<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
+            k_scan_raycast_hash<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
             ctx->launches++;
         }
-        bool grid_miss = false;
         if (!overflow) {
             k_scan_compact<<<grid_for(ctx, t->scap * 32, 256, 8), 256, 0, ctx->stream>>>(t->skeys, t->smasks, t->scap, t->delta, t->counters,
-                                                                                      (uint32_t)t->delta_cap, dense ? 1 : 0);
+                                                                                      (uint32_t)t->delta_cap);
             ctx->launches++;
             R3D_CUDA_OK(ctx, cudaGetLastError());
             R3D_TRY(tree_sync_counters(t));
-            grid_miss = dense && t->h_counters[CNT_GRID_MISS] != 0;
-            overflow = t->h_counters[CNT_OVERFLOW] != 0 || t->h_counters[CNT_DELTA] > t->delta_cap || grid_miss;
+            overflow = t->h_counters[CNT_OVERFLOW] != 0 || t->h_counters[CNT_DELTA] > t->delta_cap;
         }
         if (!overflow) {
             t->delta_n = t->h_counters[CNT_DELTA];
@@ -823,10 +1033,8 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
             t->last_scan_steps = (uint64_t)t->h_counters[CNT_STEPS_LO] | ((uint64_t)t->h_counters[CNT_STEPS_HI] << 32);
             return R3D_OK;
         }
-        // table too small for this scan (or a ray left the grid): grow / switch to the hash table, wipe, cast again
-        // (ray casting is a pure function of the scan)
-        if (grid_miss) dense = false;
-        else R3D_TRY(tree_reserve_scratch(t, t->scap * 4));
+        // table too small for this scan: grow, wipe, cast again (ray casting is a pure function of the scan)
+        R3D_TRY(tree_reserve_scratch(t, t->scap * 4));
         R3D_TRY(tree_reset_scratch(t));
     }
     return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the scratch table");
@@ -881,7 +1089,7 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     DeviceSetter ds(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
-    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters); cudaFree(t->sgrid);
+    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
     delete t;
 }
 
@@ -898,6 +1106,15 @@ extern "C" int r3d_tree_clear(r3d_tree* t) {
     t->pool_dirty = false;
     t->delta_n = 0;
     return finish(ctx);
+}
+
+extern "C" int r3d_tree_reserve(r3d_tree* t, uint64_t n_bricks) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    if (n_bricks > 0xfffffff0ull) return set_error(t->ctx, R3D_ERR_ARG, "too many bricks");
+    DeviceSetter ds(t->ctx->device);
+    R3D_TRY(tree_reserve_table(t, n_bricks));
+    R3D_TRY(tree_reserve_pool(t, n_bricks));
+    return finish(t->ctx);
 }
 
 extern "C" int r3d_tree_params(r3d_tree* t, float out[5]) {

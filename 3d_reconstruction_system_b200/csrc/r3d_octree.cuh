@@ -43,16 +43,13 @@ struct r3d_tree {
     uint32_t pool_used = 0;       // host mirror of counters[CNT_POOL_USED] as of the last counter read-back
     uint64_t pool_bound = 0;      // upper bound of the device value once every queued apply has run
     bool pool_dirty = false;      // applies were queued since the last read-back: call tree_settle before using pool_used
-    int raycast_blocks_per_sm = 0;
+    int raycast_blocks_per_sm = 0, raycast_blocks_per_sm_hash = 0;
     uint64_t* pool_keys = nullptr; // [pool_cap] brick key per pool entry, rebuilt from the table on demand
     uint64_t pool_keys_cap = 0;
     // per-scan scratch table + compacted delta
     uint64_t* skeys = nullptr;
     uint32_t* smasks = nullptr;
     uint64_t scap = 0;
-    uint32_t* sgrid = nullptr;    // dense brick -> slot lookup of the ray caster: (epoch << 24 | slot) per cell
-    uint64_t sgrid_cells = 0;
-    uint32_t epoch = 0;
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
     uint64_t last_scan_rays = 0, last_scan_steps = 0;

@@ -127,6 +127,10 @@ class OcTree:
         self._pend_pts, self._pend_upd = [], []
         check(self._lib.r3d_tree_clear(self._h), self._ctx.handle)
 
+    def reserve(self, n_bricks):
+        """Capacity hint: room for n_bricks bricks (8x8x8 voxels each) without regrowing the device pool."""
+        check(self._lib.r3d_tree_reserve(self._h, int(n_bricks)), self._ctx.handle)
+
     def toMaxLikelihood(self):
         self._flush()
         check(self._lib.r3d_tree_to_max_likelihood(self._h), self._ctx.handle)

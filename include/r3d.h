@@ -132,6 +132,8 @@ int r3d_transform_points(r3d_ctx *ctx, const double *xyz, uint64_t n, const doub
 int r3d_tree_create(r3d_ctx *ctx, double resolution, r3d_tree **tree);
 void r3d_tree_destroy(r3d_tree *tree);
 int r3d_tree_clear(r3d_tree *tree);
+/* Capacity hint (like std::vector::reserve): room for n_bricks 8x8x8-voxel bricks (2 112 B each) without regrowth. */
+int r3d_tree_reserve(r3d_tree *tree, uint64_t n_bricks);
 /* out[5] = hit, miss, clamp_min, clamp_max, occupancy threshold (float32 log-odds). */
 int r3d_tree_params(r3d_tree *tree, float out[5]);
 
