@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <float.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define R3D_HD __host__ __device__ __forceinline__
@@ -262,6 +263,152 @@ R3D_HD bool scan_point_end(float ox, float oy, float oz, float px, float py, flo
     const float mr = (float)maxrange;
     ex = fadd(ox, fmul(dx, mr)); ey = fadd(oy, fmul(dy, mr)); ez = fadd(oz, fmul(dz, mr));
     return false;
+}
+
+}  // namespace r3d
+
+// ---------------------------------------------------------------- K6: "%.4f" of a double, byte-exact (a7)
+// genply's float_formatter (transfer/camera_to_world.py:117, pixel_to_camera.py:68,108): C / Python "%.4f", i.e. the
+// exact binary value rounded half-to-even to 4 decimals.  x = m * 2^e exactly, so x * 10^4 = (m * 625) * 2^(e+4) with
+// m * 625 < 2^63: one 64-bit product and a shift with an exact remainder give the correctly rounded integer q of
+// 1e-4 units whenever |x| < 2^63 / 10^4; beyond that (x is then an integer multiple of 1/8 at least, no rounding
+// happens) a base-10^9 bignum carries the digits.  inf -> "inf" / "-inf", nan -> "nan".
+namespace r3d {
+
+R3D_HD uint64_t double_bits(double x) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; memcpy(&u, &x, 8); return u;
+#endif
+}
+
+struct Fixed4 {
+    uint64_t q;      // |x| in 1e-4 units, correctly rounded (valid when kind == 0)
+    int kind;        // 0 finite & small, 1 finite & needs the bignum, 2 inf, 3 nan
+    int neg;
+    uint64_t v;      // m * 625 (kind 1)
+    int sh;          // left shift (kind 1)
+};
+
+R3D_HD Fixed4 fixed4_decompose(double x) {
+    Fixed4 f;
+    const uint64_t b = double_bits(x);
+    f.neg = (int)(b >> 63);
+    const int ex = (int)((b >> 52) & 0x7ffu);
+    const uint64_t frac = b & 0xfffffffffffffull;
+    f.q = 0; f.v = 0; f.sh = 0; f.kind = 0;
+    if (ex == 0x7ff) { f.kind = frac ? 3 : 2; if (frac) f.neg = 0; return f; }
+    const uint64_t m = ex ? (frac | (1ull << 52)) : frac;
+    const int e = ex ? ex - 1075 : -1074;
+    const uint64_t v = m * 625ull;              // < 2^63
+    const int sh = e + 4;
+    if (sh >= 0) {
+        int lz = 0;
+        { uint64_t t = v; while (t && !(t >> 63)) { t <<= 1; ++lz; } if (!v) lz = 64; }
+        if (sh < lz || v == 0) { f.q = v << sh; return f; }   // still < 2^64
+        f.kind = 1; f.v = v; f.sh = sh;
+        return f;
+    }
+    const int s = -sh;
+    if (s >= 64) { f.q = 0; return f; }
+    uint64_t q = v >> s;
+    const uint64_t r = v & ((1ull << s) - 1ull), half = 1ull << (s - 1);
+    if (r > half || (r == half && (q & 1ull))) ++q;
+    f.q = q;
+    return f;
+}
+
+R3D_HD int dec_digits_u64(uint64_t q) {
+    int n = 1;
+    while (q >= 10ull) { q /= 10ull; ++n; }
+    return n;
+}
+
+// bignum: value = v << sh in base 1e9 limbs (little endian); returns the limb count
+constexpr int kBigLimbs = 40;
+R3D_HD int fixed4_big(uint64_t v, int sh, uint32_t* limb) {
+    int n = 0;
+    while (v) { limb[n++] = (uint32_t)(v % 1000000000ull); v /= 1000000000ull; }
+    while (sh > 0) {
+        const int step = sh > 29 ? 29 : sh;     // limb * 2^29 + carry < 2^64
+        uint64_t carry = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint64_t t = ((uint64_t)limb[i] << step) + carry;
+            limb[i] = (uint32_t)(t % 1000000000ull);
+            carry = t / 1000000000ull;
+        }
+        while (carry) { limb[n++] = (uint32_t)(carry % 1000000000ull); carry /= 1000000000ull; }
+        sh -= step;
+    }
+    return n;
+}
+
+// number of characters of "%.4f" % x
+R3D_HD int fixed4_len(double x) {
+    const Fixed4 f = fixed4_decompose(x);
+    if (f.kind == 3) return 3;
+    if (f.kind == 2) return 3 + f.neg;
+    if (f.kind == 0) {
+        const int d = dec_digits_u64(f.q);
+        return f.neg + (d > 4 ? d : 5) + 1;   // at least "0" before the point, 4 digits after it, the point
+    }
+    uint32_t limb[kBigLimbs];
+    const int n = fixed4_big(f.v, f.sh, limb);
+    const int d = (n - 1) * 9 + dec_digits_u64(limb[n - 1]);
+    return f.neg + d + 1;
+}
+
+// writes exactly fixed4_len(x) characters at dst
+R3D_HD void fixed4_write(double x, char* dst, int len) {
+    const Fixed4 f = fixed4_decompose(x);
+    if (f.kind == 3) { dst[0] = 'n'; dst[1] = 'a'; dst[2] = 'n'; return; }
+    if (f.kind == 2) { if (f.neg) *dst++ = '-'; dst[0] = 'i'; dst[1] = 'n'; dst[2] = 'f'; return; }
+    char* p = dst + len;                        // fill from the last digit backwards
+    if (f.kind == 0) {
+        uint64_t q = f.q;
+        for (int i = 0; i < 4; ++i) { *--p = (char)('0' + (int)(q % 10ull)); q /= 10ull; }
+        *--p = '.';
+        do { *--p = (char)('0' + (int)(q % 10ull)); q /= 10ull; } while (q);
+    } else {
+        uint32_t limb[kBigLimbs];
+        const int n = fixed4_big(f.v, f.sh, limb);
+        int produced = 0;
+        for (int i = 0; i < n; ++i) {
+            uint32_t w = limb[i];
+            const int cnt = (i == n - 1) ? dec_digits_u64(w) : 9;
+            for (int k = 0; k < cnt; ++k) {
+                *--p = (char)('0' + (int)(w % 10u)); w /= 10u;
+                if (++produced == 4) *--p = '.';
+            }
+        }
+    }
+    if (f.neg) *--p = '-';
+}
+
+// one PLY row: "%.4f %.4f %.4f \n" (camera_to_world.py:118-119) or "%.4f %.4f %.4f %d %d %d 0\n" (pixel_to_camera.py:70-73)
+R3D_HD int u8_len(unsigned v) { return v >= 100u ? 3 : (v >= 10u ? 2 : 1); }
+R3D_HD int ply_row_len(double x, double y, double z, bool rgb, unsigned r, unsigned g, unsigned b) {
+    const int n = fixed4_len(x) + fixed4_len(y) + fixed4_len(z);
+    return rgb ? n + 3 + u8_len(r) + u8_len(g) + u8_len(b) + 3 + 2 : n + 4;
+}
+R3D_HD char* u8_write(char* p, unsigned v) {
+    if (v >= 100u) *p++ = (char)('0' + v / 100u);
+    if (v >= 10u) *p++ = (char)('0' + (v / 10u) % 10u);
+    *p++ = (char)('0' + v % 10u);
+    return p;
+}
+R3D_HD void ply_row_write(char* p, double x, double y, double z, bool rgb, unsigned r, unsigned g, unsigned b) {
+    int n = fixed4_len(x); fixed4_write(x, p, n); p += n; *p++ = ' ';
+    n = fixed4_len(y); fixed4_write(y, p, n); p += n; *p++ = ' ';
+    n = fixed4_len(z); fixed4_write(z, p, n); p += n; *p++ = ' ';
+    if (rgb) {
+        p = u8_write(p, r); *p++ = ' ';
+        p = u8_write(p, g); *p++ = ' ';
+        p = u8_write(p, b); *p++ = ' ';
+        *p++ = '0';
+    }
+    *p++ = '\n';
 }
 
 }  // namespace r3d

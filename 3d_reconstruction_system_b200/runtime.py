@@ -47,6 +47,8 @@ class DeviceBuffer:
 
     def __init__(self, ctx, shape, dtype, _base=None, _ptr=None):
         self.ctx = ctx
+        if isinstance(shape, (int, np.integer)):
+            shape = (shape,)
         self.shape = tuple(int(v) for v in shape)
         self.dtype = np.dtype(dtype)
         self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
@@ -214,6 +216,42 @@ class Context:
         """Same from quaternion (scalar-last) + translation poses: the r3d_backproject entry point."""
         rt = self.pose_to_rt(quats, trans)
         return self.backproject(depth, intr, rt=rt, **kw)
+
+    def ply_rows(self, x, y=None, z=None, rgb=None):
+        """Vertex rows of the reference's ASCII PLY ("%.4f %.4f %.4f \\n", or with rgb "... r g b 0\\n") as bytes, formatted
+        on the GPU (K6).  x alone may be an (n, 3) float64 array; or pass three equally long 1-D arrays."""
+        if y is None:
+            p = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+            n, stride = p.shape[0], 3
+            px, py, pz = p.ctypes.data, p.ctypes.data + 8, p.ctypes.data + 16
+            keep = (p,)
+        else:
+            xa, ya, za = (np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (x, y, z))
+            if not (xa.size == ya.size == za.size):
+                raise ValueError("coordinate arrays differ in length")
+            n, stride = xa.size, 1
+            px, py, pz = xa.ctypes.data, ya.ctypes.data, za.ctypes.data
+            keep = (xa, ya, za)
+        c = None
+        if rgb is not None:
+            c = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+            if c.shape[0] != n:
+                raise ValueError("rgb must have one row per point")
+        if n == 0:
+            return b""
+        need = C.c_size_t(0)
+        # rows are at most 3*(1+17+5)+... bytes for |coordinates| < 1e17; size the buffer from a cheap bound, retry if short
+        cap = n * (96 if c is None else 112)
+        buf = np.empty(cap, dtype=np.uint8)
+        check(self.lib.r3d_format_ply_rows(self._h, px, py, pz, stride, n, None if c is None else c.ctypes.data, buf.ctypes.data, cap,
+                                           C.byref(need)), self._h)
+        if need.value > cap:
+            cap = need.value
+            buf = np.empty(cap, dtype=np.uint8)
+            check(self.lib.r3d_format_ply_rows(self._h, px, py, pz, stride, n, None if c is None else c.ctypes.data, buf.ctypes.data, cap,
+                                               C.byref(need)), self._h)
+        del keep
+        return buf[: need.value].tobytes()
 
     def transform_points(self, xyz, T):
         """T . [x y z 1]^T for an (n,3) float64 cloud (other_tools/transfer_T_icp.py:10-12)."""

@@ -89,6 +89,16 @@ def get_pointdata(p_path, q, t, xcord, ycord, zcord, point_world_path=None):
     formats.write_xyz_txt(point_world_path or POINT_WORLD_PATH, world[:, 0], world[:, 1], world[:, 2])
 
 
+def _write_ply(pc_file, x, y, z, rgb=None):
+    """Header + GPU-formatted rows (K6, r3d_format_ply_rows) + trailer: the exact bytes of the reference's writers."""
+    rows = default_context(DEVICE).ply_rows(x, y, z, rgb=rgb)
+    hdr = (formats.PLY_HEADER_XYZ if rgb is None else formats.PLY_HEADER_RGB) % x.size
+    with open(pc_file, "wb") as f:
+        f.write(hdr.encode("ascii"))
+        f.write(rows)
+        f.write(formats.PLY_TRAILER.encode("ascii"))
+
+
 def genply(gtxyz, pc_file, lenth_point):
     """ASCII PLY, byte-identical to camera_to_world.py:112-134."""
     x = np.asarray(gtxyz[0], dtype=np.float64)[:lenth_point]
@@ -96,7 +106,7 @@ def genply(gtxyz, pc_file, lenth_point):
     z = np.asarray(gtxyz[2], dtype=np.float64)[:lenth_point]
     if not (x.size == y.size == z.size == lenth_point):
         raise ValueError("could not broadcast input array into shape (%d,)" % lenth_point)
-    formats.write_ply_ascii(pc_file, x, y, z)
+    _write_ply(pc_file, x, y, z)
     print("Write into .ply file Done.")
 
 
@@ -112,7 +122,8 @@ def genply_noRGB(gtxyz, imgpath, pc_file):
     img = np.array(Image.open(imgpath))
     n = img.shape[0] * img.shape[1]
     rgb = img[:, :, 0:3].reshape(n, 3)
-    formats.write_ply_ascii(pc_file, np.asarray(gtxyz[0])[:n], np.asarray(gtxyz[1])[:n], np.asarray(gtxyz[2])[:n], rgb=rgb)
+    _write_ply(pc_file, np.asarray(gtxyz[0], dtype=np.float64)[:n], np.asarray(gtxyz[1], dtype=np.float64)[:n],
+               np.asarray(gtxyz[2], dtype=np.float64)[:n], rgb=rgb)
     print("Write into .ply file Done.", time.time() - t1)
 
 

@@ -123,6 +123,20 @@ int r3d_pose_apply_points(r3d_ctx *ctx, const double *xyz, uint64_t n, const dou
  */
 int r3d_transform_points(r3d_ctx *ctx, const double *xyz, uint64_t n, const double T[16], double *out_xyz);
 
+/* ------------------------------------------------------------------ K6: text --- */
+/*
+ * The vertex rows of genply / genply_RGB (transfer/camera_to_world.py:112-134, transfer/pixel_to_camera.py:98-124):
+ *     "%.4f %.4f %.4f \n"            per point (trailing space), or, with rgb != NULL, genply_noRGB's
+ *     "%.4f %.4f %.4f %d %d %d 0\n"  (transfer/pixel_to_camera.py:55-91),
+ * byte for byte what Python's "%.4f" prints (exact value, round half to even; "inf", "-inf", "nan").
+ * Coordinate i is x[i*stride], y[i*stride], z[i*stride] (stride in doubles: 1 for three arrays, 3 for an interleaved
+ * n x 3 block); rgb is n x 3 bytes.  Buffers may be host or device memory (a device `out` must be 16-byte aligned).
+ * *len always receives the text length; nothing is written when out is NULL or cap < *len (size query).
+ * The header / trailer around the rows are a few constant lines written by the caller.
+ */
+int r3d_format_ply_rows(r3d_ctx *ctx, const double *x, const double *y, const double *z, size_t stride, uint64_t n,
+                        const uint8_t *rgb, char *out, size_t cap, size_t *len);
+
 /* ------------------------------------------------------------------ occupancy -- */
 /*
  * octomap.OcTree(resolution) (octomap/txt_transfer_octomap.py:33, octomap/ply_transfer_octomap.py:45):

@@ -56,4 +56,15 @@ uint32_t hm_brick_voxel_index(uint32_t x, uint32_t y, uint32_t z) { return brick
 void hm_brick_voxel_coords(uint32_t i, uint32_t* xyz) { brick_voxel_coords(i, xyz[0], xyz[1], xyz[2]); }
 uint64_t hm_brick_key(uint32_t x, uint32_t y, uint32_t z) { return brick_key(x, y, z); }
 uint64_t hm_brick_morton(uint64_t bk) { return brick_morton(bk); }
+// K6: "%.4f" rows.  Formats n rows into out (rows back to back), returns the total length.
+long hm_ply_rows(const double* xyz, long n, const unsigned char* rgb, char* out) {
+    long off = 0;
+    for (long i = 0; i < n; ++i) {
+        const unsigned r = rgb ? rgb[3 * i] : 0, g = rgb ? rgb[3 * i + 1] : 0, b = rgb ? rgb[3 * i + 2] : 0;
+        const int len = ply_row_len(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rgb != nullptr, r, g, b);
+        ply_row_write(out + off, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rgb != nullptr, r, g, b);
+        off += len;
+    }
+    return off;
+}
 }

@@ -9,6 +9,7 @@ import pytest
 
 from oracle import octomap_oracle as oo
 from oracle import points_oracle as po
+from _cases import fixed4_cases
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -41,7 +42,23 @@ def hm():
     L.hm_brick_voxel_index.restype = C.c_uint32
     L.hm_brick_voxel_index.argtypes = [C.c_uint32] * 3
     L.hm_brick_voxel_coords.argtypes = [C.c_uint32, C.c_void_p]
+    L.hm_ply_rows.restype = C.c_long
+    L.hm_ply_rows.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     return L
+
+
+def test_fixed4_rows_match_python_percent_format(hm):
+    x = fixed4_cases()
+    x = x[: (x.size // 3) * 3].reshape(-1, 3).copy()
+    out = C.create_string_buffer(x.shape[0] * 3 * 330 + 64)
+    n = hm.hm_ply_rows(x.ctypes.data, x.shape[0], None, out)
+    want = "".join("%.4f %.4f %.4f \n" % (a, b, c) for a, b, c in x.tolist())
+    assert out.raw[:n].decode("ascii") == want
+    rgb = np.random.default_rng(5).integers(0, 256, size=(x.shape[0], 3), dtype=np.uint8)
+    rgb[:3] = [[0, 9, 10], [99, 100, 255], [1, 2, 3]]
+    n = hm.hm_ply_rows(x.ctypes.data, x.shape[0], rgb.ctypes.data, out)
+    want = "".join("%.4f %.4f %.4f %d %d %d 0\n" % (a, b, c, r, g, bb) for (a, b, c), (r, g, bb) in zip(x.tolist(), rgb.tolist()))
+    assert out.raw[:n].decode("ascii") == want
 
 
 def ray(hm, res, o, e):
