@@ -42,6 +42,7 @@ SIGNATURES = {
     "r3d_transform_points": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "r3d_pose_apply_points": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "r3d_format_ply_rows": (_i32, [_vp, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _sz, C.POINTER(_sz)]),
+    "r3d_format_txt_rows": (_i32, [_vp, _vp, _vp, _vp, _sz, _u64, _i32, _vp, _sz, C.POINTER(_sz)]),
     "r3d_tree_create": (_i32, [_vp, _dbl, C.POINTER(_vp)]),
     "r3d_tree_destroy": (None, [_vp]),
     "r3d_tree_clear": (_i32, [_vp]),

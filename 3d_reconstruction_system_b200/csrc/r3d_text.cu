@@ -12,6 +12,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include "r3d_common.cuh"
+#include "r3d_repr.cuh"
 
 namespace r3d {
 
@@ -22,6 +23,7 @@ struct TextArgs {
     const double *x, *y, *z;       // coordinate i at x[i * stride] ...
     unsigned long long stride;
     const unsigned char* rgb;      // n x 3 or nullptr
+    int z_int;                     // txt rows: Z printed as an integer
     unsigned long long n;
     unsigned long long* tile_len;  // [n_tiles] -> exclusive offsets after the scan
     char* out;
@@ -33,19 +35,30 @@ __device__ __forceinline__ int k6_row_len(const TextArgs& a, unsigned long long 
                        rgb ? a.rgb[3 * i + 2] : 0u);
 }
 
+// kTxt: "X,Y,Z\n" rows with str(float64) fields (r3d_repr.cuh) instead of PLY rows
+template <bool kTxt>
 __global__ void __launch_bounds__(K6_THREADS) k6_count(const TextArgs a) {
     typedef cub::BlockReduce<unsigned, K6_THREADS> Reduce;
     __shared__ typename Reduce::TempStorage tmp;
     const unsigned long long n_tiles = (a.n + K6_THREADS - 1) / K6_THREADS;
     for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const unsigned long long i = t * K6_THREADS + threadIdx.x;
-        const unsigned len = i < a.n ? (unsigned)k6_row_len(a, i) : 0u;
+        unsigned len = 0;
+        if (i < a.n) {
+            if (kTxt) {
+                char row[kTxtRowMax];
+                len = (unsigned)txt_row_write(row, a.x[i * a.stride], a.y[i * a.stride], a.z[i * a.stride], a.z_int != 0);
+            } else {
+                len = (unsigned)k6_row_len(a, i);
+            }
+        }
         const unsigned sum = Reduce(tmp).Sum(len);
         if (threadIdx.x == 0) a.tile_len[t] = sum;
         __syncthreads();
     }
 }
 
+template <bool kTxt>
 __global__ void __launch_bounds__(K6_THREADS) k6_write(const TextArgs a) {
     typedef cub::BlockScan<unsigned, K6_THREADS> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -56,10 +69,15 @@ __global__ void __launch_bounds__(K6_THREADS) k6_write(const TextArgs a) {
         const unsigned long long i = t * K6_THREADS + threadIdx.x;
         double x = 0, y = 0, z = 0;
         unsigned r = 0, g = 0, b = 0, len = 0;
+        char row[kTxt ? kTxtRowMax : 4];
         if (i < a.n) {
             x = a.x[i * a.stride]; y = a.y[i * a.stride]; z = a.z[i * a.stride];
-            if (rgb) { r = a.rgb[3 * i]; g = a.rgb[3 * i + 1]; b = a.rgb[3 * i + 2]; }
-            len = (unsigned)ply_row_len(x, y, z, rgb, r, g, b);
+            if (kTxt) {
+                len = (unsigned)txt_row_write(row, x, y, z, a.z_int != 0);
+            } else {
+                if (rgb) { r = a.rgb[3 * i]; g = a.rgb[3 * i + 1]; b = a.rgb[3 * i + 2]; }
+                len = (unsigned)ply_row_len(x, y, z, rgb, r, g, b);
+            }
         }
         unsigned off, total;
         Scan(tmp).ExclusiveSum(len, off, total);
@@ -67,7 +85,10 @@ __global__ void __launch_bounds__(K6_THREADS) k6_write(const TextArgs a) {
         if (total <= (unsigned)K6_STAGE_BYTES) {
             // stage at (base % 16) so that the copy below moves aligned 16-byte words
             const unsigned skew = (unsigned)(base & 15ull);
-            if (len) ply_row_write(stage + skew + off, x, y, z, rgb, r, g, b);
+            if (len) {
+                if (kTxt) { for (unsigned k = 0; k < len; ++k) stage[skew + off + k] = row[k]; }
+                else ply_row_write(stage + skew + off, x, y, z, rgb, r, g, b);
+            }
             __syncthreads();
             char* dst = a.out + (base - skew);
             const unsigned span = skew + total;
@@ -82,8 +103,9 @@ __global__ void __launch_bounds__(K6_THREADS) k6_write(const TextArgs a) {
             // tail (shared with the next tile), and the head when the tile is shorter than one word
             for (unsigned k = full * 16u + threadIdx.x; k < span; k += K6_THREADS)
                 if (k >= skew) dst[k] = stage[k];
-        } else {
-            if (len) ply_row_write(a.out + base + off, x, y, z, rgb, r, g, b);
+        } else if (len) {
+            if (kTxt) { for (unsigned k = 0; k < len; ++k) a.out[base + off + k] = row[k]; }
+            else ply_row_write(a.out + base + off, x, y, z, rgb, r, g, b);
         }
         __syncthreads();
     }
@@ -93,18 +115,18 @@ __global__ void __launch_bounds__(K6_THREADS) k6_write(const TextArgs a) {
 
 using namespace r3d;
 
-extern "C" int r3d_format_ply_rows(r3d_ctx* ctx, const double* x, const double* y, const double* z, size_t stride, uint64_t n,
-                                   const uint8_t* rgb, char* out, size_t cap, size_t* len) {
+static int format_rows(r3d_ctx* ctx, bool txt, int z_int, const double* x, const double* y, const double* z, size_t stride, uint64_t n,
+                       const uint8_t* rgb, char* out, size_t cap, size_t* len) {
     if (!ctx) return set_error(nullptr, R3D_ERR_ARG, "null context");
     if (!len) return set_error(ctx, R3D_ERR_ARG, "null length pointer");
     *len = 0;
     if (n == 0) return R3D_OK;
-    if (!x || !y || !z || stride == 0) return set_error(ctx, R3D_ERR_ARG, "r3d_format_ply_rows: null coordinates");
+    if (!x || !y || !z || stride == 0) return set_error(ctx, R3D_ERR_ARG, "r3d_format_*_rows: null coordinates");
     DeviceSetter ds(ctx->device);
     // coordinates: device pointers are used in place; host arrays are staged as one block [min(x,y,z), max + span)
     TextArgs a;
     memset(&a, 0, sizeof a);
-    a.n = n; a.stride = stride;
+    a.n = n; a.stride = stride; a.z_int = z_int;
     const bool dev = is_device_ptr(x);
     if (dev != is_device_ptr(y) || dev != is_device_ptr(z)) return set_error(ctx, R3D_ERR_ARG, "coordinate arrays must live on the same side");
     if (dev) { a.x = x; a.y = y; a.z = z; }
@@ -144,7 +166,8 @@ extern "C" int r3d_format_ply_rows(r3d_ctx* ctx, const double* x, const double* 
     a.tile_len = lens;
     const unsigned grid = (unsigned)(n_tiles < (unsigned long long)ctx->sm_count * 8 ? n_tiles : (unsigned long long)ctx->sm_count * 8);
     R3D_CUDA_OK(ctx, cudaMemsetAsync(lens + n_tiles, 0, 8, ctx->stream));
-    k6_count<<<grid, K6_THREADS, 0, ctx->stream>>>(a);
+    if (txt) k6_count<true><<<grid, K6_THREADS, 0, ctx->stream>>>(a);
+    else k6_count<false><<<grid, K6_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, lens, offs, (int)(n_tiles + 1), ctx->stream);
@@ -167,7 +190,8 @@ extern "C" int r3d_format_ply_rows(r3d_ctx* ctx, const double* x, const double* 
     }
     a.tile_len = offs;
     a.out = d_out;
-    k6_write<<<grid, K6_THREADS, 0, ctx->stream>>>(a);
+    if (txt) k6_write<true><<<grid, K6_THREADS, 0, ctx->stream>>>(a);
+    else k6_write<false><<<grid, K6_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     R3D_CUDA_OK(ctx, cudaGetLastError());
     if (!out_dev) {
@@ -175,4 +199,14 @@ extern "C" int r3d_format_ply_rows(r3d_ctx* ctx, const double* x, const double* 
         R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return finish(ctx);
+}
+
+extern "C" int r3d_format_ply_rows(r3d_ctx* ctx, const double* x, const double* y, const double* z, size_t stride, uint64_t n,
+                                   const uint8_t* rgb, char* out, size_t cap, size_t* len) {
+    return format_rows(ctx, false, 0, x, y, z, stride, n, rgb, out, cap, len);
+}
+
+extern "C" int r3d_format_txt_rows(r3d_ctx* ctx, const double* x, const double* y, const double* z, size_t stride, uint64_t n,
+                                   int z_is_integer, char* out, size_t cap, size_t* len) {
+    return format_rows(ctx, true, z_is_integer ? 1 : 0, x, y, z, stride, n, nullptr, out, cap, len);
 }

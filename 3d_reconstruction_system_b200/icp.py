@@ -62,7 +62,8 @@ def local_world(path_local, file_write, T, xcord, ycord, zcord, flag):
     xcord.extend(pts[:, 0].tolist())
     ycord.extend(pts[:, 1].tolist())
     zcord.extend(pts[:, 2].tolist())
-    file_write.write("".join("%r,%r,%r\n" % (a, b, c) for a, b, c in zip(pts[:, 0].tolist(), pts[:, 1].tolist(), pts[:, 2].tolist())))
+    rows = default_context(DEVICE).txt_rows(pts)          # str(x),str(y),str(z) lines, formatted on the GPU
+    file_write.write(rows.decode("ascii"))
 
 
 def run(path_T='T_data.txt', path_world='./point_world/03_testT.txt', path_ply='./ply/icp/024.ply',

@@ -253,6 +253,30 @@ class Context:
         del keep
         return buf[: need.value].tobytes()
 
+    def txt_rows(self, x, y=None, z=None, z_is_integer=False):
+        """`str(X),str(Y),str(Z)\\n` lines of the reference's x,y,z txt files as bytes, formatted on the GPU (K6): every field
+        is str(float64) (shortest round-trip repr); with z_is_integer Z is printed as an integer like gentxtcord does."""
+        if y is None:
+            p = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+            n, stride = p.shape[0], 3
+            px, py, pz = p.ctypes.data, p.ctypes.data + 8, p.ctypes.data + 16
+            keep = (p,)
+        else:
+            xa, ya, za = (np.ascontiguousarray(v, dtype=np.float64).ravel() for v in (x, y, z))
+            if not (xa.size == ya.size == za.size):
+                raise ValueError("coordinate arrays differ in length")
+            n, stride = xa.size, 1
+            px, py, pz = xa.ctypes.data, ya.ctypes.data, za.ctypes.data
+            keep = (xa, ya, za)
+        if n == 0:
+            return b""
+        need = C.c_size_t(0)
+        cap = n * 76
+        buf = np.empty(cap, dtype=np.uint8)
+        check(self.lib.r3d_format_txt_rows(self._h, px, py, pz, stride, n, 1 if z_is_integer else 0, buf.ctypes.data, cap, C.byref(need)), self._h)
+        del keep
+        return buf[: need.value].tobytes()
+
     def transform_points(self, xyz, T):
         """T . [x y z 1]^T for an (n,3) float64 cloud (other_tools/transfer_T_icp.py:10-12)."""
         p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)

@@ -73,7 +73,7 @@ def gentxtcord(filename, depth, intr=None):
     camera_to_world variant returns None; its caller ignores the value)."""
     depth = np.ascontiguousarray(depth)
     xyz = camera_points(depth, intr)
-    formats.write_xyz_txt(filename, xyz[:, 0], xyz[:, 1], xyz[:, 2], z_raw=depth)
+    _write_xyz_txt(filename, xyz[:, 0], xyz[:, 1], xyz[:, 2], z_raw=depth)
     return [xyz[:, 0].tolist(), xyz[:, 1].tolist(), depth.ravel().tolist()]
 
 
@@ -86,7 +86,22 @@ def get_pointdata(p_path, q, t, xcord, ycord, zcord, point_world_path=None):
     xcord.extend(world[:, 0].tolist())
     ycord.extend(world[:, 1].tolist())
     zcord.extend(world[:, 2].tolist())
-    formats.write_xyz_txt(point_world_path or POINT_WORLD_PATH, world[:, 0], world[:, 1], world[:, 2])
+    _write_xyz_txt(point_world_path or POINT_WORLD_PATH, world[:, 0], world[:, 1], world[:, 2])
+
+
+def _write_xyz_txt(path, x, y, z, z_raw=None):
+    """`str(X),str(Y),str(Z)` lines formatted on the GPU (K6, r3d_format_txt_rows).  z_raw: integer samples printed as
+    integers, as the reference does for camera-frame files (Z is still np.uint8 there); a float z_raw (not a reference
+    case) goes through the host formatter."""
+    if z_raw is not None:
+        zr = np.asarray(z_raw).ravel()
+        if zr.dtype.kind not in "iu":
+            return formats.write_xyz_txt(path, x, y, z, z_raw=z_raw)
+        rows = default_context(DEVICE).txt_rows(x, y, zr.astype(np.float64), z_is_integer=True)
+    else:
+        rows = default_context(DEVICE).txt_rows(x, y, z)
+    with open(path, "wb") as f:
+        f.write(rows)
 
 
 def _write_ply(pc_file, x, y, z, rgb=None):
@@ -164,9 +179,8 @@ def get_file_name(qt_path, intr=None, write_intermediate=True, ply_path=None, po
             cam = cam.reshape(j - k, -1, 3)
             for i in range(j - k):
                 name = poses["names"][k + i]
-                formats.write_xyz_txt(os.path.join(POINT_DIR, name[0:-4] + '.txt'), cam[i, :, 0], cam[i, :, 1], cam[i, :, 2],
-                                      z_raw=batch[i])
-            formats.write_xyz_txt(POINT_WORLD_PATH, world[-1, :, 0], world[-1, :, 1], world[-1, :, 2])
+                _write_xyz_txt(os.path.join(POINT_DIR, name[0:-4] + '.txt'), cam[i, :, 0], cam[i, :, 1], cam[i, :, 2], z_raw=batch[i])
+            _write_xyz_txt(POINT_WORLD_PATH, world[-1, :, 0], world[-1, :, 1], world[-1, :, 2])
         xs.append(world[:, :, 0].ravel())
         ys.append(world[:, :, 1].ravel())
         zs.append(world[:, :, 2].ravel())

@@ -137,6 +137,17 @@ int r3d_transform_points(r3d_ctx *ctx, const double *xyz, uint64_t n, const doub
 int r3d_format_ply_rows(r3d_ctx *ctx, const double *x, const double *y, const double *z, size_t stride, uint64_t n,
                         const uint8_t *rgb, char *out, size_t cap, size_t *len);
 
+/*
+ * The lines of the x,y,z txt files: gentxtcord's `str(X) + ',' + str(Y) + ',' + str(Z) + '\n'`
+ * (transfer/camera_to_world.py:79-81, transfer/pixel_to_camera.py:41-42) and get_pointdata's world lines (:103-104).
+ * Every field is Python's str(float64): the shortest decimal that reads back to the same double, laid out by repr()'s
+ * rules ("0.1", "1e-05", "1.2345678901234568e+16", "-0.0", "inf", "nan").  z_is_integer != 0 prints Z as an integer
+ * ("157"), which is what gentxtcord does because Z is still the raw integer sample there.  Same buffer and size-query
+ * conventions as r3d_format_ply_rows; a row is at most 75 bytes.
+ */
+int r3d_format_txt_rows(r3d_ctx *ctx, const double *x, const double *y, const double *z, size_t stride, uint64_t n,
+                        int z_is_integer, char *out, size_t cap, size_t *len);
+
 /* ------------------------------------------------------------------ occupancy -- */
 /*
  * octomap.OcTree(resolution) (octomap/txt_transfer_octomap.py:33, octomap/ply_transfer_octomap.py:45):

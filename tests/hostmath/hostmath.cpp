@@ -2,6 +2,7 @@
 // The kernels' scalar arithmetic is written once for host and device; this wrapper lets the CPU test-suite check
 // those formulas against the oracle where no GPU exists.  It is never loaded by the product package.
 #include "../../3d_reconstruction_system_b200/csrc/r3d_math.cuh"
+#include "../../3d_reconstruction_system_b200/csrc/r3d_repr.cuh"
 #include <cstddef>
 using namespace r3d;
 extern "C" {
@@ -57,6 +58,13 @@ void hm_brick_voxel_coords(uint32_t i, uint32_t* xyz) { brick_voxel_coords(i, xy
 uint64_t hm_brick_key(uint32_t x, uint32_t y, uint32_t z) { return brick_key(x, y, z); }
 uint64_t hm_brick_morton(uint64_t bk) { return brick_morton(bk); }
 // K6: "%.4f" rows.  Formats n rows into out (rows back to back), returns the total length.
+// K6: "X,Y,Z\n" rows with str(float64) fields (z_int: Z printed as an integer).  Returns the total length.
+long hm_txt_rows(const double* xyz, long n, int z_int, char* out) {
+    long off = 0;
+    for (long i = 0; i < n; ++i) off += txt_row_write(out + off, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], z_int != 0);
+    return off;
+}
+int hm_repr(double x, char* out) { return repr_double(x, out); }
 long hm_ply_rows(const double* xyz, long n, const unsigned char* rgb, char* out) {
     long off = 0;
     for (long i = 0; i < n; ++i) {

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import octomap_oracle as oo
 from oracle import points_oracle as po
-from _cases import fixed4_cases
+from _cases import fixed4_cases, repr_cases
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -42,6 +42,8 @@ def hm():
     L.hm_brick_voxel_index.restype = C.c_uint32
     L.hm_brick_voxel_index.argtypes = [C.c_uint32] * 3
     L.hm_brick_voxel_coords.argtypes = [C.c_uint32, C.c_void_p]
+    L.hm_txt_rows.restype = C.c_long
+    L.hm_txt_rows.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p]
     L.hm_ply_rows.restype = C.c_long
     L.hm_ply_rows.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     return L
@@ -158,3 +160,21 @@ def test_brick_indexing_roundtrip(hm):
     for b in range(13):
         want |= ((8191 >> b) & 1) << (3 * b) | ((1 >> b) & 1) << (3 * b + 1) | ((4096 >> b) & 1) << (3 * b + 2)
     assert m == want
+
+
+def test_shortest_repr_rows_match_python_repr(hm):
+    x = repr_cases()
+    x = x[: (x.size // 3) * 3].reshape(-1, 3).copy()
+    out = C.create_string_buffer(x.shape[0] * 76 + 64)
+    n = hm.hm_txt_rows(x.ctypes.data, x.shape[0], 0, out)
+    want = "".join("%r,%r,%r\n" % (a, b, c) for a, b, c in x.tolist())
+    got = out.raw[:n].decode("ascii")
+    if got != want:
+        g, w = got.split("\n"), want.split("\n")
+        bad = [(a, b) for a, b in zip(g, w) if a != b][:5]
+        raise AssertionError("first mismatches (got, want): %r" % bad)
+    # camera txt: Z is the raw integer sample
+    y = x[:5000].copy()
+    y[:, 2] = np.random.default_rng(1).integers(0, 65536, size=5000)
+    n = hm.hm_txt_rows(y.ctypes.data, y.shape[0], 1, out)
+    assert out.raw[:n].decode("ascii") == "".join("%r,%r,%d\n" % (a, b, int(c)) for a, b, c in y.tolist())

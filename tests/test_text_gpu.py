@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from _cases import fixed4_cases
+from _cases import fixed4_cases, repr_cases
 from oracle import points_oracle as po
 
 pytestmark = pytest.mark.gpu
@@ -76,3 +76,30 @@ def test_genply_files_equal_reference_text(ctx, r3d, golden_dir, tmp_path):
     assert p.read_text() == po.genply_text([], [], [])
     with pytest.raises(ValueError):
         transfer.genply([[1.0], [2.0], [3.0]], str(p), 2)
+
+
+def test_txt_rows_match_python_repr(ctx):
+    v = repr_cases()
+    x = v[: (v.size // 3) * 3].reshape(-1, 3).copy()
+    want = "".join("%r,%r,%r\n" % (a, b, c) for a, b, c in x.tolist()).encode()
+    assert ctx.txt_rows(x) == want
+    assert ctx.txt_rows(x[:, 0].copy(), x[:, 1].copy(), x[:, 2].copy()) == want
+    zi = np.random.default_rng(2).integers(0, 65536, size=x.shape[0])
+    want = "".join("%r,%r,%d\n" % (a, b, c) for (a, b, _), c in zip(x.tolist(), zi.tolist())).encode()
+    assert ctx.txt_rows(x[:, 0].copy(), x[:, 1].copy(), zi.astype(np.float64), z_is_integer=True) == want
+    assert ctx.txt_rows(np.zeros((0, 3))) == b""
+
+
+def test_gentxtcord_text_equals_reference(ctx, r3d, golden_dir, tmp_path):
+    """gentxtcord through the GPU formatter writes the bytes the reference wrote (tests/golden: 640x480 frame, sha256)."""
+    import hashlib
+    import json
+    transfer = importlib.import_module("3d_reconstruction_system_b200.transfer")
+    z = np.load(os.path.join(golden_dir, "ref_p2c_640.npz"))
+    meta = json.load(open(os.path.join(golden_dir, "ref_meta.json")))["p2c_640"]
+    p = tmp_path / "p.txt"
+    out = transfer.gentxtcord(str(p), z["depth"])
+    txt = p.read_text()
+    assert txt.splitlines()[:5] == meta["txt_first_lines"]
+    assert hashlib.sha256(txt.encode()).hexdigest() == meta["txt_sha256"]
+    assert np.array_equal(np.asarray(out[0])[z["sel"]], z["X"]) and np.array_equal(np.asarray(out[1])[z["sel"]], z["Y"])
