@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libr3d_b200.so")
 OK = 0
 U8, U16, F32 = 0, 1, 2
 MODE_DEPTH, MODE_DISPARITY = 0, 1
+PNG_GRAY8, PNG_CHANNEL, PNG_RAW = 0, 1, 2
 OUT_F32, OUT_F64 = 0, 1
 DELTA_RECORD_BYTES = 136
 BRICK_RECORD_BYTES = 2120
@@ -36,6 +37,8 @@ SIGNATURES = {
     "r3d_device_alloc": (_vp, [_vp, _sz]),
     "r3d_device_free": (None, [_vp, _vp]),
     "r3d_memcpy": (_i32, [_vp, _vp, _vp, _sz]),
+    "r3d_png_info": (_i32, [C.c_char_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "r3d_png_decode_batch": (_i32, [_vp, _i32, _i32, _i32, _vp, _sz, _i32, _i32, _i32, _i32, _vp]),
     "r3d_pose_to_rt": (_i32, [_vp, _i32, _dbl, _vp]),
     "r3d_backproject_rt": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _vp, _vp]),
     "r3d_backproject": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _vp, _vp]),

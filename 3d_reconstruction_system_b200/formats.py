@@ -58,8 +58,88 @@ def write_pose_file(path, t, q, names):
 # ------------------------------------------------------------------------------------------------ depth images
 
 
+def png_info(path):
+    """(W, H, channels as IMREAD_UNCHANGED shapes them (1 = no axis, 3, 4), bits per sample 8 | 16)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    w, h, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib.r3d_png_info(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), C.byref(d))
+    if rc != 0:
+        msg = lib.r3d_last_error(None).decode("utf-8", "replace")
+        if rc == -5:
+            raise FileNotFoundError(msg)
+        raise ValueError(msg)
+    return w.value, h.value, c.value, d.value
+
+
+def imread_batch(paths, mode="gray", channel=1, out=None, n_threads=0):
+    """Decode a batch of equally sized PNG files on the native thread pool (r3d_png_decode_batch) into one (n, H, W) stack.
+    mode: "gray" = cv.imread(p, IMREAD_GRAYSCALE); "channel" = cv.imread(p, IMREAD_UNCHANGED)[:, :, channel];
+    "raw" = IMREAD_UNCHANGED, first channel of a multi-channel file.  out: optional preallocated (pinned) array."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    paths = [os.fspath(p) for p in paths]
+    n = len(paths)
+    code = {"gray": _lib.PNG_GRAY8, "channel": _lib.PNG_CHANNEL, "raw": _lib.PNG_RAW}[mode]
+    if n == 0:
+        return np.zeros((0, 0, 0), dtype=np.uint8)
+    w, h, _, depth = png_info(paths[0])
+    dt = np.uint8 if (code == _lib.PNG_GRAY8 or depth == 8) else np.uint16
+    if out is None:
+        out = np.empty((n, h, w), dtype=dt)
+    if out.shape != (n, h, w) or out.dtype != dt or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous %s array of shape %r" % (np.dtype(dt).name, (n, h, w)))
+    arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    rc = lib.r3d_png_decode_batch(arr, n, code, int(channel), out.ctypes.data, 0, out.dtype.itemsize, w, h, int(n_threads), None)
+    if rc != 0:
+        msg = lib.r3d_last_error(None).decode("utf-8", "replace")
+        if "cannot open" in msg:
+            raise FileNotFoundError(msg)
+        if "no channel axis" in msg:
+            raise IndexError(msg)
+        raise ValueError(msg)
+    return out
+
+
+def read_frame_batch(paths, mode="gray", max_frames=256):
+    """Longest prefix of `paths` (at most max_frames) that decodes to equally shaped frames of one dtype, as one (n, H, W)
+    stack: PNG prefixes go through the thread-pool decoder in one call, anything else frame by frame.
+    Returns (stack, n_consumed)."""
+    one = {"gray": imread_gray, "raw": imread_raw, "green": imread_unchanged_green}[mode]
+    bmode, chan = {"gray": ("gray", 0), "raw": ("raw", 0), "green": ("channel", 1)}[mode]
+    if not paths:
+        return np.zeros((0, 0, 0), np.uint8), 0
+    if _is_png(paths[0]):
+        w, h, _, d = png_info(paths[0])
+        n = 1
+        while n < len(paths) and n < max_frames and _is_png(paths[n]) and png_info(paths[n])[:2] + (png_info(paths[n])[3],) == (w, h, d):
+            n += 1
+        return imread_batch(paths[:n], bmode, channel=chan), n
+    first = one(paths[0])
+    batch = [first]
+    while len(batch) < len(paths) and len(batch) < max_frames and not _is_png(paths[len(batch)]):
+        img = one(paths[len(batch)])
+        if img.shape != first.shape or img.dtype != first.dtype:
+            break
+        batch.append(img)
+    return np.stack(batch), len(batch)
+
+
+def _is_png(path):
+    try:
+        with open(path, "rb") as f:
+            return f.read(8) == b"\x89PNG\r\n\x1a\n"
+    except OSError:
+        return False
+
+
 def imread_gray(path):
-    """cv.imread(path, IMREAD_GRAYSCALE) (transfer/camera_to_world.py:160): always uint8 (16-bit -> >>8)."""
+    """cv.imread(path, IMREAD_GRAYSCALE) (transfer/camera_to_world.py:160): always uint8 (16-bit -> >>8).  PNG files go
+    through the native decoder; other formats (the reference only uses PNG) through OpenCV."""
+    if _is_png(path):
+        return imread_batch([path], "gray", n_threads=1)[0]
     import cv2
     img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
     if img is None:
@@ -69,6 +149,8 @@ def imread_gray(path):
 
 def imread_unchanged_green(path):
     """cv.imread(path, IMREAD_UNCHANGED)[:, :, 1] (transfer/pixel_to_camera.py:133-134)."""
+    if _is_png(path):
+        return imread_batch([path], "channel", channel=1, n_threads=1)[0]
     import cv2
     img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     if img is None:
@@ -78,6 +160,8 @@ def imread_unchanged_green(path):
 
 def imread_raw(path):
     """Full-precision single-channel depth / disparity (uint8 or uint16), for the metric pipelines."""
+    if _is_png(path):
+        return imread_batch([path], "raw", n_threads=1)[0]
     import cv2
     img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     if img is None:

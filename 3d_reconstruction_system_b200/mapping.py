@@ -92,20 +92,13 @@ def pose_sequence_to_bt(qt_path, file_bt, intr, depth_dir='./depth/', resolution
                         raw_depth=False, **kw):
     """Pose file + depth PNGs -> .bt, the file-level form of sequence_to_octree."""
     poses = formats.read_pose_file(qt_path) if pose_format == "comma" else formats.read_colmap_images_txt(qt_path)
-    read = formats.imread_raw if raw_depth else formats.imread_gray
     tree = None
     k, n = 0, len(poses["names"])
     while k < n:
-        first = read(os.path.join(depth_dir, poses["names"][k]))
-        batch = [first]
-        j = k + 1
-        while j < n and len(batch) < 64:
-            img = read(os.path.join(depth_dir, poses["names"][j]))
-            if img.shape != first.shape or img.dtype != first.dtype:
-                break
-            batch.append(img)
-            j += 1
-        tree = sequence_to_octree(np.stack(batch), poses["q"][k:j], poses["t"][k:j], intr, resolution=resolution, maxrange=maxrange,
+        stack, used = formats.read_frame_batch([os.path.join(depth_dir, nm) for nm in poses["names"][k:k + 64]],
+                                               "raw" if raw_depth else "gray", max_frames=64)
+        j = k + used
+        tree = sequence_to_octree(stack, poses["q"][k:j], poses["t"][k:j], intr, resolution=resolution, maxrange=maxrange,
                                   tree=tree, **kw)
         k = j
     if tree is None:

@@ -162,16 +162,9 @@ def get_file_name(qt_path, intr=None, write_intermediate=True, ply_path=None, po
     k = 0
     while k < n:
         t1 = time.time()
-        first = formats.imread_gray(os.path.join(DEPTH_DIR, poses["names"][k]))
-        batch = [first]
-        j = k + 1
-        while j < n and len(batch) < 256:
-            img = formats.imread_gray(os.path.join(DEPTH_DIR, poses["names"][j]))
-            if img.shape != first.shape:
-                break
-            batch.append(img)
-            j += 1
-        stack = np.stack(batch)
+        stack, used = formats.read_frame_batch([os.path.join(DEPTH_DIR, nm) for nm in poses["names"][k:k + 256]], "gray")
+        j = k + used
+        batch = stack
         world, _ = sequence_to_world(stack, poses["q"][k:j], poses["t"][k:j], intr, out_dtype=np.float64)
         world = world.reshape(j - k, -1, 3)
         if write_intermediate:

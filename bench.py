@@ -274,6 +274,41 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
     return out
 
 
+def png_decode_section(n_frames=64):
+    """a1 beside the GPU numbers: the frame decode that feeds the path.  The reference reads one PNG at a time with
+    cv.imread on one core (transfer/camera_to_world.py:160); the native decoder inflates a batch on every core."""
+    import shutil
+    import tempfile
+    from oracle import points_oracle as po
+    formats = importlib.import_module("3d_reconstruction_system_b200.formats")
+    try:
+        import cv2
+    except Exception:
+        return None
+    d = tempfile.mkdtemp(prefix="r3d_png_")
+    try:
+        paths = []
+        for k in range(n_frames):
+            img = po.synth_depth_u16(W, H, po.KITTI_INTRINSICS, 20261018 + 2 + (k % 8), "street")
+            p = os.path.join(d, "%05d.png" % k)
+            cv2.imwrite(p, np.roll(img, k, axis=1))
+            paths.append(p)
+        size = sum(os.path.getsize(p) for p in paths)
+        formats.imread_batch(paths[:8], "raw")
+        t0 = time.perf_counter()
+        got = formats.imread_batch(paths, "raw")
+        t_native = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ref = [cv2.imread(p, cv2.IMREAD_UNCHANGED) for p in paths[:16]]
+        t_cv = (time.perf_counter() - t0) * n_frames / 16
+        ok = all(np.array_equal(got[i], ref[i]) for i in range(16))
+        return {"frames": n_frames, "png_bytes_per_frame": size // n_frames, "native_frames_per_s": n_frames / t_native, "threads": os.cpu_count(),
+                "cv2_imread_frames_per_s_1core": n_frames / t_cv, "identical_to_cv2": bool(ok),
+                "pixels_per_s": n_frames * W * H / t_native}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def octomap_section_multi(args, torch, dist, r3d, ctx, dev, depth, rt_host, scans_per_gpu, rank, world):
     """OctoMap scans/s on N GPUs: S = scans_per_gpu * N consecutive scans of the sequence; every rank
     ray-casts only its share, the brick-delta records of each round are all-gathered over NCCL and applied in global scan
@@ -458,6 +493,7 @@ def run_gpu_arm(args):
         else:
             octo = octomap_section_multi(args, torch, dist, r3d, ctx, dev, depth, rt_host, args.octomap_scans, rank, world)
 
+    png = png_decode_section() if (rank == 0 and not args.no_cpu_baseline) else None
     if rank == 0:
         peak, peak_src = load_peaks()
         kernel_ms = float(np.mean(per_step))
@@ -479,7 +515,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k1_bulk<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
                          "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo, "png_decode": png,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -73,6 +73,22 @@ void *r3d_device_alloc(r3d_ctx *ctx, size_t bytes);
 void r3d_device_free(r3d_ctx *ctx, void *p);
 int r3d_memcpy(r3d_ctx *ctx, void *dst, const void *src, size_t bytes);
 
+/* ------------------------------------------------------------------ a1: PNG ---- */
+/*
+ * Depth / disparity PNG decode for whole frame batches on a host thread pool (zlib inflate + un-filter + conversion
+ * straight into the caller's frame stack, which may be pinned memory from r3d_host_alloc).  Replaces, for PNG files,
+ *   R3D_PNG_GRAY8   cv.imread(path, IMREAD_GRAYSCALE)          transfer/camera_to_world.py:160  (uint8; 16-bit >> 8)
+ *   R3D_PNG_CHANNEL cv.imread(path, IMREAD_UNCHANGED)[:, :, c] transfer/pixel_to_camera.py:133-134 (c = 1: green)
+ *   R3D_PNG_RAW     IMREAD_UNCHANGED, first channel when there are several (full-precision 16-bit depth / disparity)
+ * bit for bit (pinned against OpenCV 4.13 in tests/test_png_cpu.py).  Every file must be W x H; elem_bytes is 1 for
+ * GRAY8 and the file's sample width (1 or 2) otherwise.  frame_stride_bytes 0 = packed.  n_threads 0 = one per core.
+ * status (optional, n ints) receives R3D_OK / R3D_ERR_IO per file.  Needs no GPU.
+ */
+enum { R3D_PNG_GRAY8 = 0, R3D_PNG_CHANNEL = 1, R3D_PNG_RAW = 2 };
+int r3d_png_info(const char *path, int *W, int *H, int *channels, int *bit_depth);
+int r3d_png_decode_batch(const char *const *paths, int n, int mode, int channel, void *out, size_t frame_stride_bytes,
+                         int elem_bytes, int W, int H, int n_threads, int *status);
+
 /* ------------------------------------------------------------------ poses ------ */
 /*
  * Replaces scipy_transfer(quat) = np.matrix(R.from_quat(quat).as_matrix()).I
