@@ -51,6 +51,7 @@ SIGNATURES = {
     "r3d_tree_clear": (_i32, [_vp]),
     "r3d_tree_reserve": (_i32, [_vp, _u64]),
     "r3d_tree_params": (_i32, [_vp, _vp]),
+    "r3d_tree_resolution": (_i32, [_vp, C.POINTER(_dbl)]),
     "r3d_tree_update_points": (_i32, [_vp, _vp, _u64, _i32, _u64p]),
     "r3d_tree_update_points_f64": (_i32, [_vp, _vp, _u64, _i32, _u64p]),
     "r3d_tree_update_points_logodds": (_i32, [_vp, _vp, _u64, _flt, _u64p]),
@@ -68,6 +69,8 @@ SIGNATURES = {
     "r3d_tree_write_bt": (_i32, [_vp, C.c_char_p]),
     "r3d_tree_write_bt_mem": (_i32, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "r3d_tree_to_max_likelihood": (_i32, [_vp]),
+    "r3d_tree_read_bt": (_i32, [_vp, C.c_char_p]),
+    "r3d_tree_read_bt_mem": (_i32, [_vp, _vp, _sz]),
     "r3d_tree_num_voxels": (_i32, [_vp, _u64p]),
     "r3d_tree_size": (_i32, [_vp, _u64p]),
     "r3d_tree_search": (_i32, [_vp, _vp, _u64, _vp, _vp]),

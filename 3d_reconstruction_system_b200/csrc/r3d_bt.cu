@@ -481,3 +481,149 @@ extern "C" int r3d_tree_write_bt(r3d_tree* t, const char* path) {
     if (!ok) return set_error(t->ctx, R3D_ERR_IO, "short write to %s", path);
     return R3D_OK;
 }
+
+// ------------------------------------------------------------------ .bt reader (section 8f: the step after the path)
+// AbstractOcTree::readBinary / OcTreeBase::readBinaryData of the `octomap` extension: header text, then the pre-order
+// 2-bits-per-child stream; an occupied leaf gets the upper clamping value, a free leaf the lower one.  The stream is
+// walked on the host (it is a few hundred KB) into whole-brick records -- a leaf at depth d <= 13 covers 8^(13-d)
+// bricks -- which the GPU store imports (k_import_bricks).
+namespace r3d {
+
+struct BtReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    float occ, fre;
+    std::vector<BrickRecord> bricks;           // depth-13 nodes in stream order; the last one is under construction
+    bool overflow = false;
+    uint64_t nodes = 1;                        // the root
+
+    // fill voxels [first, first+count) of the brick being built
+    static void fill(BrickRecord& b, uint32_t first, uint32_t count, float v) {
+        for (uint32_t i = first; i < first + count; ++i) { b.value[i] = v; b.known[i >> 5] |= 1u << (i & 31u); }
+    }
+    // a leaf at depth <= 13: every brick below it is completely v.  prefix = Morton code of the node (3 bits per level)
+    void leaf_above_bricks(uint64_t prefix, int depth, float v) {
+        const uint64_t n = 1ull << (3 * (13 - depth));
+        if (bricks.size() + n > (1ull << 24)) { overflow = true; return; }
+        for (uint64_t k = 0; k < n; ++k) {
+            BrickRecord b;
+            memset(&b, 0, sizeof b);
+            b.key = morton_to_brick_key((prefix << (3 * (13 - depth))) | k);
+            fill(b, 0, 512, v);
+            bricks.push_back(b);
+        }
+    }
+    static uint64_t morton_to_brick_key(uint64_t m) {
+        uint64_t x = 0, y = 0, z = 0;
+        for (int i = 0; i < 13; ++i) {
+            x |= ((m >> (3 * i)) & 1ull) << i;
+            y |= ((m >> (3 * i + 1)) & 1ull) << i;
+            z |= ((m >> (3 * i + 2)) & 1ull) << i;
+        }
+        return x | (y << 13) | (z << 26);
+    }
+    // inner node at `depth` (0 = root) with Morton prefix; below depth 13 vox_first is the node's first voxel in its brick
+    bool node(uint64_t prefix, int depth, uint32_t vox_first) {
+        if (p + 2 > end) return false;
+        const unsigned bits = (unsigned)p[0] | ((unsigned)p[1] << 8);
+        p += 2;
+        for (int c = 0; c < 8; ++c) {
+            // child c: bit 2c set -> "free" flag, bit 2c+1 -> "occupied" flag; both -> inner (writeBinaryNode's encoding)
+            const unsigned code = (bits >> (2 * c)) & 3u;
+            if (code == 0u) continue;
+            ++nodes;
+            const int cd = depth + 1;
+            const uint64_t cp = (prefix << 3) | (uint64_t)c;
+            if (cd <= 13) {
+                if (code == 3u) {
+                    if (cd == 13) {
+                        if (bricks.size() >= (1ull << 24)) { overflow = true; return false; }
+                        BrickRecord b;
+                        memset(&b, 0, sizeof b);
+                        b.key = morton_to_brick_key(cp);
+                        bricks.push_back(b);
+                        if (!node(cp, cd, 0)) return false;
+                    } else if (!node(cp, cd, 0)) return false;
+                } else {
+                    leaf_above_bricks(cp, cd, code == 2u ? occ : fre);
+                    if (overflow) return false;
+                }
+            } else {
+                // inside the last brick: voxel range of the child, Morton order = child-index order
+                const uint32_t span = 1u << (3 * (16 - cd));
+                const uint32_t first = vox_first + (uint32_t)c * span;
+                if (code == 3u) { if (!node(cp, cd, first)) return false; }
+                else fill(bricks.back(), first, span, code == 2u ? occ : fre);
+            }
+        }
+        return true;
+    }
+};
+
+}  // namespace r3d
+
+extern "C" int r3d_tree_read_bt_mem(r3d_tree* t, const uint8_t* data, size_t len) {
+    if (!t || (!data && len)) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    r3d_ctx* ctx = t->ctx;
+    // header: lines until "data\n"
+    const char* s = reinterpret_cast<const char*>(data);
+    size_t pos = 0;
+    auto next_line = [&](std::string& line) {
+        if (pos >= len) return false;
+        size_t e = pos;
+        while (e < len && s[e] != '\n') ++e;
+        line.assign(s + pos, e - pos);
+        pos = e < len ? e + 1 : e;
+        return true;
+    };
+    std::string line;
+    if (!next_line(line) || line.rfind("# Octomap OcTree binary file", 0) != 0)
+        return set_error(ctx, R3D_ERR_UNSUPPORTED, "not an OctoMap binary (.bt) file: first line is not '# Octomap OcTree binary file'");
+    std::string id;
+    double res = 0.0;
+    unsigned long long size = 0;
+    bool have_data = false;
+    while (next_line(line)) {
+        if (line.empty() || line[0] == '#') continue;
+        if (line == "data") { have_data = true; break; }
+        char key[32] = {0};
+        char val[128] = {0};
+        if (sscanf(line.c_str(), "%31s %127s", key, val) == 2) {
+            if (!strcmp(key, "id")) id = val;
+            else if (!strcmp(key, "res")) res = atof(val);
+            else if (!strcmp(key, "size")) size = strtoull(val, nullptr, 10);
+        }
+    }
+    if (!have_data) return set_error(ctx, R3D_ERR_UNSUPPORTED, ".bt header has no 'data' line");
+    if (id != "OcTree") return set_error(ctx, R3D_ERR_UNSUPPORTED, ".bt holds a tree of type '%s', only OcTree is supported", id.c_str());
+    if (!(res > 0.0)) return set_error(ctx, R3D_ERR_UNSUPPORTED, ".bt header has no valid resolution");
+    DeviceSetter ds(ctx->device);
+    R3D_TRY(r3d_tree_clear(t));
+    t->res = res;
+    t->res_factor = 1.0 / res;
+    if (size == 0) return R3D_OK;
+    BtReader rd;
+    rd.p = data + pos;
+    rd.end = data + len;
+    rd.occ = t->cmax;
+    rd.fre = t->cmin;
+    if (!rd.node(0, 0, 0)) {
+        if (rd.overflow) return set_error(ctx, R3D_ERR_OOM, ".bt expands to more than 2^24 bricks");
+        return set_error(ctx, R3D_ERR_IO, ".bt payload is truncated");
+    }
+    if (rd.nodes != size) return set_error(ctx, R3D_ERR_IO, ".bt header says %llu nodes, the stream holds %llu", size, (unsigned long long)rd.nodes);
+    if (!rd.bricks.empty()) R3D_TRY(r3d_tree_import_bricks(t, rd.bricks.data(), rd.bricks.size()));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_read_bt(r3d_tree* t, const char* path) {
+    if (!t || !path) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(t->ctx, R3D_ERR_IO, "cannot open %s", path);
+    std::vector<uint8_t> buf;
+    uint8_t chunk[1 << 16];
+    size_t n;
+    while ((n = fread(chunk, 1, sizeof chunk, f)) > 0) buf.insert(buf.end(), chunk, chunk + n);
+    fclose(f);
+    return r3d_tree_read_bt_mem(t, buf.data(), buf.size());
+}

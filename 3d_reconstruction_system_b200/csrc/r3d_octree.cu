@@ -1117,6 +1117,12 @@ extern "C" int r3d_tree_reserve(r3d_tree* t, uint64_t n_bricks) {
     return finish(t->ctx);
 }
 
+extern "C" int r3d_tree_resolution(r3d_tree* t, double* res) {
+    if (!t || !res) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    *res = t->res;
+    return R3D_OK;
+}
+
 extern "C" int r3d_tree_params(r3d_tree* t, float out[5]) {
     if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
     out[0] = t->hit; out[1] = t->miss; out[2] = t->cmin; out[3] = t->cmax; out[4] = t->occ_thres;

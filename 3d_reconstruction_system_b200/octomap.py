@@ -113,6 +113,30 @@ class OcTree:
         check(rc, self._ctx.handle)
         return True
 
+    def readBinary(self, source):
+        """readBinary(bytes path | str path) -> bool, or readBinary(file content as bytes starting with '# Octomap'):
+        replaces the tree (and its resolution) with the .bt file's content."""
+        self._pend_pts, self._pend_upd = [], []
+        if isinstance(source, (bytes, bytearray)) and bytes(source[:9]) == b"# Octomap":
+            buf = np.frombuffer(bytes(source), dtype=np.uint8)
+            check(self._lib.r3d_tree_read_bt_mem(self._h, buf.ctypes.data, buf.size), self._ctx.handle)
+        else:
+            if isinstance(source, str):
+                source = source.encode("utf-8")
+            rc = self._lib.r3d_tree_read_bt(self._h, bytes(source))
+            if rc == -5 and b"cannot open" in self._lib.r3d_last_error(self._ctx.handle):
+                return False
+            check(rc, self._ctx.handle)
+        p = (C.c_float * 5)()
+        check(self._lib.r3d_tree_params(self._h, p), self._ctx.handle)
+        self._res = float(self.getResolutionFromLibrary())
+        return True
+
+    def getResolutionFromLibrary(self):
+        r = C.c_double(0)
+        check(self._lib.r3d_tree_resolution(self._h, C.byref(r)), self._ctx.handle)
+        return r.value
+
     # ------------------------------------------------------------------ further binding methods
     def getResolution(self):
         return self._res

@@ -177,6 +177,7 @@ int r3d_tree_clear(r3d_tree *tree);
 int r3d_tree_reserve(r3d_tree *tree, uint64_t n_bricks);
 /* out[5] = hit, miss, clamp_min, clamp_max, occupancy threshold (float32 log-odds). */
 int r3d_tree_params(r3d_tree *tree, float out[5]);
+int r3d_tree_resolution(r3d_tree *tree, double *resolution);   /* tree.getResolution() */
 
 /*
  * tree.updateNode(point, True|False) for n points in call order
@@ -246,6 +247,13 @@ int r3d_tree_write_bt(r3d_tree *tree, const char *path);
 /* Same into caller memory: header+payload; *len receives the size needed even when cap is too small. */
 int r3d_tree_write_bt_mem(r3d_tree *tree, uint8_t *buf, size_t cap, size_t *len);
 int r3d_tree_to_max_likelihood(r3d_tree *tree);
+/*
+ * tree.readBinary(path) of the `octomap` module (the step after the path: what octovis and the thesis' viewers do with
+ * the .bt files of octomap/txt_transfer_octomap.py:36): replaces the tree's content (and resolution) with the file's;
+ * occupied leaves get the upper clamping log-odds, free leaves the lower one, pruned leaves are expanded to voxels.
+ */
+int r3d_tree_read_bt(r3d_tree *tree, const char *path);
+int r3d_tree_read_bt_mem(r3d_tree *tree, const uint8_t *data, size_t len);
 
 /* Queries used by tests / tools. */
 int r3d_tree_num_voxels(r3d_tree *tree, uint64_t *n);            /* depth-16 leaves ever updated */

@@ -294,3 +294,53 @@ def test_dropped_points_and_device_buffers(octomap):
     t.insertPointCloud(d[100:2000], origin, maxrange=4.0)
     r.insertPointCloud_f32(pts[100:2000], origin, 4.0)
     assert_same_tree(t, r)
+
+
+def test_read_binary_roundtrip(octomap, tmp_path):
+    """writeBinary -> readBinary -> writeBinary is the identity on the bytes; every voxel comes back at the clamping value
+    of its occupancy; pruned leaves (whole bricks and larger) expand to voxels."""
+    rng = np.random.default_rng(31)
+    t = octomap.OcTree(0.1)
+    origin = np.array([0.2, -0.1, 0.3])
+    t.insertPointCloud(_scan(rng, 20000, origin, far=25.0), origin, maxrange=20.0)
+    # a solid block so that pruning reaches above brick level (depth 12 = 16^3 voxels)
+    g = (np.arange(32) + 0.5) * 0.1 + 40.0
+    t.updateNodes(np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3), True)
+    bt = t.writeBinary()
+    p = tmp_path / "a.bt"
+    assert t.writeBinary(bytes(str(p), "utf-8"))
+    u = octomap.OcTree(0.5)                      # resolution comes from the file
+    assert u.readBinary(bytes(str(p), "utf-8"))
+    assert u.getResolution() == 0.1
+    assert u.writeBinary() == bt
+    k0, v0 = t.voxels()
+    k1, v1 = u.voxels()
+    assert np.array_equal(k0, k1)
+    want = np.where(v0 >= 0, np.float32(t._cmax), np.float32(t._cmin))
+    assert np.array_equal(v1.view(np.uint32), want.view(np.uint32))
+    assert u.size() == oo_size_after_ml(t, octomap)
+    # from memory, then keep mapping into the loaded tree
+    w = octomap.OcTree(0.1)
+    assert w.readBinary(bt)
+    assert w.writeBinary() == bt
+    w.insertPointCloud(_scan(rng, 500, origin, far=5.0), origin, maxrange=-1.0)
+    assert w.numVoxels() >= u.numVoxels()
+    # the oracle's files load too
+    r = oo.OcTree(0.05)
+    pts = rng.normal(scale=1.5, size=(5000, 3))
+    r.updateNodes(pts, True)
+    rb = r.write_binary_bytes()
+    x = octomap.OcTree(0.1)
+    assert x.readBinary(rb) and x.getResolution() == 0.05 and x.writeBinary() == rb
+    assert not octomap.OcTree(0.1).readBinary(bytes(str(tmp_path / "missing.bt"), "utf-8"))
+    with pytest.raises(Exception):
+        octomap.OcTree(0.1).readBinary(bt[:len(bt) // 2])
+    empty = octomap.OcTree(0.25).writeBinary()
+    e = octomap.OcTree(0.1)
+    assert e.readBinary(empty) and e.numVoxels() == 0 and e.writeBinary() == empty
+
+
+def oo_size_after_ml(tree, octomap):
+    """size() of the max-likelihood, pruned tree = the `size` field writeBinary puts in the header."""
+    hdr = tree.writeBinary().split(b"data\n")[0].decode()
+    return int([ln for ln in hdr.splitlines() if ln.startswith("size ")][0].split()[1])
