@@ -1246,6 +1246,26 @@ extern "C" int r3d_tree_insert_scan(r3d_tree* t, const float* xyz, uint64_t n, c
     return finish(t->ctx);
 }
 
+extern "C" int r3d_tree_insert_scans(r3d_tree* t, const float* xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans,
+                                     double maxrange, int discretize) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (n_scans && (!n_points || !origins)) return set_error(ctx, R3D_ERR_ARG, "null scan table");
+    if (is_device_ptr(n_points) || is_device_ptr(origins)) return set_error(ctx, R3D_ERR_ARG, "n_points / origins must be host arrays");
+    DeviceSetter ds(ctx->device);
+    uint64_t off = 0, rays = 0, steps = 0;
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        R3D_TRY(scan_delta_impl(t, xyz ? xyz + off * 3 : nullptr, n_points[s], origins + 3 * (size_t)s, maxrange, discretize));
+        R3D_TRY(apply_delta_impl(t, t->delta, t->delta_n));
+        off += n_points[s];
+        rays += t->last_scan_rays;
+        steps += t->last_scan_steps;
+    }
+    t->last_scan_rays = rays;       // totals of the batch
+    t->last_scan_steps = steps;
+    return finish(ctx);
+}
+
 extern "C" int r3d_delta_expand_keys(const void* records_host, uint64_t n_records, uint16_t* free_keys, uint64_t free_cap,
                                      uint64_t* n_free, uint16_t* occ_keys, uint64_t occ_cap, uint64_t* n_occ) {
     if (!records_host && n_records) return set_error(nullptr, R3D_ERR_ARG, "null records");

@@ -82,8 +82,7 @@ def sequence_to_octree(depths, quats, trans, intr, resolution=0.1, maxrange=80.0
             # the batch's world points never leave the GPU between the two kernels
             xyz = ctx.device_empty(((b - a) * H * W, 3), np.float32)
             ctx.backproject(depths[a:b], intr, rt=rt[a:b], mode=mode, depth_scale=depth_scale, fB=fB, out=xyz)
-            for k in range(a, b):
-                tree.insertPointCloud(xyz[(k - a) * H * W:(k - a + 1) * H * W], camera_centre(rt[k]), maxrange=maxrange)
+            tree.insertPointClouds(xyz, [camera_centre(rt[k]) for k in range(a, b)], maxrange=maxrange)
             xyz.free()
     return tree
 

@@ -86,6 +86,31 @@ class OcTree:
             ptr, n = _ptr(pointcloud), int(pointcloud.shape[0])
         check(self._lib.r3d_tree_insert_scan(self._h, ptr, n, oa, float(maxrange), 1 if discretize else 0), self._ctx.handle)
 
+    def insertPointClouds(self, pointclouds, origins, maxrange=-1.0, discretize=False, counts=None):
+        """A sequence of insertPointCloud calls in one library call.  pointclouds: (S, N, 3) float32 host array or device
+        buffer (scans back to back), or a flat (sum N_s, 3) buffer with `counts` giving N_s; origins: (S, 3)."""
+        self._flush()
+        o = np.ascontiguousarray(np.asarray(origins, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+        S = o.shape[0]
+        if isinstance(pointclouds, np.ndarray):
+            p = np.ascontiguousarray(pointclouds, dtype=np.float32)
+            ptr = p.ctypes.data
+            total = p.size // 3
+        else:
+            p = pointclouds
+            ptr = _ptr(p)
+            total = int(np.prod(p.shape)) // 3
+        if counts is None:
+            if S == 0 or total % S:
+                raise ValueError("pointclouds do not divide into %d equal scans; pass counts" % S)
+            cnt = np.full(S, total // S, dtype=np.uint64)
+        else:
+            cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+            if cnt.size != S or int(cnt.sum()) != total:
+                raise ValueError("counts do not match the point buffer")
+        check(self._lib.r3d_tree_insert_scans(self._h, ptr, cnt.ctypes.data, o.ctypes.data, S, float(maxrange), 1 if discretize else 0),
+              self._ctx.handle)
+
     def lastScanStats(self):
         """dict(rays, steps, records, bricks) of the most recent insertPointCloud / computeScanDelta."""
         a = (C.c_uint64 * 4)()

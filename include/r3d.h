@@ -200,6 +200,11 @@ int r3d_tree_update_points_logodds(r3d_tree *tree, const float *xyz, uint64_t n,
  */
 int r3d_tree_insert_scan(r3d_tree *tree, const float *xyz, uint64_t n, const float origin[3], double maxrange,
                          int discretize);
+/* n_scans consecutive insertPointCloud calls in one library call (no per-scan trip through the caller's language):
+ * scan s has n_points[s] points stored back to back in xyz (host or device) and origin origins[3 s .. 3 s + 2] (host).
+ * r3d_tree_last_scan_stats then reports the totals of the batch. */
+int r3d_tree_insert_scans(r3d_tree *tree, const float *xyz, const uint64_t *n_points, const float *origins, uint32_t n_scans,
+                          double maxrange, int discretize);
 /*
  * The two halves of r3d_tree_insert_scan, for multi-GPU merging:
  * compute the scan's delta (set of free / occupied voxels) without touching the tree, export it as

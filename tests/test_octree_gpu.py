@@ -344,3 +344,21 @@ def oo_size_after_ml(tree, octomap):
     """size() of the max-likelihood, pruned tree = the `size` field writeBinary puts in the header."""
     hdr = tree.writeBinary().split(b"data\n")[0].decode()
     return int([ln for ln in hdr.splitlines() if ln.startswith("size ")][0].split()[1])
+
+
+def test_insert_point_clouds_batch_equals_loop(octomap):
+    rng = np.random.default_rng(41)
+    S, N = 5, 3000
+    origins = np.array([[0.3 * s, -0.1 * s, 0.05] for s in range(S)])
+    scans = np.stack([_scan(rng, N, origins[s], far=15.0) for s in range(S)]).astype(np.float32)
+    a, b, r = octomap.OcTree(0.1), octomap.OcTree(0.1), oo.OcTree(0.1)
+    for s in range(S):
+        a.insertPointCloud(scans[s], origins[s], maxrange=12.0)
+        r.insertPointCloud_f32(scans[s], origins[s], 12.0)
+    b.insertPointClouds(scans, origins, maxrange=12.0)
+    assert b.lastScanStats()["rays"] == S * N
+    ragged = octomap.OcTree(0.1)
+    ragged.insertPointClouds(np.concatenate([scans[0], scans[1][:100], scans[2]]), origins[:3], maxrange=12.0, counts=[N, 100, N])
+    assert ragged.numVoxels() > 0
+    assert a.writeBinary() == b.writeBinary()
+    assert_same_tree(b, r)
