@@ -1043,7 +1043,10 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
 static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1) {
     r3d_ctx* ctx = t->ctx;
     if (n == 0) return R3D_OK;
-    // sized from the host-side upper bound of the pool cursor: no read-back between a scan's apply and the next scan
+    // sized from the host-side upper bound of the pool cursor: no read-back between a scan's apply and the next scan.
+    // When the BOUND (not necessarily the pool) would outgrow the capacity, read the exact cursor back first: several
+    // applies in a row (multi-GPU rounds) inflate the bound by every record, most of which hit existing bricks.
+    if (t->pool_dirty && t->pool_bound + n > t->pool_cap) R3D_TRY(tree_settle(t));
     R3D_TRY(tree_reserve_table(t, t->pool_bound + n));
     R3D_TRY(tree_reserve_pool(t, t->pool_bound + n));
     k_apply_delta<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(d_recs, (uint32_t)n, t->tkeys, t->tvals, t->tcap, t->values, t->known,
@@ -1263,6 +1266,47 @@ extern "C" int r3d_tree_insert_scans(r3d_tree* t, const float* xyz, const uint64
     }
     t->last_scan_rays = rays;       // totals of the batch
     t->last_scan_steps = steps;
+    return finish(ctx);
+}
+
+extern "C" int r3d_scan_deltas_compute(r3d_tree* t, const float* xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans,
+                                       double maxrange, int discretize, void* records, uint64_t capacity_records, uint64_t* counts) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (n_scans && (!n_points || !origins || !counts)) return set_error(ctx, R3D_ERR_ARG, "null scan table");
+    DeviceSetter ds(ctx->device);
+    uint64_t off = 0, used = 0;
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        R3D_TRY(scan_delta_impl(t, xyz ? xyz + off * 3 : nullptr, n_points[s], origins + 3 * (size_t)s, maxrange, discretize));
+        off += n_points[s];
+        counts[s] = t->delta_n;
+        if (used + t->delta_n > capacity_records) {
+            // report what is needed so far; the caller grows the buffer and calls again from scan s
+            for (uint32_t r = s + 1; r < n_scans; ++r) counts[r] = 0;
+            return set_error(ctx, R3D_ERR_OOM, "record buffer holds %llu records, scan %u needs %llu in total so far",
+                             (unsigned long long)capacity_records, s, (unsigned long long)(used + t->delta_n));
+        }
+        if (t->delta_n)
+            R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)records + used * sizeof(DeltaRecord), t->delta, t->delta_n * sizeof(DeltaRecord), cudaMemcpyDefault, ctx->stream));
+        used += t->delta_n;
+    }
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_apply_deltas_owned(r3d_tree* t, const void* records, const uint64_t* counts, uint32_t n_scans, uint32_t part, uint32_t nparts) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (n_scans && (!records || !counts)) return set_error(ctx, R3D_ERR_ARG, "null argument");
+    if (nparts == 0 || part >= nparts) return set_error(ctx, R3D_ERR_ARG, "bad partition %u of %u", part, nparts);
+    if (n_scans && !is_device_ptr(records)) return set_error(ctx, R3D_ERR_ARG, "r3d_tree_apply_deltas_owned expects device records");
+    DeviceSetter ds(ctx->device);
+    const DeltaRecord* d = reinterpret_cast<const DeltaRecord*>(records);
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        if (counts[s] > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "too many records");
+        R3D_TRY(apply_delta_impl(t, d, counts[s], part, nparts));
+        d += counts[s];
+    }
     return finish(ctx);
 }
 

@@ -264,6 +264,28 @@ class OcTree:
         check(self._lib.r3d_scan_delta_compute(self._h, ptr, n, oa, float(maxrange), 1 if discretize else 0, C.byref(cnt)), self._ctx.handle)
         return int(cnt.value)
 
+    def computeScanDeltasInto(self, pointclouds, counts, origins, maxrange, out_ptr, capacity_records, discretize=False):
+        """Ray-cast len(origins) scans (points back to back in one float32 device / host buffer, `counts` points each)
+        into the record buffer at out_ptr.  Returns per-scan record counts; raises MemoryError when the buffer is too
+        small (the counts so far are in the exception's args[1])."""
+        self._flush()
+        o = np.ascontiguousarray(np.asarray(origins, dtype=np.float64).astype(np.float32)).reshape(-1, 3)
+        cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+        rec = np.zeros(o.shape[0], dtype=np.uint64)
+        ptr = pointclouds.ctypes.data if isinstance(pointclouds, np.ndarray) else _ptr(pointclouds)
+        rc = self._lib.r3d_scan_deltas_compute(self._h, ptr, cnt.ctypes.data, o.ctypes.data, o.shape[0], float(maxrange), 1 if discretize else 0,
+                                               _ptr(out_ptr), int(capacity_records), rec.ctypes.data)
+        if rc == -3:
+            raise MemoryError(self._lib.r3d_last_error(self._ctx.handle).decode(), rec)
+        check(rc, self._ctx.handle)
+        return rec
+
+    def applyDeltasOwned(self, records_ptr, counts, part=0, nparts=1):
+        """Apply consecutive deltas (device records back to back, counts[s] each) in order, restricted to owned bricks."""
+        self._flush()
+        cnt = np.ascontiguousarray(counts, dtype=np.uint64)
+        check(self._lib.r3d_tree_apply_deltas_owned(self._h, _ptr(records_ptr), cnt.ctypes.data, cnt.size, int(part), int(nparts)), self._ctx.handle)
+
     def scanDeltaInto(self, buf, capacity_records):
         """Export the last computed delta into a caller buffer (host array or device tensor); returns the record count."""
         cnt = C.c_uint64(0)

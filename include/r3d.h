@@ -231,6 +231,12 @@ int r3d_tree_apply_delta_owned(r3d_tree *tree, const void *records, uint64_t n_r
 int r3d_tree_num_bricks(r3d_tree *tree, uint64_t *n);
 int r3d_tree_export_bricks(r3d_tree *tree, void *records, uint64_t capacity_records, uint64_t *n_records);
 int r3d_tree_import_bricks(r3d_tree *tree, const void *records, uint64_t n_records);
+/* Batched forms for the multi-GPU rounds: n_scans deltas computed back to back into one record buffer (counts[s] records
+ * each; R3D_ERR_OOM when the buffer is too small), and n_scans deltas (device memory, back to back) applied in order. */
+int r3d_scan_deltas_compute(r3d_tree *tree, const float *xyz, const uint64_t *n_points, const float *origins, uint32_t n_scans,
+                            double maxrange, int discretize, void *records, uint64_t capacity_records, uint64_t *counts);
+int r3d_tree_apply_deltas_owned(r3d_tree *tree, const void *records, const uint64_t *counts, uint32_t n_scans, uint32_t part,
+                                uint32_t nparts);
 /* Expand delta records to explicit OcTreeKeys (n x 3 uint16) for inspection / parity tests (host buffers). */
 int r3d_delta_expand_keys(const void *records_host, uint64_t n_records, uint16_t *free_keys, uint64_t free_cap,
                           uint64_t *n_free, uint16_t *occ_keys, uint64_t occ_cap, uint64_t *n_occ);

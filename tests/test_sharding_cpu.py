@@ -47,13 +47,13 @@ def test_brick_owner_matches_kernel_hash(r3d):
     assert np.bincount(own, minlength=8).min() > 11000      # balanced
 
 
-@pytest.mark.parametrize("world,n_scans,per_rank", [(2, 23, 3), (3, 10, 2), (2, 4, 4)])
-def test_scan_ordered_merge_gloo(world, n_scans, per_rank):
+@pytest.mark.parametrize("world,n_scans,per_rank,mode", [(2, 23, 3, "plain"), (3, 10, 2, "plain"), (2, 4, 4, "plain"), (2, 17, 2, "overlap")])
+def test_scan_ordered_merge_gloo(world, n_scans, per_rank, mode):
     port = free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="1")
-        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "workers", "gloo_merge_worker.py"), str(n_scans), str(per_rank)],
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "workers", "gloo_merge_worker.py"), str(n_scans), str(per_rank), mode],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
     for p in procs:

@@ -64,6 +64,7 @@ def apply_keys(tree, free, occ):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     n_scans, per_rank = int(sys.argv[1]), int(sys.argv[2])
+    overlap = len(sys.argv) > 3 and sys.argv[3] == "overlap"
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"], rank=rank, world_size=world)
     res, maxrange = 0.1, 2.5
     caster = oo.OcTree(res)          # never updated: only computeUpdate
@@ -92,7 +93,7 @@ def main():
         apply_keys(tree, free, occ)
 
     applied = sharding.merged_insert(n_scans, rank, world, compute_delta, apply_delta, lambda nb: torch.zeros(64, dtype=torch.uint8),
-                                     scans_per_rank=per_rank)
+                                     scans_per_rank=per_rank, overlap=overlap)
     # serial reference on every rank
     ref = oo.OcTree(res)
     ref_log = []

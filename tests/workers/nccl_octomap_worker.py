@@ -52,9 +52,14 @@ def main():
     want_bt = serial.writeBinary()
     wk, wv = serial.voxels()
 
-    for owner in (False, True):
+    def get_scan_batch(first, n):
+        got = [get_scan(first + i) for i in range(n)]
+        return np.concatenate([g[0] for g in got]), [g[0].shape[0] for g in got], np.stack([g[1] for g in got])
+
+    for owner, batched in ((False, False), (True, False), (True, True), (False, True)):
         tree = octomap.OcTree(res, ctx=ctx)
-        sh = sharding.OctreeSharder(tree, get_scan, maxrange=maxrange, owner_partition=owner, rank=rank, world=world)
+        sh = sharding.OctreeSharder(tree, get_scan, maxrange=maxrange, owner_partition=owner, rank=rank, world=world,
+                                    get_scan_batch=get_scan_batch if batched else None)
         scans.clear()
         sh.run(n_scans, scans_per_rank=per_rank)
         mine = sorted(scans)
