@@ -208,3 +208,58 @@ def test_point_camera_and_transform_points(ctx, golden_dir):
     out = ctx.transform_points(cam, T)
     want = np.stack([((T[i, 0] * cam[:, 0] + T[i, 1] * cam[:, 1]) + T[i, 2] * cam[:, 2]) + T[i, 3] for i in range(3)], axis=1)
     assert np.array_equal(out, want)
+
+
+def test_c5_shape_1920x1080_bit_exact(ctx):
+    """BASELINE config 5 frame shape (1920x1080 RGBD): bit-exact against the oracle, float64 and float32 records."""
+    rng = np.random.default_rng(55)
+    n, H, W = 2, 1080, 1920
+    depths = rng.integers(0, 65536, size=(n, H, W)).astype(np.uint16)
+    intr = (1050.0, 1050.0, 959.5, 539.5)
+    rt = random_rt(n, rng)
+    _, world_ref = oracle_batch(depths, intr, rt, 0, 1.0 / 256.0)
+    got64, _ = ctx.backproject(depths, intr, rt=rt, depth_scale=1.0 / 256.0, out_dtype=np.float64)
+    assert np.array_equal(got64, world_ref)
+    got32, _ = ctx.backproject(depths, intr, rt=rt, depth_scale=1.0 / 256.0)
+    assert np.array_equal(got32, world_ref.astype(np.float32))
+
+
+def test_c2_full_size_properties(ctx):
+    """BASELINE config 2 at full size (4 500 x 1242x375 frames, 2.1 G points, 29 GB of traffic), device resident:
+    the one-launch result equals a chunked recomputation bit for bit (tile / CTA decomposition invariance), frames at
+    sampled positions equal the oracle, and re-running is idempotent."""
+    torch = pytest.importorskip("torch")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70 << 30:
+        pytest.skip("needs ~60 GB of free device memory")
+    dev = torch.device("cuda", 0)
+    n, H, W = 4500, 375, 1242
+    g = torch.Generator(device=dev)
+    g.manual_seed(20261018)
+    depth = torch.randint(0, 32768, (n, H, W), dtype=torch.int16, device=dev, generator=g)      # uint16 bit patterns
+    depth[7] = 0
+    q = np.stack([po.synth_pose(k, n)[0] for k in range(n)])
+    t = np.stack([po.synth_pose(k, n)[1] for k in range(n)])
+    rt_h = ctx.pose_to_rt(q, t)
+    rt = torch.from_numpy(rt_h).to(dev)
+    whole = torch.empty((n * H * W, 3), dtype=torch.float32, device=dev)
+    parts = torch.empty((n * H * W, 3), dtype=torch.float32, device=dev)
+    cnt = np.zeros(n, np.uint64)
+    ctx.backproject(depth, po.KITTI_INTRINSICS, rt=rt, depth_scale=1 / 256.0, out=whole, shape=(n, H, W), counts=cnt)
+    assert int(cnt.sum()) == n * H * W
+    step = 613                                          # not a divisor of anything in the tiling
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        ctx.backproject(depth[a:b], po.KITTI_INTRINSICS, rt=rt[a:b], depth_scale=1 / 256.0, out=parts[a * H * W:b * H * W], shape=(b - a, H, W),
+                        counts=np.zeros(b - a, np.uint64))
+    ctx.synchronize()
+    assert torch.equal(whole.view(torch.int32), parts.view(torch.int32))
+    for k in (0, 7, 2250, 4499):
+        d = depth[k].cpu().numpy().view(np.uint16)
+        _, wref = po.depth_to_world(d, po.KITTI_INTRINSICS, rt_h[k, :9].reshape(3, 3), rt_h[k, 9:], 0, 1 / 256.0)
+        assert np.array_equal(whole[k * H * W:(k + 1) * H * W].cpu().numpy(), wref.astype(np.float32))
+    ctx.backproject(depth, po.KITTI_INTRINSICS, rt=rt, depth_scale=1 / 256.0, out=parts, shape=(n, H, W), counts=cnt)
+    ctx.synchronize()
+    assert torch.equal(whole.view(torch.int32), parts.view(torch.int32))
+    del whole, parts, depth
+    torch.cuda.empty_cache()

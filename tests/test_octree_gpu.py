@@ -362,3 +362,32 @@ def test_insert_point_clouds_batch_equals_loop(octomap):
     assert ragged.numVoxels() > 0
     assert a.writeBinary() == b.writeBinary()
     assert_same_tree(b, r)
+
+
+def test_c4_airsim_disparity_octree_005(octomap, r3d):
+    """BASELINE config 4: 640x480 disparity (PSMNet-style uint16/256) -> Z = fx*B/d -> world -> insertPointCloud at 0.05 m,
+    80 m (the dense scan scratch is 405^3 brick cells here), against the oracle on a sub-sampled frame."""
+    ctx = r3d.default_context(0)
+    intr = po.AIRSIM_INTRINSICS
+    W, H, B = 640, 480, 0.25
+    z = po.synth_depth_u16(W, H, intr, 20261018 + 4, "street").astype(np.float64) / 256.0
+    disp = np.where(z > 0, np.round(256.0 * intr[0] * B / np.maximum(z, 1e-9)), 0).clip(0, 65535).astype(np.uint16)
+    q, tr = po.synth_pose(500, 1000, step=0.2)
+    rt = ctx.pose_to_rt(q, tr)
+    world, _ = ctx.backproject(disp, intr, rt=rt, mode=po.MODE_DISPARITY, depth_scale=1.0 / 256.0, fB=intr[0] * B)
+    _, wref = po.depth_to_world(disp, intr, rt[0, :9].reshape(3, 3), rt[0, 9:], po.MODE_DISPARITY, 1.0 / 256.0, intr[0] * B)
+    assert np.array_equal(world, wref.astype(np.float32))
+    world = world[::5]
+    origin = po.camera_centre(rt[0, :9].reshape(3, 3), rt[0, 9:])
+    t, r = octomap.OcTree(0.05), oo.OcTree(0.05)
+    t.insertPointCloud(world, origin, maxrange=80.0)
+    r.insertPointCloud_f32(world, origin, 80.0)
+    assert_same_tree(t, r)
+    # idempotence of the read-only passes
+    bt = t.writeBinary()
+    t.updateInnerOccupancy()
+    assert t.writeBinary() == bt
+    t.toMaxLikelihood()
+    assert t.writeBinary() == bt
+    t.toMaxLikelihood()
+    assert t.writeBinary() == bt
