@@ -13,6 +13,8 @@
 //     512-bit occupied mask and a 512-bit free mask, filled by the ray-casting kernel (K3) with atomicOr, then
 //     compacted to 136-byte records and applied to the store by the clamped log-odds kernel (K4).  Records are
 //     what multi-GPU runs exchange.
+#include <vector>
+
 #include "r3d_octree.cuh"
 
 namespace r3d {
@@ -237,7 +239,8 @@ __device__ __forceinline__ bool dense_step(const ScanArgs& a, uint64_t* masks64,
     return !done;
 }
 
-__global__ void __launch_bounds__(K3_THREADS, 3) k_scan_raycast_dense(const ScanArgs a, unsigned long long* ray_counter) {
+__global__ void __launch_bounds__(K3_THREADS, 3) k_scan_raycast_dense(const ScanArgs a, unsigned long long* ray_counter, const uint32_t* abort_flag) {
+    if (__ldcg(abort_flag)) return;   // an earlier scan of the pipeline is waiting for the host: leave the scratch alone
     const unsigned lane = threadIdx.x & 31u;
     uint64_t* const masks64 = reinterpret_cast<uint64_t*>(a.cmasks);
     uint8_t* const touched = reinterpret_cast<uint8_t*>(a.ctouched);
@@ -315,7 +318,9 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_raycast_dense(const Scan
 }
 
 // dense mode read-back, step 1: list the touched cells (one byte per cell, four cells per thread and load)
-__global__ void k_cells_list(const uint32_t* __restrict__ touched, uint32_t n_words, uint32_t* list, uint32_t cap, uint32_t* counters) {
+__global__ void k_cells_list(const uint32_t* __restrict__ touched, uint32_t n_words, uint32_t* list, uint32_t cap, uint32_t* counters,
+                             const uint32_t* abort_flag) {
+    if (__ldcg(abort_flag)) return;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
         const uint32_t w = touched[i];
@@ -332,9 +337,14 @@ __global__ void k_cells_list(const uint32_t* __restrict__ touched, uint32_t n_wo
 // step 2: one warp per listed cell -> record (free already minus occupied); clears the cell and its bit.  Does nothing
 // when the list overflowed (the host grows the buffers and runs both steps again: the masks are still intact).
 __global__ void __launch_bounds__(256) k_cells_emit(uint32_t* cmasks, uint8_t* touched, const uint32_t* __restrict__ list, uint32_t cap,
-                                                    const uint32_t* counters, DeltaRecord* out, int gx0, int gy0, int gz0, uint32_t gdim) {
+                                                    const uint32_t* counters, DeltaRecord* out, int gx0, int gy0, int gz0, uint32_t gdim,
+                                                    uint32_t* abort_flag, int set_abort) {
+    if (__ldcg(abort_flag)) return;
     const uint32_t n = counters[CNT_DELTA];
-    if (n > cap) return;
+    if (n > cap) {   // pipelined use: stop every queued scan kernel until the host has grown the buffers and listed again
+        if (set_abort && blockIdx.x == 0 && threadIdx.x == 0) atomicExch(abort_flag, 1u);
+        return;
+    }
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += warps) {
@@ -698,6 +708,7 @@ int tree_settle(r3d_tree* t) {
 // zero every per-scan counter with one memset (everything but the pool cursor and the sticky apply-overflow flag)
 static int tree_reset_scan_counters(r3d_tree* t) {
     r3d_ctx* ctx = t->ctx;
+    // (includes the pipeline's abort flag: the serial path must never inherit one from a failed pipelined batch)
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + 1, 0, (CNT_APPLY_OVERFLOW - 1) * sizeof(uint32_t), ctx->stream));
     return R3D_OK;
 }
@@ -936,7 +947,7 @@ static int scan_delta_dense(r3d_tree* t, const ScanArgs& a0, bool* fallback) {
         const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
         if (blocks > need) blocks = need;
         cudaEventRecord(ctx->ev_a, ctx->stream);
-        k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
+        k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter, t->counters + CNT_ABORT);
         cudaEventRecord(ctx->ev_b, ctx->stream);
         ctx->launches++;
     }
@@ -945,9 +956,10 @@ static int scan_delta_dense(r3d_tree* t, const ScanArgs& a0, bool* fallback) {
         R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)t->delta_cap * 4 + 256));
         if (attempt) R3D_TRY(tree_set_counter(t, CNT_DELTA, 0));
         k_cells_list<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(a.ctouched, n_words, (uint32_t*)ctx->scratch[SCR_TILE],
-                                                                              (uint32_t)t->delta_cap, t->counters);
+                                                                              (uint32_t)t->delta_cap, t->counters, t->counters + CNT_ABORT);
         k_cells_emit<<<grid_for(ctx, (uint64_t)t->delta_cap * 32, 256, 8), 256, 0, ctx->stream>>>(
-            a.cmasks, reinterpret_cast<uint8_t*>(a.ctouched), (const uint32_t*)ctx->scratch[SCR_TILE], (uint32_t)t->delta_cap, t->counters, t->delta, a.gx0, a.gy0, a.gz0, a.gdim);
+            a.cmasks, reinterpret_cast<uint8_t*>(a.ctouched), (const uint32_t*)ctx->scratch[SCR_TILE], (uint32_t)t->delta_cap, t->counters, t->delta, a.gx0, a.gy0, a.gz0, a.gdim,
+            t->counters + CNT_ABORT, 0);
         ctx->launches += 2;
         R3D_CUDA_OK(ctx, cudaGetLastError());
         R3D_TRY(tree_sync_counters(t));
@@ -961,6 +973,144 @@ static int scan_delta_dense(r3d_tree* t, const ScanArgs& a0, bool* fallback) {
         R3D_TRY(tree_reserve_delta(t, (uint64_t)t->h_counters[CNT_DELTA] * 2));   // list overflow: masks untouched, list again
     }
     return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the record buffer");
+}
+
+static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1);
+
+// ---- two-deep scan pipeline (dense mode, device-resident scans): scan s+1 is queued -- ray cast, cell list, records,
+// counter read-back -- before the host waits for scan s's counters and queues its apply, so the GPU never idles on the
+// host's turnaround.  Each slot has its own counters, cell list and record buffer; the cell scratch is shared (scan
+// s's emit clears it before scan s+1's ray cast starts, in stream order).  If a scan's records do not fit, its emit
+// sets the sticky abort flag instead of touching anything and every later queued kernel skips; the host then grows the
+// buffers, clears the flag, lists / emits again and re-queues what was skipped.
+static int pipe_reserve(r3d_tree* t, uint64_t cap) {
+    r3d_ctx* ctx = t->ctx;
+    if (!t->pipe_counters) {
+        R3D_CUDA_OK(ctx, cudaMalloc(&t->pipe_counters, 2 * CNT_COUNT * sizeof(uint32_t)));
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->pipe_counters, 0, 2 * CNT_COUNT * sizeof(uint32_t), ctx->stream));
+        for (int i = 0; i < 2; ++i) R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_done[i], cudaEventDisableTiming));
+    }
+    if (t->delta_cap < cap) R3D_TRY(tree_reserve_delta(t, cap));
+    if (t->delta_b_cap < t->delta_cap) {
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(t->delta_b);
+        t->delta_b = nullptr; t->delta_b_cap = 0;
+        R3D_CUDA_OK(ctx, cudaMalloc(&t->delta_b, t->delta_cap * sizeof(DeltaRecord)));
+        t->delta_b_cap = t->delta_cap;
+    }
+    if (t->pipe_list_cap < t->delta_cap) {
+        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(t->pipe_list);
+        t->pipe_list = nullptr; t->pipe_list_cap = 0;
+        R3D_CUDA_OK(ctx, cudaMalloc(&t->pipe_list, 2 * t->delta_cap * sizeof(uint32_t)));
+        t->pipe_list_cap = t->delta_cap;
+    }
+    return R3D_OK;
+}
+
+struct PipeScan {
+    ScanArgs a;
+    bool timed;
+};
+
+static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
+    r3d_ctx* ctx = t->ctx;
+    uint32_t* cnt = t->pipe_counters + slot * CNT_COUNT;
+    ScanArgs a = ps.a;
+    a.counters = cnt;
+    uint32_t* abort_flag = t->counters + CNT_ABORT;
+    if (cast) {
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, CNT_COUNT * sizeof(uint32_t), ctx->stream));
+        if (a.n) {
+            raycast_blocks(t, a.n);
+            unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
+            const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
+            if (blocks > need) blocks = need;
+            if (ps.timed) cudaEventRecord(ctx->ev_a, ctx->stream);
+            k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, reinterpret_cast<unsigned long long*>(cnt + CNT_RAY_LO), abort_flag);
+            if (ps.timed) cudaEventRecord(ctx->ev_b, ctx->stream);
+            ctx->launches++;
+        }
+    } else {
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt + CNT_DELTA, 0, sizeof(uint32_t), ctx->stream));
+    }
+    const uint32_t n_words = a.gcells / 4 + 1;
+    uint32_t* list = t->pipe_list + (size_t)slot * t->pipe_list_cap;
+    DeltaRecord* out = slot ? t->delta_b : t->delta;
+    k_cells_list<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(a.ctouched, n_words, list, (uint32_t)t->delta_cap, cnt, abort_flag);
+    k_cells_emit<<<grid_for(ctx, (uint64_t)t->delta_cap * 32, 256, 8), 256, 0, ctx->stream>>>(
+        a.cmasks, reinterpret_cast<uint8_t*>(a.ctouched), list, (uint32_t)t->delta_cap, cnt, out, a.gx0, a.gy0, a.gz0, a.gdim, abort_flag, 1);
+    ctx->launches += 2;
+    R3D_CUDA_OK(ctx, cudaGetLastError());
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)ctx->pinned + 1024 + 256 * slot, cnt, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_done[slot], ctx->stream));
+    return R3D_OK;
+}
+
+// Returns the number of scans fully inserted; fewer than n_scans means "continue with the serial path from there".
+static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans,
+                                  double maxrange, uint32_t* done_out, uint64_t* rays_out, uint64_t* steps_out) {
+    r3d_ctx* ctx = t->ctx;
+    *done_out = 0;
+    std::vector<PipeScan> scans(n_scans);
+    uint64_t off = 0;
+    uint32_t gcells_max = 0;
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        ScanArgs& a = scans[s].a;
+        memset(&a, 0, sizeof a);
+        int gx0, gy0, gz0;
+        uint32_t gdim;
+        if (n_points[s] > 0xfffffff0ull || dense_grid_geometry(t, origins + 3 * (size_t)s, maxrange, &gx0, &gy0, &gz0, &gdim) != 0) return R3D_OK;   // serial path decides
+        a.xyz = d_xyz + off * 3; a.n = n_points[s];
+        a.ox = origins[3 * s]; a.oy = origins[3 * s + 1]; a.oz = origins[3 * s + 2];
+        a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
+        a.gx0 = gx0; a.gy0 = gy0; a.gz0 = gz0; a.gdim = gdim; a.gcells = gdim * gdim * gdim;
+        if (a.gcells > gcells_max) gcells_max = a.gcells;
+        scans[s].timed = s + 1 == n_scans;
+        off += n_points[s];
+    }
+    R3D_TRY(ctx_reserve_cells(ctx, gcells_max));
+    R3D_TRY(pipe_reserve(t, t->delta_cap < (1u << 16) ? (1u << 16) : t->delta_cap));
+    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
+    for (uint32_t s = 0; s < n_scans; ++s) { scans[s].a.cmasks = ctx->cell_masks; scans[s].a.ctouched = ctx->cell_touched; }
+    ctx->cells_dirty = true;
+    R3D_TRY(pipe_enqueue(t, scans[0], 0, true));
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        const int slot = (int)(s & 1u);
+        if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
+        uint32_t hc[CNT_COUNT];
+        for (int attempt = 0;; ++attempt) {
+            R3D_CUDA_OK(ctx, cudaEventSynchronize(t->pipe_done[slot]));
+            memcpy(hc, (char*)ctx->pinned + 1024 + 256 * slot, sizeof hc);
+            if (hc[CNT_DELTA] <= t->delta_cap) break;
+            if (attempt >= 8) return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the record buffer");
+            // records of scan s did not fit: nothing after its list kernel has run (abort flag).  Grow, clear, list again,
+            // and queue scan s+1 again.
+            R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            R3D_TRY(pipe_reserve(t, (uint64_t)hc[CNT_DELTA] * 2));   // the other slot's records were applied already
+            R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
+            R3D_TRY(pipe_enqueue(t, scans[s], slot, false));
+            if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
+        }
+        if (hc[CNT_GRID_MISS]) {
+            // cannot happen by construction; hand the rest (from this scan on) to the serial path, which falls back to the hash table
+            R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->cells_dirty = false;   // both queued scans have been emitted: the scratch is clean
+            return R3D_OK;
+        }
+        R3D_TRY(apply_delta_impl(t, slot ? t->delta_b : t->delta, hc[CNT_DELTA]));
+        *rays_out += scans[s].a.n;
+        *steps_out += (uint64_t)hc[CNT_STEPS_LO] | ((uint64_t)hc[CNT_STEPS_HI] << 32);
+        t->delta_n = hc[CNT_DELTA];
+        *done_out = s + 1;
+        if (scans[s].timed && scans[s].a.n) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
+    }
+    if ((n_scans & 1u) == 0u) {   // the last scan used slot 1: keep t->delta = "records of the last scan"
+        DeltaRecord* tmp = t->delta; t->delta = t->delta_b; t->delta_b = tmp;
+        const uint64_t c = t->delta_cap; t->delta_cap = t->delta_b_cap; t->delta_b_cap = c;
+    }
+    ctx->cells_dirty = false;
+    return R3D_OK;
 }
 
 // ray-cast one scan into the scratch table and compact it into t->delta (t->delta_n records)
@@ -1040,7 +1190,7 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
     return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the scratch table");
 }
 
-static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1) {
+static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part, uint32_t nparts) {
     r3d_ctx* ctx = t->ctx;
     if (n == 0) return R3D_OK;
     // sized from the host-side upper bound of the pool cursor: no read-back between a scan's apply and the next scan.
@@ -1093,6 +1243,8 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
+    cudaFree(t->delta_b); cudaFree(t->pipe_counters); cudaFree(t->pipe_list);
+    for (int i = 0; i < 2; ++i) if (t->pipe_done[i]) cudaEventDestroy(t->pipe_done[i]);
     delete t;
 }
 
@@ -1257,7 +1409,12 @@ extern "C" int r3d_tree_insert_scans(r3d_tree* t, const float* xyz, const uint64
     if (is_device_ptr(n_points) || is_device_ptr(origins)) return set_error(ctx, R3D_ERR_ARG, "n_points / origins must be host arrays");
     DeviceSetter ds(ctx->device);
     uint64_t off = 0, rays = 0, steps = 0;
-    for (uint32_t s = 0; s < n_scans; ++s) {
+    uint32_t first = 0;
+    if (n_scans > 1 && !discretize && maxrange >= 0.0 && xyz && is_device_ptr(xyz)) {
+        R3D_TRY(insert_scans_pipelined(t, xyz, n_points, origins, n_scans, maxrange, &first, &rays, &steps));
+        for (uint32_t s = 0; s < first; ++s) off += n_points[s];
+    }
+    for (uint32_t s = first; s < n_scans; ++s) {
         R3D_TRY(scan_delta_impl(t, xyz ? xyz + off * 3 : nullptr, n_points[s], origins + 3 * (size_t)s, maxrange, discretize));
         R3D_TRY(apply_delta_impl(t, t->delta, t->delta_n));
         off += n_points[s];

@@ -25,7 +25,8 @@ static_assert(sizeof(BrickRecord) == R3D_BRICK_RECORD_BYTES, "record layout is p
 
 // device counters of a tree
 enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_STEPS_LO, CNT_STEPS_HI, CNT_RAY_LO, CNT_RAY_HI, CNT_GRID_MISS,
-       CNT_APPLY_OVERFLOW = 15 /* sticky, outside the per-scan reset range */, CNT_COUNT = 16 };
+       CNT_ABORT = 14 /* sticky: a pipelined scan could not be read back; every queued scan kernel skips until the host clears it */,
+       CNT_APPLY_OVERFLOW = 15 /* sticky */, CNT_COUNT = 16 };
 
 }  // namespace r3d
 
@@ -52,6 +53,13 @@ struct r3d_tree {
     uint64_t scap = 0;
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
+    // second slot of the two-deep scan pipeline (r3d_tree_insert_scans): record buffer, per-slot counters, cell lists, events
+    r3d::DeltaRecord* delta_b = nullptr;
+    uint64_t delta_b_cap = 0;
+    uint32_t* pipe_counters = nullptr;   // [2][CNT_COUNT]
+    uint32_t* pipe_list = nullptr;       // [2][pipe_list_cap]
+    uint64_t pipe_list_cap = 0;
+    cudaEvent_t pipe_done[2] = {nullptr, nullptr};
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};

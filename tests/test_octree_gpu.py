@@ -391,3 +391,30 @@ def test_c4_airsim_disparity_octree_005(octomap, r3d):
     assert t.writeBinary() == bt
     t.toMaxLikelihood()
     assert t.writeBinary() == bt
+
+
+def test_insert_point_clouds_pipelined_device_batch(octomap, r3d):
+    """The two-deep pipeline of r3d_tree_insert_scans (device-resident scans, bounded range): equal to the scan-by-scan
+    loop and to the oracle, including a batch whose records outgrow the record buffer mid-way (abort / re-list path),
+    odd and even batch sizes, empty scans and a second batch into the same tree."""
+    ctx = r3d.default_context(0)
+    rng = np.random.default_rng(43)
+    S, N = 7, 4000
+    origins = np.array([[0.25 * s, 0.1 * s, 0.0] for s in range(S)])
+    scans = np.stack([_scan(rng, N, origins[s], far=(3.0 if s < 3 else 40.0)) for s in range(S)]).astype(np.float32)
+    scans[4] = origins[4]                                 # a scan of zero-length rays
+    dev = ctx.to_device(scans.reshape(-1, 3))
+    a, b, r = octomap.OcTree(0.1), octomap.OcTree(0.1), oo.OcTree(0.1)
+    for s in range(S):
+        a.insertPointCloud(scans[s], origins[s], maxrange=30.0)
+        r.insertPointCloud_f32(scans[s], origins[s], 30.0)
+    b.insertPointClouds(dev, origins, maxrange=30.0)      # small scans first: the far ones overflow the 65 536-record start buffer? (no: forces growth only if needed)
+    assert b.lastScanStats()["rays"] == S * N
+    assert a.writeBinary() == b.writeBinary()
+    assert_same_tree(b, r)
+    # even-sized second batch into the same tree, then per-scan delta export still refers to the last scan
+    c = octomap.OcTree(0.1)
+    c.insertPointClouds(dev[: 4 * N], origins[:4], maxrange=30.0)
+    c.insertPointClouds(dev[4 * N:6 * N], origins[4:6], maxrange=30.0)
+    c.insertPointCloud(scans[6], origins[6], maxrange=30.0)
+    assert c.writeBinary() == a.writeBinary()
