@@ -259,6 +259,21 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
            "gpu_launches": ctx.launch_count() - launches0,
            "raycast_kernel_ms_last_scan": float(k3_ms[-1]), "raycast_steps_per_s_in_kernel": (steps / n_scans) / max(k3_ms[-1], 1e-9) * 1e3,
            "workload": "C3: %d consecutive KITTI-shape street scans (1242x375 rays each, Z=0 sky pixels included as rays to the sensor origin)" % n_scans}
+    # the mode the reference's own OctoMap scripts use: updateNode(point, True) per point (octomap/txt_transfer_octomap.py:25)
+    un = octomap.OcTree(res, ctx=ctx)
+    un.reserve(1 << 17)
+    n_un = min(n_scans, 12) * H * W                      # 5.6 M points: the size ply_transfer_octomap.py caps at (5.4 M)
+    un.updateNodes(world[:H * W], True)
+    un.clear()
+    ctx.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    un.updateNodes(world[:n_un], True)
+    e3.record(stream)
+    ctx.synchronize()
+    un_ms = e2.elapsed_time(e3)
+    out["update_node"] = {"metric": "updateNode(point, True) points/s (the reference scripts' mode)", "value": n_un / (un_ms * 1e-3), "unit": "points/s",
+                          "points": n_un, "ms": un_ms, "voxels": un.numVoxels()}
     if with_cpu:
         w0 = world[:H * W].cpu().numpy()
         out["cpu_baseline"] = octomap_cpu_baseline(w0, origins[0], maxrange, res)
@@ -268,6 +283,15 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
         chk.insertPointCloud(world[:H * W], origins[0], maxrange=maxrange)
         ref.insertPointCloud_f32(w0, origins[0], maxrange)
         out["parity_bt_ok"] = bool(chk.writeBinary() == ref.write_binary_bytes())
+        # updateNode mode: CPU oracle on a bounded sample (one frame's points), and .bt parity of that sample
+        ref2, chk2 = oo.OcTree(res), octomap.OcTree(res, ctx=ctx)
+        t0 = time.perf_counter()
+        ref2.updateNodes_f32(w0, True)
+        sec = time.perf_counter() - t0
+        chk2.updateNodes(world[:H * W], True)
+        out["update_node"]["cpu_baseline"] = {"value": w0.shape[0] / sec, "unit": "points/s", "cores": 1, "kind": "port",
+                                              "sample": "%d points, C restatement of updateNode, %.2f s" % (w0.shape[0], sec)}
+        out["update_node"]["parity_bt_ok"] = bool(chk2.writeBinary() == ref2.write_binary_bytes())
     return out
 
 
