@@ -39,6 +39,7 @@ SIGNATURES = {
     "r3d_memcpy": (_i32, [_vp, _vp, _vp, _sz]),
     "r3d_png_info": (_i32, [C.c_char_p, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "r3d_png_decode_batch": (_i32, [_vp, _i32, _i32, _i32, _vp, _sz, _i32, _i32, _i32, _i32, _vp]),
+    "r3d_read_xyz_text": (_i32, [C.c_char_p, _i32, _i32, _u64, _vp, _u64, _u64p, _i32]),
     "r3d_pose_to_rt": (_i32, [_vp, _i32, _dbl, _vp]),
     "r3d_backproject_rt": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _i32, _vp, _vp]),
     "r3d_backproject": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _vp, _vp]),

@@ -1,0 +1,143 @@
+// r3d_textin.cu -- a8: the point-cloud text readers of the OctoMap scripts on a host thread pool (host code only).
+//
+// txt_read of octomap/txt_transfer_octomap.py:16-28 parses every `x,y,z` line with float() in a Python loop, the PLY
+// twin (octomap/ply_transfer_octomap.py:16-40) skips 8 lines, splits on whitespace and stops after point 5 400 000.
+// Here the file is split at line boundaries into one piece per worker; every piece is parsed with strtod (correctly
+// rounded, like Python's float()) in two passes -- count the rows, then write them at their final offsets -- so the
+// points come out in file order.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "r3d_common.cuh"
+
+namespace {
+
+using r3d::set_error;
+
+// parses up to three numbers from [p, e) (one line, no newline); comma_mode: fields separated by ',' (surrounding blanks
+// allowed, like float(" 1.5 ")), else by runs of blanks.  Returns the number of leading numeric fields (0..3).
+inline int parse_row(const char* p, const char* e, bool comma_mode, double v[3]) {
+    int got = 0;
+    char buf[64];
+    while (got < 3 && p < e) {
+        while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+        const char* q = p;
+        if (comma_mode) { while (q < e && *q != ',') ++q; }
+        else { while (q < e && *q != ' ' && *q != '\t' && *q != '\r') ++q; }
+        const char* te = q;
+        while (te > p && (te[-1] == ' ' || te[-1] == '\t' || te[-1] == '\r')) --te;
+        const size_t len = (size_t)(te - p);
+        if (len == 0 || len >= sizeof buf) break;
+        memcpy(buf, p, len);
+        buf[len] = 0;
+        char* end = nullptr;
+        const double d = strtod(buf, &end);
+        if (end != buf + len) break;     // not a number (float() would raise)
+        v[got++] = d;
+        p = (comma_mode && q < e) ? q + 1 : q;
+    }
+    return got;
+}
+
+struct Piece {
+    size_t begin = 0, end = 0;   // byte range, whole lines
+    uint64_t rows = 0, first = 0;
+};
+
+}  // namespace
+
+// Points of an `x,y,z` text (comma_mode != 0) or of an ASCII PLY body (comma_mode == 0, whitespace separated, only the
+// first three columns used) after skipping skip_lines lines; rows with fewer than three numeric fields (blank lines, the
+// reference writer's trailing indentation) are skipped; at most max_points points (0 = no limit).
+// out == NULL or capacity too small: only *n_points is set (size query).  Needs no GPU.
+extern "C" int r3d_read_xyz_text(const char* path, int skip_lines, int comma_mode, uint64_t max_points, double* out, uint64_t capacity,
+                                 uint64_t* n_points, int n_threads) {
+    if (!path || !n_points) return set_error(nullptr, R3D_ERR_ARG, "r3d_read_xyz_text: null argument");
+    *n_points = 0;
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(nullptr, R3D_ERR_IO, "cannot open %s", path);
+    std::vector<char> data;
+    {
+        fseek(f, 0, SEEK_END);
+        const long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (n < 0) { fclose(f); return set_error(nullptr, R3D_ERR_IO, "cannot size %s", path); }
+        data.resize((size_t)n);
+        const size_t got = n ? fread(data.data(), 1, (size_t)n, f) : 0;
+        fclose(f);
+        if (got != (size_t)n) return set_error(nullptr, R3D_ERR_IO, "short read on %s", path);
+    }
+    const char* base = data.data();
+    const size_t size = data.size();
+    size_t pos = 0;
+    for (int i = 0; i < skip_lines && pos < size; ++i) {
+        const void* nl = memchr(base + pos, '\n', size - pos);
+        pos = nl ? (size_t)((const char*)nl - base) + 1 : size;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    int nt = n_threads > 0 ? n_threads : (int)hw;
+    const size_t body = size - pos;
+    if ((size_t)nt > body / 65536 + 1) nt = (int)(body / 65536 + 1);
+    std::vector<Piece> pieces((size_t)nt);
+    size_t b = pos;
+    for (int t = 0; t < nt; ++t) {
+        size_t e = t + 1 == nt ? size : pos + body * (size_t)(t + 1) / (size_t)nt;
+        if (e < b) e = b;
+        if (e < size) {
+            const void* nl = memchr(base + e, '\n', size - e);
+            e = nl ? (size_t)((const char*)nl - base) + 1 : size;
+        }
+        pieces[(size_t)t].begin = b;
+        pieces[(size_t)t].end = e;
+        b = e;
+    }
+    const bool comma = comma_mode != 0;
+    auto scan = [&](Piece& pc, double* dst, uint64_t limit) {
+        uint64_t rows = 0;
+        size_t p = pc.begin;
+        while (p < pc.end && rows < limit) {
+            const void* nl = memchr(base + p, '\n', pc.end - p);
+            const size_t le = nl ? (size_t)((const char*)nl - base) : pc.end;
+            double v[3];
+            if (parse_row(base + p, base + le, comma, v) == 3) {
+                if (dst) { dst[3 * rows] = v[0]; dst[3 * rows + 1] = v[1]; dst[3 * rows + 2] = v[2]; }
+                ++rows;
+            }
+            p = le + 1;
+        }
+        return rows;
+    };
+    // pass 1: rows per piece
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back([&, t] { pieces[(size_t)t].rows = scan(pieces[(size_t)t], nullptr, ~0ull); });
+        pieces[0].rows = scan(pieces[0], nullptr, ~0ull);
+        for (auto& th : pool) th.join();
+    }
+    uint64_t total = 0;
+    for (auto& pc : pieces) { pc.first = total; total += pc.rows; }
+    if (max_points && total > max_points) total = max_points;
+    *n_points = total;
+    if (!out || capacity < total) return R3D_OK;
+    // pass 2: parse into place (pieces beyond the cap write nothing)
+    {
+        std::vector<std::thread> pool;
+        auto fill = [&](int t) {
+            Piece& pc = pieces[(size_t)t];
+            if (pc.first >= total) return;
+            scan(pc, out + 3 * pc.first, total - pc.first);
+        };
+        for (int t = 1; t < nt; ++t) pool.emplace_back(fill, t);
+        fill(0);
+        for (auto& th : pool) th.join();
+    }
+    return R3D_OK;
+}

@@ -196,14 +196,28 @@ def write_xyz_txt(path, x, y, z, z_raw=None, mode="w"):
         f.write("".join([a + "," + b + "," + c + "\n" for a, b, c in zip(xs, ys, zs)]))
 
 
+def _read_text_points(path, skip_lines, comma, max_points, n_threads=0):
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    n = C.c_uint64(0)
+    bp = os.fsencode(path)
+    rc = lib.r3d_read_xyz_text(bp, int(skip_lines), 1 if comma else 0, int(max_points), None, 0, C.byref(n), int(n_threads))
+    if rc != 0:
+        msg = lib.r3d_last_error(None).decode("utf-8", "replace")
+        raise FileNotFoundError(msg) if "cannot open" in msg else ValueError(msg)
+    out = np.empty((n.value, 3), dtype=np.float64)
+    if n.value:
+        rc = lib.r3d_read_xyz_text(bp, int(skip_lines), 1 if comma else 0, int(max_points), out.ctypes.data, n.value, C.byref(n), int(n_threads))
+        if rc != 0:
+            raise ValueError(lib.r3d_last_error(None).decode("utf-8", "replace"))
+    return out
+
+
 def read_xyz_txt(path):
-    """x,y,z per line, comma separated (octomap/txt_transfer_octomap.py:16-25; camera_to_world.py:92-98)."""
-    import pandas as pd
-    try:
-        df = pd.read_csv(path, header=None, usecols=[0, 1, 2], dtype=np.float64, float_precision="round_trip")
-    except pd.errors.EmptyDataError:
-        return np.zeros((0, 3), dtype=np.float64)
-    return np.ascontiguousarray(df.to_numpy(dtype=np.float64))
+    """x,y,z per line, comma separated (octomap/txt_transfer_octomap.py:16-25; camera_to_world.py:92-98), parsed by the
+    native thread pool (r3d_read_xyz_text)."""
+    return _read_text_points(path, 0, True, 0)
 
 
 # ------------------------------------------------------------------------------------------------ PLY
@@ -260,18 +274,7 @@ def read_ply_points(path, skip_lines=8, max_points=5400001):
     """txt_read of octomap/ply_transfer_octomap.py:16-40: skip exactly `skip_lines` lines, then whitespace-split rows
     (first three tokens used), stop after `max_points` points (the reference breaks at generation >= 5 400 000 after
     inserting that point).  Blank / indentation-only lines are skipped instead of raising (documented deviation)."""
-    pts = []
-    with open(path, "r") as f:
-        for _ in range(skip_lines):
-            f.readline()
-        for line in f:
-            tok = line.split()
-            if len(tok) < 3:
-                continue
-            pts.append((float(tok[0]), float(tok[1]), float(tok[2])))
-            if len(pts) >= max_points:
-                break
-    return np.array(pts, dtype=np.float64).reshape(-1, 3)
+    return _read_text_points(path, skip_lines, False, max_points)
 
 
 def ensure_dir(path):
