@@ -418,19 +418,6 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # one rank per GPU: keep the rank (and the pinned host buffers it first-touches) on the CPUs / NUMA node next to its GPU
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            uuid = str(torch.cuda.get_device_properties(dev).uuid)
-            try:
-                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
-            except Exception:
-                h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
-            pynvml.nvmlDeviceSetCpuAffinity(h)
-        except Exception:
-            pass
     dist = None
     if world > 1:
         import torch.distributed as dist
