@@ -34,6 +34,7 @@ struct K1Args {
     const unsigned long long* tile_offsets;  // exclusive scan of valid counts per tile
     unsigned long long* tile_counts;
     unsigned long long* frame_counts;
+    unsigned long long* frame_ends;          // fast compaction: records written up to and including each frame's last pixel
 };
 
 // ------------------------------------------------------------------ PTX helpers (mbarrier + bulk async copy)
@@ -302,6 +303,36 @@ __global__ void __launch_bounds__(K1_THREADS) k1_count(const K1Args a) {
     }
 }
 
+// fast path, pass 1 for the partial last tile: same count, no per-frame atomics (frame counts come from frame_ends)
+template <typename DepthT>
+__global__ void __launch_bounds__(K1_THREADS) k1_count_tail(const K1Args a) {
+    __shared__ unsigned warp_cnt[K1_THREADS / 32];
+    const unsigned long long n_tiles = (a.px_count + K1_TILE - 1) / K1_TILE;
+    for (unsigned long long t = a.n_tiles; t < n_tiles; ++t) {
+        unsigned mine = 0;
+        for (int j = 0; j < K1_PPT; ++j) {
+            const unsigned long long p = t * K1_TILE + threadIdx.x + j * K1_THREADS;
+            bool valid = false;
+            if (p < a.px_count) {
+                const unsigned f = (unsigned)(p / a.WH);
+                const unsigned r = (unsigned)(p - (unsigned long long)f * a.WH);
+                const unsigned v = r / a.W, u = r - v * a.W;
+                decode_z(load_raw<DepthT>(a, f, v, u), a.mode, a.depth_scale, a.fB, valid);
+            }
+            mine += valid ? 1u : 0u;
+        }
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31u) == 0) warp_cnt[threadIdx.x >> 5] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned sum = 0;
+            for (int w = 0; w < K1_THREADS / 32; ++w) sum += warp_cnt[w];
+            a.tile_counts[t] = sum;
+        }
+        __syncthreads();
+    }
+}
+
 // compaction pass 2: ordered write of the valid records
 template <typename DepthT, typename OutT, bool kWorld>
 __global__ void __launch_bounds__(K1_THREADS) k1_compact(const K1Args a) {
@@ -316,7 +347,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_compact(const K1Args a) {
     Pose pose;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned long long n_tiles = (a.px_count + K1_TILE - 1) / K1_TILE;
-    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    // (fast path: a.n_tiles full tiles were written by k1_bulk_compact; this kernel then only handles the partial last tile)
+    for (unsigned long long t = (a.frame_ends ? a.n_tiles : 0ull) + blockIdx.x; t < n_tiles; t += gridDim.x) {
         OutT x[K1_PPT], y[K1_PPT], z[K1_PPT];
         unsigned rank[K1_PPT];
         bool ok[K1_PPT];
@@ -347,9 +379,187 @@ __global__ void __launch_bounds__(K1_THREADS) k1_compact(const K1Args a) {
                 const unsigned long long q = base + before + rank[j];
                 gout[q * 3 + 0] = x[j]; gout[q * 3 + 1] = y[j]; gout[q * 3 + 2] = z[j];
             }
+            if (a.frame_ends) {
+                const unsigned long long p = t * K1_TILE + threadIdx.x + j * K1_THREADS;
+                if (p < a.px_count && (p + 1) % a.WH == 0) a.frame_ends[p / a.WH] = base + before + rank[j] + (ok[j] ? 1u : 0u);
+            }
         }
         __syncthreads();
     }
+}
+
+// ------------------------------------------------------------------ fast compaction (bulk-eligible input)
+// pass 1: valid pixels per full 1024-pixel tile; one 8-byte (u16) / 4-byte (u8) / 16-byte (f32) load per thread
+template <typename DepthT>
+__global__ void __launch_bounds__(K1_THREADS) k1_count_tiles(const K1Args a) {
+    __shared__ unsigned warp_cnt[K1_THREADS / 32];
+    const DepthT* gin = reinterpret_cast<const DepthT*>(a.depth);
+    for (unsigned long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+        const DepthT* p = gin + t * K1_TILE + threadIdx.x * K1_PPT;
+        DepthT v[K1_PPT];
+        if (sizeof(DepthT) == 2) *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(p);
+        else if (sizeof(DepthT) == 1) *reinterpret_cast<unsigned*>(v) = *reinterpret_cast<const unsigned*>(p);
+        else *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(p);
+        unsigned mine = 0;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            bool valid;
+            decode_z(raw_to_double(v[j]), a.mode, a.depth_scale, a.fB, valid);
+            mine += valid ? 1u : 0u;
+        }
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31u) == 0) warp_cnt[threadIdx.x >> 5] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned sum = 0;
+            for (int w = 0; w < K1_THREADS / 32; ++w) sum += warp_cnt[w];
+            a.tile_counts[t] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2: k1_bulk with in-tile compaction.  The tile's records are packed in shared memory in pixel order (warp
+// ballots + a 32-entry scan over the (row-of-256, warp) counts) at the same 16-byte phase as their destination, the
+// 16-byte aligned middle leaves through one cp.async.bulk store, the (<= 3 float) head and tail through scalar stores.
+template <typename DepthT, typename OutT, bool kWorld, int kMode>
+__global__ void __launch_bounds__(K1_THREADS, 3) k1_bulk_compact(const K1Args a) {
+    constexpr int kOutBufs = 2;
+    constexpr int kPerWord = 16 / (int)sizeof(OutT);                    // output elements per 16 bytes
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    unsigned* part = reinterpret_cast<unsigned*>(smem + 64);             // [K1_PPT][8] warp counts
+    double* col = reinterpret_cast<double*>(smem + 256);
+    double* row = col + a.W;
+    size_t off = 256 + ((size_t)(a.W + a.H) * 8 + 127) / 128 * 128;
+    DepthT* in_s = reinterpret_cast<DepthT*>(smem + off);
+    off += (size_t)K1_STAGES * K1_TILE * sizeof(DepthT);
+    OutT* out_s = reinterpret_cast<OutT*>(smem + off);                   // kOutBufs x (K1_TILE * 3 + kPerWord)
+    constexpr size_t kOutStride = (size_t)K1_TILE * 3 + kPerWord;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    constexpr uint32_t kInBytes = K1_TILE * sizeof(DepthT);
+    const unsigned long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
+    unsigned long long t1 = t0 + per;
+    if (t1 > a.n_tiles) t1 = a.n_tiles;
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) mbar_init(&full[s], 1);
+        fence_mbar_init();
+    }
+    k1_tables(a, col, row);
+    __syncthreads();
+    if (t0 >= t1) return;
+    const DepthT* gin = reinterpret_cast<const DepthT*>(a.depth);
+    OutT* gout = reinterpret_cast<OutT*>(a.out);
+    if (tid == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) {
+            if (t0 + s < t1) {
+                mbar_arrive_expect_tx(&full[s], kInBytes);
+                bulk_load(in_s + (size_t)s * K1_TILE, gin + (t0 + s) * K1_TILE, kInBytes, &full[s]);
+            }
+        }
+    }
+    const unsigned long long px0 = t0 * K1_TILE + tid;
+    unsigned f0 = (unsigned)(px0 / a.WH);
+    const unsigned r0 = (unsigned)(px0 - (unsigned long long)f0 * a.WH);
+    unsigned v0 = r0 / a.W, u0 = r0 - v0 * a.W;
+    const unsigned W = a.W, H = a.H;
+    const unsigned q_tile = K1_TILE / W, r_tile = K1_TILE - q_tile * W;
+    unsigned pose_frame = 0xffffffffu;
+    Pose pose;
+    unsigned stage = 0, parity = 0, ob = 0;
+    for (unsigned long long t = t0; t < t1; ++t) {
+        mbar_wait(&full[stage], parity);
+        const DepthT* tin = in_s + (size_t)stage * K1_TILE + tid;
+        unsigned u = u0, v = v0, f = f0;
+        if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
+        OutT rx[K1_PPT], ry[K1_PPT], rz[K1_PPT];
+        unsigned rank[K1_PPT];
+        bool ok[K1_PPT], last_of_frame[K1_PPT];
+        unsigned fr[K1_PPT];
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            bool valid;
+            const double raw = raw_to_double(tin[j * K1_THREADS]);
+            const double Z = decode_z(raw, kMode, a.depth_scale, a.fB, valid);
+            const double X = dmul(col[u], Z), Y = dmul(row[v], Z);
+            if (kWorld) {
+                double wx, wy, wz;
+                pose_apply(pose, X, Y, Z, wx, wy, wz);
+                rx[j] = out_cast<OutT>(wx); ry[j] = out_cast<OutT>(wy); rz[j] = out_cast<OutT>(wz);
+            } else {
+                rx[j] = out_cast<OutT>(X); ry[j] = out_cast<OutT>(Y); rz[j] = out_cast<OutT>(Z);
+            }
+            ok[j] = valid;
+            fr[j] = f;
+            last_of_frame[j] = (u == W - 1) & (v == H - 1);
+            const unsigned b = __ballot_sync(0xffffffffu, valid);
+            rank[j] = __popc(b & ((1u << lane) - 1u));
+            if (lane == 0) part[j * 8 + warp] = __popc(b);
+            u += K1_THREADS;
+            if (u >= W) {
+                u -= W;
+                if (++v == H) {
+                    v = 0;
+                    ++f;
+                    if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
+                }
+            }
+        }
+        // the bulk store issued from the buffer we are about to fill must have finished reading it
+        if (tid == 0) bulk_wait_read<kOutBufs - 2>();
+        __syncthreads();                                                // part[] complete, buffer free
+        // exclusive scan of the 32 (j, warp) counts, redundantly in every warp
+        unsigned c = part[lane], incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
+        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned excl = incl - c;
+        const unsigned long long base = a.tile_offsets[t];              // records before this tile
+        const unsigned skew = (unsigned)((base * 3ull) % (unsigned)kPerWord);
+        OutT* buf = out_s + (size_t)ob * kOutStride;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; ++j) {
+            const unsigned before = __shfl_sync(0xffffffffu, excl, j * 8 + (int)warp);
+            const unsigned pos = before + rank[j];
+            if (ok[j]) { OutT* o = buf + skew + pos * 3u; o[0] = rx[j]; o[1] = ry[j]; o[2] = rz[j]; }
+            if (last_of_frame[j]) a.frame_ends[fr[j]] = base + pos + (ok[j] ? 1u : 0u);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();                                                // records packed
+        // split [skew, skew + 3 total) into head | 16-byte aligned middle | tail (element indices in the staging buffer)
+        const unsigned first = skew, end = skew + total * 3u;
+        unsigned mid0 = (first + kPerWord - 1) / kPerWord * kPerWord, mid1 = end / kPerWord * kPerWord;
+        if (mid1 < mid0) { mid0 = end; mid1 = end; }
+        OutT* gdst = gout + base * 3ull - skew;                         // 16-byte aligned
+        if (tid == 0) {
+            if (mid1 > mid0) bulk_store(gdst + mid0, buf + mid0, (mid1 - mid0) * (unsigned)sizeof(OutT));
+            bulk_commit();
+            const unsigned long long tn = t + K1_STAGES;
+            if (tn < t1) {
+                mbar_arrive_expect_tx(&full[stage], kInBytes);
+                bulk_load(in_s + (size_t)stage * K1_TILE, gin + tn * K1_TILE, kInBytes, &full[stage]);
+            }
+        }
+        if (tid >= 32 && tid < 32 + (unsigned)kPerWord) {               // head and tail: a few scalar stores by warp 1
+            const unsigned k = tid - 32;
+            if (first + k < mid0 && first + k < end) gdst[first + k] = buf[first + k];
+            if (mid1 + k < end && mid1 >= mid0 && mid1 + k >= mid0) gdst[mid1 + k] = buf[mid1 + k];
+        }
+        u0 += r_tile; v0 += q_tile;
+        if (u0 >= W) { u0 -= W; ++v0; }
+        if (v0 >= H) { v0 -= H; ++f0; }
+        if (++stage == K1_STAGES) { stage = 0; parity ^= 1u; }
+        if (++ob == kOutBufs) ob = 0;
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+// frame_ends (records written up to each frame's end) -> per-frame counts
+__global__ void k1_frame_counts(const unsigned long long* __restrict__ ends, unsigned n, unsigned long long* counts) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) counts[i] = ends[i] - (i ? ends[i - 1] : 0ull);
 }
 
 // T . [x y z 1]^T (other_tools/transfer_T_icp.py:10-12), rows left to right
@@ -385,7 +595,7 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
     const size_t table_bytes = ((size_t)(a.W + a.H) * 8 + 127) / 128 * 128;
     if (compact) {
         const unsigned long long n_tiles = (total + K1_TILE - 1) / K1_TILE;
-        R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)n_tiles * 16 + 256));
+        R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)n_tiles * 16 + (size_t)a.n_frames * 8 + 512));
         unsigned long long* counts = (unsigned long long*)ctx->scratch[SCR_TILE];
         unsigned long long* offsets = counts + n_tiles;
         a.tile_counts = counts;
@@ -393,13 +603,50 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
         a.px_begin = 0;
         a.px_count = total;
         const int grid = (int)((n_tiles < (unsigned long long)ctx->sm_count * 8) ? n_tiles : (unsigned long long)ctx->sm_count * 8);
-        k1_count<DepthT><<<grid, K1_THREADS, 0, st>>>(a);
-        ctx->launches++;
+        const bool fast = bulk_ok && total >= K1_TILE && a.frame_counts != nullptr;
+        if (fast) {
+            // pass 1: full tiles with vector loads, the partial last tile (if any) with the generic counter
+            a.n_tiles = total / K1_TILE;
+            a.frame_ends = offsets + n_tiles;
+            k1_count_tiles<DepthT><<<(unsigned)((a.n_tiles < (unsigned long long)ctx->sm_count * 16) ? a.n_tiles : (unsigned long long)ctx->sm_count * 16), K1_THREADS, 0, st>>>(a);
+            ctx->launches++;
+            if (a.n_tiles < n_tiles) {
+                K1Args tail = a;
+                tail.frame_counts = nullptr;
+                tail.n_tiles = a.n_tiles;      // first tile of the tail
+                k1_count_tail<DepthT><<<1, K1_THREADS, 0, st>>>(tail);
+                ctx->launches++;
+            }
+        } else {
+            k1_count<DepthT><<<grid, K1_THREADS, 0, st>>>(a);
+            ctx->launches++;
+        }
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts, offsets, (int)n_tiles, st);
         R3D_TRY(scratch_reserve(ctx, SCR_CUBTMP, tmp_bytes + 256));
         R3D_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->scratch[SCR_CUBTMP], tmp_bytes, counts, offsets, (int)n_tiles, st));
         ctx->launches++;
+        if (fast) {
+            const size_t smem = 256 + table_bytes + (size_t)K1_STAGES * K1_TILE * sizeof(DepthT) + 2 * ((size_t)K1_TILE * 3 + 16 / sizeof(OutT)) * sizeof(OutT);
+            auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk_compact<DepthT, OutT, kWorld, 0> : k1_bulk_compact<DepthT, OutT, kWorld, 1>;
+            R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 0;
+            R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem));
+            if (per_sm < 1) return set_error(ctx, R3D_ERR_UNSUPPORTED, "image %ux%u needs %zu B of shared memory per CTA", a.W, a.H, smem);
+            unsigned long long g2 = (unsigned long long)ctx->sm_count * per_sm;
+            if (g2 > a.n_tiles) g2 = a.n_tiles;
+            kern<<<(unsigned)g2, K1_THREADS, smem, st>>>(a);
+            ctx->launches++;
+            if (a.n_tiles < n_tiles) {
+                R3D_CUDA_OK(ctx, cudaFuncSetAttribute(k1_compact<DepthT, OutT, kWorld>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
+                k1_compact<DepthT, OutT, kWorld><<<1, K1_THREADS, table_bytes, st>>>(a);
+                ctx->launches++;
+            }
+            k1_frame_counts<<<(a.n_frames + 255) / 256, 256, 0, st>>>(a.frame_ends, a.n_frames, a.frame_counts);
+            ctx->launches++;
+            R3D_CUDA_OK(ctx, cudaGetLastError());
+            return R3D_OK;
+        }
         R3D_CUDA_OK(ctx, cudaFuncSetAttribute(k1_compact<DepthT, OutT, kWorld>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
         k1_compact<DepthT, OutT, kWorld><<<grid, K1_THREADS, table_bytes, st>>>(a);
         ctx->launches++;

@@ -295,6 +295,34 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
     return out
 
 
+def compaction_section(torch, ctx, dev, depth, rt, n=1024):
+    """Secondary K1 figure: the same frames with invalid pixels (Z = 0 sky) compacted away, order kept (device resident)."""
+    from oracle import points_oracle as po
+    n = min(n, depth.shape[0])
+    out = torch.empty((n * H * W, 3), dtype=torch.float32, device=dev)
+    cnt = torch.zeros(n, dtype=torch.int64, device=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    def step():
+        ctx.backproject(depth[:n], po.KITTI_INTRINSICS, rt=rt[:n], depth_scale=DEPTH_SCALE, out=out, shape=(n, H, W), counts=cnt, compact=True)
+
+    for _ in range(3):
+        step()
+    ctx.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(5):
+        step()
+    e1.record(stream)
+    ctx.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    valid = int(cnt.sum().item())
+    px = n * H * W
+    return {"frames": n, "ms": ms, "input_pixels_per_s": px / (ms * 1e-3), "valid_fraction": valid / px,
+            "algorithmic_gbs": (px * 2 + valid * 12) / (ms * 1e-3) / 1e9,
+            "kernels": "k1_count_tiles + CUB scan + k1_bulk_compact (warp ballots, in-tile packing in shared memory, bulk stores)"}
+
+
 def png_decode_section(n_frames=64):
     """a1 beside the GPU numbers: the frame decode that feeds the path.  The reference reads one PNG at a time with
     cv.imread on one core (transfer/camera_to_world.py:160); the native decoder inflates a batch on every core."""
@@ -514,6 +542,7 @@ def run_gpu_arm(args):
     lib.r3d_host_free(h_in)
     lib.r3d_host_free(h_out)
 
+    compaction = compaction_section(torch, ctx, dev, depth, rt) if world == 1 else None
     octo = None
     if args.octomap_scans > 0:
         del out
@@ -545,7 +574,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k1_bulk<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
                          "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo, "png_decode": png,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo, "png_decode": png, "compact_mode": compaction,
         }
         print(json.dumps(line))
     if dist is not None:

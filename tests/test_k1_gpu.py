@@ -263,3 +263,36 @@ def test_c2_full_size_properties(ctx):
     assert torch.equal(whole.view(torch.int32), parts.view(torch.int32))
     del whole, parts, depth
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype,scale,out_dtype,world", [(np.uint16, 1.0 / 256.0, np.float32, True), (np.uint8, 1.0, np.float64, True),
+                                                         (np.float32, 1.0, np.float32, False), (np.uint16, 1.0 / 256.0, np.float64, False)])
+def test_fast_compaction_paths(ctx, dtype, scale, out_dtype, world):
+    """The bulk compaction kernel (full 1024-pixel tiles) + generic tail: order, per-frame counts and values for sparse,
+    dense, empty and full frames, every 16-byte phase of the output offset, all sample types."""
+    rng = np.random.default_rng(77)
+    n, H, W = 6, 33, 1025                                  # 202 950 px: 198 full tiles + a 198-px tail, frames end mid-tile
+    if dtype == np.float32:
+        depths = rng.uniform(0.5, 80, size=(n, H, W)).astype(np.float32)
+    else:
+        depths = rng.integers(1, np.iinfo(dtype).max, size=(n, H, W)).astype(dtype)
+    keep = rng.random(size=(n, H, W))
+    depths[0][keep[0] < 0.9] = 0                           # sparse
+    depths[1][keep[1] < 0.01] = 0                          # dense
+    depths[2] = 0                                          # empty
+    depths[4][keep[4] < 0.5] = 0                           # frame 3 stays full
+    depths[5, -1, -1] = 0
+    rt = random_rt(n, rng) if world else None
+    cam_ref, world_ref = oracle_batch(depths, po.REF_INTRINSICS, rt if world else random_rt(n, rng), 0, scale)
+    ref = world_ref if world else cam_ref
+    mask = np.concatenate([po.valid_mask(depths[k], 0, scale).ravel() for k in range(n)])
+    got, counts = ctx.backproject(depths, po.REF_INTRINSICS, rt=rt, depth_scale=scale, compact=True, out_dtype=out_dtype)
+    assert counts.tolist() == [int(po.valid_mask(depths[k], 0, scale).sum()) for k in range(n)]
+    assert got.shape[0] == int(mask.sum())
+    assert np.array_equal(got, ref[mask].astype(out_dtype))
+    # disparity mode through the same kernels
+    if dtype == np.uint16 and world:
+        got, counts = ctx.backproject(depths, po.AIRSIM_INTRINSICS, rt=rt, mode=po.MODE_DISPARITY, depth_scale=scale, fB=67.375, compact=True,
+                                      out_dtype=np.float64)
+        _, wref = oracle_batch(depths, po.AIRSIM_INTRINSICS, rt, po.MODE_DISPARITY, scale, 67.375)
+        assert np.array_equal(got, wref[mask])
