@@ -1043,6 +1043,9 @@ static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
     ctx->launches += 2;
     R3D_CUDA_OK(ctx, cudaGetLastError());
     R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)ctx->pinned + 1024 + 256 * slot, cnt, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // the pool cursor as of this point of the stream (= after every apply queued before this scan): keeps the host's
+    // upper bound of it tight without a synchronising read-back
+    R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)ctx->pinned + 1024 + 256 * slot + 128, t->counters + CNT_POOL_USED, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_done[slot], ctx->stream));
     return R3D_OK;
 }
@@ -1075,6 +1078,7 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
     for (uint32_t s = 0; s < n_scans; ++s) { scans[s].a.cmasks = ctx->cell_masks; scans[s].a.ctouched = ctx->cell_touched; }
     ctx->cells_dirty = true;
     R3D_TRY(pipe_enqueue(t, scans[0], 0, true));
+    uint64_t prev_records = 0;      // records of the apply queued last (not yet reflected in the cursor read back below)
     for (uint32_t s = 0; s < n_scans; ++s) {
         const int slot = (int)(s & 1u);
         if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
@@ -1098,7 +1102,14 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
             ctx->cells_dirty = false;   // both queued scans have been emitted: the scratch is clean
             return R3D_OK;
         }
+        {   // scan s's read-back was queued after apply(s-2) and before apply(s-1)
+            uint32_t cursor;
+            memcpy(&cursor, (char*)ctx->pinned + 1024 + 256 * slot + 128, sizeof cursor);
+            const uint64_t tight = (uint64_t)cursor + prev_records;
+            if (tight < t->pool_bound) t->pool_bound = tight;
+        }
         R3D_TRY(apply_delta_impl(t, slot ? t->delta_b : t->delta, hc[CNT_DELTA]));
+        prev_records = hc[CNT_DELTA];
         *rays_out += scans[s].a.n;
         *steps_out += (uint64_t)hc[CNT_STEPS_LO] | ((uint64_t)hc[CNT_STEPS_HI] << 32);
         t->delta_n = hc[CNT_DELTA];
