@@ -47,7 +47,8 @@ def _deps_mtime():
 
 def _compile(src, log):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    extra = os.environ.get("R3D_NVCC_EXTRA", "").split()      # e.g. -DK3_VARIANT=1 for kernel experiments
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + p.stdout + p.stderr)

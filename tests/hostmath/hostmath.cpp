@@ -43,6 +43,29 @@ long hm_ray_keys_predicated(double res, const float* o, const float* e, uint16_t
     }
     return n;
 }
+// the loop order the dense kernel uses: choose the axis first, then decide about the key the previous advance reached
+long hm_ray_keys_pending(double res, const float* o, const float* e, uint16_t* out, long cap) {
+    Ray r;
+    const int st = ray_setup(res, 1.0 / res, o[0], o[1], o[2], e[0], e[1], e[2], r);
+    if (st < 0) return -1;
+    if (st == 0) return 0;
+    long n = 0;
+    if (n < cap) { out[0] = (uint16_t)r.kx; out[1] = (uint16_t)r.ky; out[2] = (uint16_t)r.kz; }
+    ++n;
+    bool pending = false;
+    for (;;) {
+        double t;
+        const int a = ray_select(r, t);
+        if (pending) {
+            if (ray_at_end(r) || t > (double)r.length) break;
+            if (n < cap) { out[3 * n] = (uint16_t)r.kx; out[3 * n + 1] = (uint16_t)r.ky; out[3 * n + 2] = (uint16_t)r.kz; }
+            ++n;
+        }
+        ray_advance(r, a);
+        pending = true;
+    }
+    return n;
+}
 int hm_scan_point_end(const float* o, const float* p, double maxrange, float* e) {
     return scan_point_end(o[0], o[1], o[2], p[0], p[1], p[2], maxrange, e[0], e[1], e[2]) ? 1 : 0;
 }

@@ -28,6 +28,8 @@ def hm():
     L.hm_ray_keys.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
     L.hm_ray_keys_predicated.restype = C.c_long
     L.hm_ray_keys_predicated.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
+    L.hm_ray_keys_pending.restype = C.c_long
+    L.hm_ray_keys_pending.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long]
     L.hm_coord_to_key.argtypes = [C.c_double, C.c_float, C.c_float, C.c_float, C.c_void_p]
     L.hm_scan_point_end.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     L.hm_pose_apply.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -71,6 +73,8 @@ def ray(hm, res, o, e):
     buf2 = np.zeros((300000, 3), np.uint16)
     n2 = hm.hm_ray_keys_predicated(res, o32.ctypes.data, e32.ctypes.data, buf2.ctypes.data, buf2.shape[0])
     assert n2 == n and (n < 0 or np.array_equal(buf[:n], buf2[:n]))
+    n3 = hm.hm_ray_keys_pending(res, o32.ctypes.data, e32.ctypes.data, buf2.ctypes.data, buf2.shape[0])
+    assert n3 == n and (n < 0 or np.array_equal(buf[:n], buf2[:n]))
     return None if n < 0 else buf[:n].copy()
 
 
