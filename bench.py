@@ -177,11 +177,11 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def synth_on_device(torch, n_frames, rank, dev):
+def synth_on_device(torch, n_frames, rank, dev, kind="street"):
     """Synthetic depth of the named shape: 32 analytic 'street' frames made on the host (oracle generator, the same
     data the CPU arm uses), expanded on the device to n_frames distinct frames (shift + offset per frame)."""
     from oracle import points_oracle as po
-    base = np.stack([po.synth_depth_u16(W, H, po.KITTI_INTRINSICS, 20261018 + 2 + k, "street") for k in range(32)])
+    base = np.stack([po.synth_depth_u16(W, H, po.KITTI_INTRINSICS, 20261018 + 2 + k, kind) for k in range(32)])
     b = torch.from_numpy(base.astype(np.int32)).to(dev).reshape(32, H * W)
     out = torch.empty((n_frames, H * W), dtype=torch.int16, device=dev)
     step = 256
@@ -258,7 +258,7 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
            "voxels": tree.numVoxels(), "bricks": tree.numBricks(), "bt_bytes": len(bt), "bt_write_s": bt_s,
            "gpu_launches": ctx.launch_count() - launches0,
            "raycast_kernel_ms_last_scan": float(k3_ms[-1]), "raycast_steps_per_s_in_kernel": (steps / n_scans) / max(k3_ms[-1], 1e-9) * 1e3,
-           "workload": "C3: %d consecutive KITTI-shape street scans (1242x375 rays each, Z=0 sky pixels included as rays to the sensor origin)" % n_scans}
+           "workload": "C3: %d consecutive KITTI-shape %s scans (1242x375 rays each, Z=0 sky pixels included as rays to the sensor origin)" % (n_scans, args.depth_kind)}
     # the mode the reference's own OctoMap scripts use: updateNode(point, True) per point (octomap/txt_transfer_octomap.py:25)
     un = octomap.OcTree(res, ctx=ctx)
     un.reserve(1 << 17)
@@ -453,7 +453,7 @@ def run_gpu_arm(args):
 
     ctx = r3d.Context(local_rank)
     n_frames = args.frames or N_FRAMES_C2
-    depth, q, t = synth_on_device(torch, n_frames, rank, dev)
+    depth, q, t = synth_on_device(torch, n_frames, rank, dev, args.depth_kind)
     rt_host = ctx.pose_to_rt(q, t)
     rt = torch.from_numpy(rt_host).to(dev)
     px = n_frames * H * W
@@ -592,6 +592,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--octomap-scans", type=int, default=32, help="scans for the OctoMap scans/s section (0 = skip)")
     ap.add_argument("--octomap-scans-per-round", type=int, default=4, help="multi-GPU: scans each rank ray-casts between two exchanges")
+    ap.add_argument("--depth-kind", default="street", choices=["street", "uniform"],
+                    help="synthetic depth: analytic street scene (headline) or i.i.d. U[1, 80] m (ray-casting worst case, SURVEY.md section 8d)")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default: the 4500 of BASELINE config 2)")
     args = ap.parse_args()
     if args.impl == "reference":
