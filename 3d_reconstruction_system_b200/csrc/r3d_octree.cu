@@ -9,10 +9,11 @@
 //     brick key -> pool index.  Leaf log-odds of the flat store equal the leaf log-odds of upstream's tree
 //     (update-time pruning / expansion never changes a leaf value); the tree shape needed for .bt and size() is
 //     derived from the values on demand (r3d_bt.cu).
-//   * one scan's update (insertPointCloud) is a DELTA: a per-scan scratch hash table of bricks, each with a
-//     512-bit occupied mask and a 512-bit free mask, filled by the ray-casting kernel (K3) with atomicOr, then
-//     compacted to 136-byte records and applied to the store by the clamped log-odds kernel (K4).  Records are
-//     what multi-GPU runs exchange.
+//   * one scan's update (insertPointCloud) is a DELTA: per touched brick a 512-bit occupied mask and a 512-bit free
+//     mask, filled by the ray-casting kernel (K3) with red.or.  With a bounded range the masks are direct-mapped (a
+//     cube of brick cells around the sensor origin, context-level scratch, byte map of touched cells); with an
+//     unbounded one they sit in a per-scan hash table.  Either way they are read back as 136-byte records and applied
+//     to the store by the clamped log-odds kernel (K4).  Records are what multi-GPU runs exchange.
 #include <vector>
 
 #include "r3d_octree.cuh"
