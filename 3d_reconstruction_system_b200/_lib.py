@@ -75,6 +75,10 @@ SIGNATURES = {
     "r3d_tree_to_max_likelihood": (_i32, [_vp]),
     "r3d_tree_read_bt": (_i32, [_vp, C.c_char_p]),
     "r3d_tree_read_bt_mem": (_i32, [_vp, _vp, _sz]),
+    "r3d_tree_write_ot": (_i32, [_vp, C.c_char_p]),
+    "r3d_tree_write_ot_mem": (_i32, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "r3d_tree_read_ot": (_i32, [_vp, C.c_char_p]),
+    "r3d_tree_read_ot_mem": (_i32, [_vp, _vp, _sz]),
     "r3d_tree_num_voxels": (_i32, [_vp, _u64p]),
     "r3d_tree_size": (_i32, [_vp, _u64p]),
     "r3d_tree_search": (_i32, [_vp, _vp, _u64, _vp, _vp]),

@@ -12,7 +12,9 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "r3d_octree.cuh"
@@ -626,4 +628,249 @@ extern "C" int r3d_tree_read_bt(r3d_tree* t, const char* path) {
     while ((n = fread(chunk, 1, sizeof chunk, f)) > 0) buf.insert(buf.end(), chunk, chunk + n);
     fclose(f);
     return r3d_tree_read_bt_mem(t, buf.data(), buf.size());
+}
+
+// ------------------------------------------------------------------ .ot writer / reader (section 8f: full tree, log-odds kept)
+// AbstractOcTree::write / OcTreeBaseImpl::writeData of the `octomap` extension: header ("# Octomap OcTree file"), then
+// pre-order per node: float32 value, one byte of child-exists bits, the children.  The tree written is upstream's tree
+// as it stands after non-lazy updates: maximally pruned under exact equality of sibling leaf values, inner values =
+// max of the children (the same shape r3d_tree_size counts).  Rarely used next to .bt, so it is assembled on the host
+// from the exported bricks (sorted by Morton code; voxels inside a brick already are in child order).
+namespace r3d {
+
+struct OtWriter {
+    std::vector<uint8_t> bytes;
+    const BrickRecord* rec = nullptr;
+    const std::vector<std::pair<uint64_t, uint32_t>>* order = nullptr;   // (brick Morton code, record index), sorted
+
+    struct Res { float value; bool leaf; };
+
+    size_t open_node() { const size_t pos = bytes.size(); bytes.resize(pos + 5); return pos; }
+    void close_node(size_t pos, float v, uint8_t mask) { memcpy(&bytes[pos], &v, 4); bytes[pos + 4] = mask; }
+
+    // children results -> this node (pruning when all 8 are equal-valued leaves)
+    Res finish(size_t pos, const Res* child, uint8_t mask) {
+        float mx = 0.f;
+        bool first = true, all_leaf = true, all_eq = true;
+        float v0 = 0.f;
+        for (int c = 0; c < 8; ++c) {
+            if (!((mask >> c) & 1)) continue;
+            if (first) { mx = child[c].value; v0 = child[c].value; first = false; }
+            else { if (child[c].value > mx) mx = child[c].value; if (!(child[c].value == v0)) all_eq = false; }
+            if (!child[c].leaf) all_leaf = false;
+        }
+        if (mask == 0xff && all_leaf && all_eq) {
+            bytes.resize(pos + 5);
+            close_node(pos, v0, 0);
+            return {v0, true};
+        }
+        close_node(pos, mx, mask);
+        return {mx, false};
+    }
+
+    // node inside a brick: level 13 (span 512) .. 16 (span 1); exists iff any voxel of its range is known
+    Res brick_node(const BrickRecord& b, uint32_t first, uint32_t span) {
+        const size_t pos = open_node();
+        if (span == 1) { close_node(pos, b.value[first], 0); return {b.value[first], true}; }
+        Res child[8];
+        uint8_t mask = 0;
+        const uint32_t cs = span / 8;
+        for (int c = 0; c < 8; ++c) {
+            const uint32_t f = first + (uint32_t)c * cs;
+            bool any = false;
+            for (uint32_t i = f; i < f + cs && !any; ++i) any = (b.known[i >> 5] >> (i & 31u)) & 1u;
+            if (!any) continue;
+            child[c] = brick_node(b, f, cs);
+            mask |= (uint8_t)(1u << c);
+        }
+        return finish(pos, child, mask);
+    }
+
+    // node above brick level: bricks [lo, hi) of the sorted order share the Morton prefix of this node
+    Res upper_node(int level, size_t lo, size_t hi) {
+        if (level == 13) return brick_node(rec[(*order)[lo].second], 0, 512);
+        const size_t pos = open_node();
+        Res child[8];
+        uint8_t mask = 0;
+        const int sh = 3 * (12 - level);
+        size_t i = lo;
+        while (i < hi) {
+            const unsigned c = (unsigned)(((*order)[i].first >> sh) & 7u);
+            size_t j = i + 1;
+            while (j < hi && (unsigned)(((*order)[j].first >> sh) & 7u) == c) ++j;
+            child[c] = upper_node(level + 1, i, j);
+            mask |= (uint8_t)(1u << c);
+            i = j;
+        }
+        return finish(pos, child, mask);
+    }
+};
+
+static std::string ot_header(unsigned long long n_nodes, double res) {
+    std::string h = bt_header(n_nodes, res);
+    const std::string from = "# Octomap OcTree binary file";
+    h.replace(0, from.size(), "# Octomap OcTree file");
+    return h;
+}
+
+static int tree_serialise_ot(r3d_tree* t, std::vector<uint8_t>& out) {
+    r3d_ctx* ctx = t->ctx;
+    uint64_t nb = 0;
+    R3D_TRY(r3d_tree_num_bricks(t, &nb));
+    std::vector<BrickRecord> recs(nb);
+    if (nb) R3D_TRY(r3d_tree_export_bricks(t, recs.data(), nb, &nb));
+    std::vector<std::pair<uint64_t, uint32_t>> order;
+    order.reserve(nb);
+    for (uint32_t i = 0; i < nb; ++i) {
+        bool any = false;
+        for (int w = 0; w < 16 && !any; ++w) any = recs[i].known[w] != 0;
+        if (any) order.emplace_back(brick_morton(recs[i].key), i);
+    }
+    std::sort(order.begin(), order.end());
+    OtWriter w;
+    w.rec = recs.data();
+    w.order = &order;
+    if (!order.empty()) w.upper_node(0, 0, order.size());
+    const std::string hdr = ot_header(w.bytes.size() / 5, t->res);
+    out.assign(hdr.begin(), hdr.end());
+    out.insert(out.end(), w.bytes.begin(), w.bytes.end());
+    (void)ctx;
+    return R3D_OK;
+}
+
+// reader: leaves at any depth carry their own value
+struct OtReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    std::vector<BrickRecord> bricks;
+    bool overflow = false;
+    uint64_t nodes = 0;
+
+    void leaf_above_bricks(uint64_t prefix, int depth, float v) {
+        const uint64_t n = 1ull << (3 * (13 - depth));
+        if (bricks.size() + n > (1ull << 24)) { overflow = true; return; }
+        for (uint64_t k = 0; k < n; ++k) {
+            BrickRecord b;
+            memset(&b, 0, sizeof b);
+            b.key = BtReader::morton_to_brick_key((prefix << (3 * (13 - depth))) | k);
+            BtReader::fill(b, 0, 512, v);
+            bricks.push_back(b);
+        }
+    }
+    bool node(uint64_t prefix, int depth, uint32_t vox_first) {
+        if (p + 5 > end) return false;
+        float v;
+        memcpy(&v, p, 4);
+        const unsigned mask = p[4];
+        p += 5;
+        ++nodes;
+        if (mask == 0) {   // leaf
+            if (depth <= 13) { leaf_above_bricks(prefix, depth, v); return !overflow; }
+            BtReader::fill(bricks.back(), vox_first, 1u << (3 * (16 - depth)), v);
+            return true;
+        }
+        if (depth >= 16) return false;   // a depth-16 node cannot have children
+        if (depth == 13) {
+            if (bricks.size() >= (1ull << 24)) { overflow = true; return false; }
+            BrickRecord b;
+            memset(&b, 0, sizeof b);
+            b.key = BtReader::morton_to_brick_key(prefix);
+            bricks.push_back(b);
+        }
+        for (int c = 0; c < 8; ++c) {
+            if (!((mask >> c) & 1u)) continue;
+            const int cd = depth + 1;
+            uint32_t first = 0;
+            if (cd > 13) first = vox_first + (uint32_t)c * (1u << (3 * (16 - cd)));
+            if (!node((prefix << 3) | (uint64_t)c, cd, first)) return false;
+        }
+        return true;
+    }
+};
+
+}  // namespace r3d
+
+extern "C" int r3d_tree_write_ot_mem(r3d_tree* t, uint8_t* buf, size_t cap, size_t* len) {
+    if (!t || !len) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    DeviceSetter ds(t->ctx->device);
+    std::vector<uint8_t> out;
+    R3D_TRY(tree_serialise_ot(t, out));
+    *len = out.size();
+    if (buf && cap >= out.size()) memcpy(buf, out.data(), out.size());
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_write_ot(r3d_tree* t, const char* path) {
+    if (!t || !path) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    DeviceSetter ds(t->ctx->device);
+    std::vector<uint8_t> out;
+    R3D_TRY(tree_serialise_ot(t, out));
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_error(t->ctx, R3D_ERR_IO, "cannot open %s for writing", path);
+    const bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    if (fclose(f) != 0 || !ok) return set_error(t->ctx, R3D_ERR_IO, "short write to %s", path);
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_read_ot_mem(r3d_tree* t, const uint8_t* data, size_t len) {
+    if (!t || (!data && len)) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    r3d_ctx* ctx = t->ctx;
+    const char* s = reinterpret_cast<const char*>(data);
+    size_t pos = 0;
+    auto next_line = [&](std::string& line) {
+        if (pos >= len) return false;
+        size_t e = pos;
+        while (e < len && s[e] != '\n') ++e;
+        line.assign(s + pos, e - pos);
+        pos = e < len ? e + 1 : e;
+        return true;
+    };
+    std::string line;
+    if (!next_line(line) || line.rfind("# Octomap OcTree file", 0) != 0)
+        return set_error(ctx, R3D_ERR_UNSUPPORTED, "not an OctoMap .ot file: first line is not '# Octomap OcTree file'");
+    std::string id;
+    double res = 0.0;
+    unsigned long long size = 0;
+    bool have_data = false;
+    while (next_line(line)) {
+        if (line.empty() || line[0] == '#') continue;
+        if (line == "data") { have_data = true; break; }
+        char key[32] = {0};
+        char val[128] = {0};
+        if (sscanf(line.c_str(), "%31s %127s", key, val) == 2) {
+            if (!strcmp(key, "id")) id = val;
+            else if (!strcmp(key, "res")) res = atof(val);
+            else if (!strcmp(key, "size")) size = strtoull(val, nullptr, 10);
+        }
+    }
+    if (!have_data) return set_error(ctx, R3D_ERR_UNSUPPORTED, ".ot header has no 'data' line");
+    if (id != "OcTree") return set_error(ctx, R3D_ERR_UNSUPPORTED, ".ot holds a tree of type '%s', only OcTree is supported", id.c_str());
+    if (!(res > 0.0)) return set_error(ctx, R3D_ERR_UNSUPPORTED, ".ot header has no valid resolution");
+    DeviceSetter ds(ctx->device);
+    R3D_TRY(r3d_tree_clear(t));
+    t->res = res;
+    t->res_factor = 1.0 / res;
+    if (size == 0) return R3D_OK;
+    OtReader rd;
+    rd.p = data + pos;
+    rd.end = data + len;
+    if (!rd.node(0, 0, 0)) {
+        if (rd.overflow) return set_error(ctx, R3D_ERR_OOM, ".ot expands to more than 2^24 bricks");
+        return set_error(ctx, R3D_ERR_IO, ".ot payload is truncated or malformed");
+    }
+    if (rd.nodes != size) return set_error(ctx, R3D_ERR_IO, ".ot header says %llu nodes, the stream holds %llu", size, (unsigned long long)rd.nodes);
+    if (!rd.bricks.empty()) R3D_TRY(r3d_tree_import_bricks(t, rd.bricks.data(), rd.bricks.size()));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_read_ot(r3d_tree* t, const char* path) {
+    if (!t || !path) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(t->ctx, R3D_ERR_IO, "cannot open %s", path);
+    std::vector<uint8_t> buf;
+    uint8_t chunk[1 << 16];
+    size_t n;
+    while ((n = fread(chunk, 1, sizeof chunk, f)) > 0) buf.insert(buf.end(), chunk, chunk + n);
+    fclose(f);
+    return r3d_tree_read_ot_mem(t, buf.data(), buf.size());
 }

@@ -157,6 +157,39 @@ class OcTree:
         self._res = float(self.getResolutionFromLibrary())
         return True
 
+    def write(self, filename=None):
+        """write(bytes path) -> bool: the .ot format (every node's log-odds kept); with no argument returns the bytes."""
+        self._flush()
+        if filename is None:
+            n = C.c_size_t(0)
+            check(self._lib.r3d_tree_write_ot_mem(self._h, None, 0, C.byref(n)), self._ctx.handle)
+            buf = (C.c_uint8 * max(n.value, 1))()
+            check(self._lib.r3d_tree_write_ot_mem(self._h, buf, n.value, C.byref(n)), self._ctx.handle)
+            return bytes(buf[: n.value])
+        if isinstance(filename, str):
+            filename = filename.encode("utf-8")
+        rc = self._lib.r3d_tree_write_ot(self._h, filename)
+        if rc == -5:
+            return False
+        check(rc, self._ctx.handle)
+        return True
+
+    def read(self, source):
+        """read(bytes path | str path), or read(.ot file content starting with '# Octomap'): replaces the tree."""
+        self._pend_pts, self._pend_upd = [], []
+        if isinstance(source, (bytes, bytearray)) and bytes(source[:9]) == b"# Octomap":
+            buf = np.frombuffer(bytes(source), dtype=np.uint8)
+            check(self._lib.r3d_tree_read_ot_mem(self._h, buf.ctypes.data, buf.size), self._ctx.handle)
+        else:
+            if isinstance(source, str):
+                source = source.encode("utf-8")
+            rc = self._lib.r3d_tree_read_ot(self._h, bytes(source))
+            if rc == -5 and b"cannot open" in self._lib.r3d_last_error(self._ctx.handle):
+                return False
+            check(rc, self._ctx.handle)
+        self._res = float(self.getResolutionFromLibrary())
+        return True
+
     def getResolutionFromLibrary(self):
         r = C.c_double(0)
         check(self._lib.r3d_tree_resolution(self._h, C.byref(r)), self._ctx.handle)

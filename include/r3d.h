@@ -277,6 +277,16 @@ int r3d_tree_to_max_likelihood(r3d_tree *tree);
  */
 int r3d_tree_read_bt(r3d_tree *tree, const char *path);
 int r3d_tree_read_bt_mem(r3d_tree *tree, const uint8_t *data, size_t len);
+/*
+ * tree.write(path) / tree.read(path) of the `octomap` module: the .ot format, which keeps every node's log-odds
+ * ("# Octomap OcTree file" header; pre-order, per node float32 value + one byte of child-exists bits).  The tree written
+ * is upstream's tree as it stands after non-lazy updates (maximally pruned under exact equality of sibling leaf values,
+ * inner values = max of the children).  Assembled on the host from the exported bricks (section 8f-4).
+ */
+int r3d_tree_write_ot(r3d_tree *tree, const char *path);
+int r3d_tree_write_ot_mem(r3d_tree *tree, uint8_t *buf, size_t cap, size_t *len);
+int r3d_tree_read_ot(r3d_tree *tree, const char *path);
+int r3d_tree_read_ot_mem(r3d_tree *tree, const uint8_t *data, size_t len);
 
 /* Queries used by tests / tools. */
 int r3d_tree_num_voxels(r3d_tree *tree, uint64_t *n);            /* depth-16 leaves ever updated */

@@ -520,6 +520,30 @@ uint8_t *oo_write_binary_mem(OTree *t, size_t *len) {
     *len = b.len;
     return b.buf;
 }
+/* write() (AbstractOcTree::write + OcTreeBaseImpl::writeData / writeNodesRecurs): the full tree, log-odds preserved.
+ * Header like .bt but for the first line "# Octomap OcTree file"; then pre-order, per node: float32 value, one byte with
+ * bit i set when child i exists, then the existing children in index order.  The tree is written as it is (no
+ * max-likelihood conversion, no extra pruning). */
+static void write_ot_node(const Node *n, ByteBuf *b) {
+    bb_put(b, &n->value, sizeof(float));
+    unsigned char mask = 0;
+    for (unsigned i = 0; i < 8; ++i) if (child_exists(n, i)) mask |= (unsigned char)(1u << i);
+    bb_put(b, &mask, 1);
+    for (unsigned i = 0; i < 8; ++i) if (child_exists(n, i)) write_ot_node(n->children[i], b);
+}
+uint8_t *oo_write_ot_mem(const OTree *t, size_t *len) {
+    ByteBuf b = {NULL, 0, 0};
+    char hdr[512], res[64];
+    fmt_res(t->resolution, res, sizeof res);
+    int hl = snprintf(hdr, sizeof hdr,
+                      "# Octomap OcTree file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n"
+                      "id OcTree\nsize %zu\nres %s\ndata\n", t->tree_size, res);
+    bb_put(&b, hdr, (size_t)hl);
+    if (t->root) write_ot_node(t->root, &b);
+    *len = b.len;
+    return b.buf;
+}
+
 int oo_write_binary(OTree *t, const char *path) {
     size_t len; uint8_t *buf = oo_write_binary_mem(t, &len);
     FILE *f = fopen(path, "wb");

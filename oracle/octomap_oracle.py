@@ -72,6 +72,8 @@ def lib():
     L.oo_prune.argtypes = [vp]
     L.oo_write_binary_mem.restype = vp
     L.oo_write_binary_mem.argtypes = [vp, C.POINTER(sz)]
+    L.oo_write_ot_mem.restype = vp
+    L.oo_write_ot_mem.argtypes = [vp, C.POINTER(sz)]
     L.oo_write_binary.restype = i32
     L.oo_write_binary.argtypes = [vp, C.c_char_p]
     _lib = L
@@ -147,6 +149,14 @@ class OcTree:
     def write_binary_bytes(self):
         n = C.c_size_t(0)
         p = self._L.oo_write_binary_mem(self._t, C.byref(n))
+        data = C.string_at(p, n.value)
+        self._L.oo_free(p)
+        return data
+
+    def write_ot_bytes(self):
+        """tree.write(): the full .ot serialisation (log-odds preserved); does not modify the tree."""
+        n = C.c_size_t(0)
+        p = self._L.oo_write_ot_mem(self._t, C.byref(n))
         data = C.string_at(p, n.value)
         self._L.oo_free(p)
         return data

@@ -418,3 +418,45 @@ def test_insert_point_clouds_pipelined_device_batch(octomap, r3d):
     c.insertPointClouds(dev[4 * N:6 * N], origins[4:6], maxrange=30.0)
     c.insertPointCloud(scans[6], origins[6], maxrange=30.0)
     assert c.writeBinary() == a.writeBinary()
+
+
+def test_ot_write_read_match_oracle(octomap, tmp_path):
+    """tree.write() (.ot: every node's log-odds, upstream's pruned shape, inner values = max of children) byte-identical
+    to the oracle's real-tree serialisation; read() restores every voxel's float32 value; round trips are identities."""
+    rng = np.random.default_rng(61)
+    t, r = octomap.OcTree(0.1), oo.OcTree(0.1)
+    assert t.write() == r.write_ot_bytes()                                   # empty tree
+    origin = np.array([0.1, 0.2, -0.1])
+    for s in range(3):
+        sc = _scan(rng, 5000, origin + 0.2 * s, far=15.0).astype(np.float32)
+        t.insertPointCloud(sc, origin + 0.2 * s, maxrange=10.0)
+        r.insertPointCloud_f32(sc, origin + 0.2 * s, 10.0)
+    g = (np.arange(16) + 0.5) * 0.1 + 20.0                                    # a solid block: prunes up to depth 12
+    blk = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    for _ in range(5):                                                        # saturate: equal values -> collapsible
+        t.updateNodes(blk, True)
+        r.updateNodes(blk, True)
+    pts = rng.normal(scale=1.0, size=(3000, 3))
+    t.updateNodes(pts, False)
+    r.updateNodes(pts, False)
+    ot = t.write()
+    assert ot == r.write_ot_bytes()
+    assert t.size() == r.size() == (len(ot.split(b"data\n", 1)[1]) // 5)
+    p = tmp_path / "a.ot"
+    assert t.write(bytes(str(p), "utf-8")) and p.read_bytes() == ot
+    u = octomap.OcTree(0.3)
+    assert u.read(bytes(str(p), "utf-8")) and u.getResolution() == 0.1
+    k0, v0 = t.voxels()
+    k1, v1 = u.voxels()
+    assert np.array_equal(k0, k1) and np.array_equal(v0.view(np.uint32), v1.view(np.uint32))
+    assert u.write() == ot and u.writeBinary() == t.writeBinary()
+    w = octomap.OcTree(0.1)
+    assert w.read(ot) and w.write() == ot
+    # .bt and .ot are not interchangeable, and truncated payloads are rejected
+    with pytest.raises(Exception):
+        octomap.OcTree(0.1).read(t.writeBinary())
+    with pytest.raises(Exception):
+        octomap.OcTree(0.1).readBinary(ot)
+    with pytest.raises(Exception):
+        octomap.OcTree(0.1).read(ot[:len(ot) - 7])
+    assert not octomap.OcTree(0.1).read(bytes(str(tmp_path / "missing.ot"), "utf-8"))
