@@ -114,7 +114,10 @@ def read_frame_batch(paths, mode="gray", max_frames=256):
     if _is_png(paths[0]):
         w, h, _, d = png_info(paths[0])
         n = 1
-        while n < len(paths) and n < max_frames and _is_png(paths[n]) and png_info(paths[n])[:2] + (png_info(paths[n])[3],) == (w, h, d):
+        while n < len(paths) and n < max_frames and _is_png(paths[n]):
+            wn, hn, _, dn = png_info(paths[n])
+            if (wn, hn, dn) != (w, h, d):
+                break
             n += 1
         return imread_batch(paths[:n], bmode, channel=chan), n
     first = one(paths[0])
