@@ -460,3 +460,26 @@ def test_ot_write_read_match_oracle(octomap, tmp_path):
     with pytest.raises(Exception):
         octomap.OcTree(0.1).read(ot[:len(ot) - 7])
     assert not octomap.OcTree(0.1).read(bytes(str(tmp_path / "missing.ot"), "utf-8"))
+
+
+def test_sequence_to_octree_modes(octomap, r3d):
+    """mapping.sequence_to_octree: frames -> fused K1 -> one insertPointCloud per frame, with and without dropping the
+    invalid (Z = 0) pixels, against the oracle fed with the oracle's own points."""
+    mapping = importlib.import_module("3d_reconstruction_system_b200.mapping")
+    rng = np.random.default_rng(71)
+    n, H, W = 3, 24, 40
+    depth = rng.integers(0, 1500, size=(n, H, W)).astype(np.uint16)
+    depth[rng.random(size=depth.shape) < 0.3] = 0
+    q = np.stack([po.synth_pose(k, n)[0] for k in range(n)])
+    t = np.stack([po.synth_pose(k, n)[1] for k in range(n)])
+    intr = (60.0, 60.0, 20.0, 12.0)
+    for drop in (False, True):
+        tree = mapping.sequence_to_octree(depth, q, t, intr, resolution=0.1, maxrange=6.0, depth_scale=1 / 256.0, drop_invalid=drop)
+        ref = oo.OcTree(0.1)
+        for k in range(n):
+            rinv = po.quat_to_rinv_fixed(q[k])
+            w = po.depth_to_world(depth[k], intr, rinv, t[k], po.MODE_DEPTH, 1 / 256.0)[1].astype(np.float32)
+            if drop:
+                w = w[po.valid_mask(depth[k], 0, 1 / 256.0).ravel()]
+            ref.insertPointCloud_f32(w, po.camera_centre(rinv, t[k]), 6.0)
+        assert_same_tree(tree, ref)
