@@ -483,3 +483,30 @@ def test_sequence_to_octree_modes(octomap, r3d):
                 w = w[po.valid_mask(depth[k], 0, 1 / 256.0).ravel()]
             ref.insertPointCloud_f32(w, po.camera_centre(rinv, t[k]), 6.0)
         assert_same_tree(tree, ref)
+
+
+def test_pipelined_batch_record_overflow_path(octomap, r3d):
+    """Scans whose deltas hold far more than the 65 536 records the pipeline's buffers start with: the emit kernel raises
+    the device-side abort flag, the queued next scan skips, the host grows the buffers, lists again and re-queues.
+    The result must still equal the scan-by-scan loop (whose parity with the oracle the other tests establish; the
+    oracle itself needs minutes for rays this long)."""
+    ctx = r3d.default_context(0)
+    rng = np.random.default_rng(83)
+    S, N = 3, 8000
+    origins = np.array([[0.5 * s, 0.0, 0.0] for s in range(S)])
+    scans = []
+    for s in range(S):
+        d = rng.normal(size=(N, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        scans.append((origins[s] + d * rng.uniform(60.0, 100.0, size=(N, 1))).astype(np.float32))
+    scans = np.stack(scans)
+    dev = ctx.to_device(scans.reshape(-1, 3))
+    a, b = octomap.OcTree(0.1), octomap.OcTree(0.1)
+    b.insertPointClouds(dev, origins, maxrange=90.0)              # fresh tree: buffers at their initial size
+    assert b.lastScanStats()["records"] > 65536
+    for s in range(S):
+        a.insertPointCloud(scans[s], origins[s], maxrange=90.0)
+    ka, va = a.voxels()
+    kb, vb = b.voxels()
+    assert np.array_equal(ka, kb) and np.array_equal(va.view(np.uint32), vb.view(np.uint32))
+    assert a.writeBinary() == b.writeBinary()
