@@ -31,6 +31,7 @@ class OcTree:
         h = C.c_void_p()
         check(self._lib.r3d_tree_create(self._ctx.handle, float(resolution), C.byref(h)), self._ctx.handle)
         self._h = h
+        self._ctx._children.add(self)
         self._res = float(resolution)
         self._pend_pts = []      # queued updateNode points (float64 triples)
         self._pend_upd = []      # their log-odds increments (float32)
@@ -39,11 +40,14 @@ class OcTree:
         self._hit, self._miss, self._cmin, self._cmax, self._thres = (np.float32(v) for v in p)
         self.n_dropped = 0       # out-of-range points silently ignored, as upstream does
 
+    def _release(self):
+        if getattr(self, "_h", None):
+            self._lib.r3d_tree_destroy(self._h)
+            self._h = None
+
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
-                self._lib.r3d_tree_destroy(self._h)
-                self._h = None
+            self._release()
         except Exception:
             pass
 

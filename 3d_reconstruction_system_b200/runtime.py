@@ -1,6 +1,7 @@
 """Thin object layer over the C ABI: one Context per GPU, buffers are numpy arrays (host) or anything with
 data_ptr() / __cuda_array_interface__ (device, e.g. torch CUDA tensors used purely as memory holders)."""
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -123,6 +124,7 @@ class Context:
     def __init__(self, device=0):
         self.lib = _lib.load()
         self.device = int(device)
+        self._children = weakref.WeakSet()     # objects whose native handles point into this context (trees)
         self._h = self.lib.r3d_create(self.device)
         if not self._h:
             msg = self.lib.r3d_last_error(None)
@@ -130,6 +132,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):      # native trees keep a pointer to the context: free them first
+                child._release()
             self.lib.r3d_destroy(self._h)
             self._h = None
 
