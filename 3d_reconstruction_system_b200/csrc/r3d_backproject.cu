@@ -3,8 +3,8 @@
 // Replaces gentxtcord + get_pointdata/point_camera of the reference (transfer/camera_to_world.py:57-59,
 // 67-105; transfer/pixel_to_camera.py:24-44).  HBM-bound: sizeof(depth sample) + 12 B per pixel.
 //
-// Main kernel (k1_bulk): persistent CTAs, each owning a contiguous run of 1024-pixel tiles of the
-// flattened frame batch.  Depth tiles arrive in shared memory through a 4-stage cp.async.bulk (UBLKCP)
+// Main kernel (k1_bulk_vec): persistent CTAs, each owning a contiguous run of 2048-pixel tiles of the
+// flattened frame batch.  Depth tiles arrive in shared memory through a 2-stage cp.async.bulk (UBLKCP)
 // ring signalled by mbarriers; xyz records are assembled in shared memory and leave through
 // cp.async.bulk shared->global stores (bulk groups), so the SM's LSU only sees conflict-free LDS/STS.
 // All arithmetic is fp64 with separately rounded products/sums (r3d_math.cuh) and is cast once.
@@ -140,32 +140,83 @@ __device__ __forceinline__ void k1_tables(const K1Args& a, double* col, double* 
     for (unsigned j = threadIdx.x; j < a.H; j += blockDim.x) row[j] = pixel_coeff((int)j, a.cy, a.fy);
 }
 
-// ------------------------------------------------------------------ k1_bulk: the hot kernel
+// ------------------------------------------------------------------ k1_bulk_vec: the hot kernel
 // Requires W >= K1_THREADS and H >= 8 (smaller images take the generic kernel) so that stepping a pixel index by
-// 256 or 1024 wraps the column at most (1 + 1024/W) times and the row at most once.
-template <typename DepthT, typename OutT, bool kWorld, int kMode, int kOutBufs>
-__global__ void __launch_bounds__(K1_THREADS, 4) k1_bulk(const K1Args a) {
+// 1024 wraps the column at most (1 + 1024/W) times and the row at most once.
+//
+// A thread owns 4 CONSECUTIVE pixels of each 1024-pixel group: one vector load of the samples, the column
+// coefficients as two 16-byte loads, one row coefficient, and three 16-byte stores of the 12 output floats (48-byte
+// thread stride: conflict-free per quarter warp).  A tile is kGroups groups, so the per-tile work (mbarrier wait,
+// proxy fence, CTA barrier, bulk issue) is paid once per 4 * kGroups pixels per thread.  The first version of this
+// kernel (one pixel per thread per 256-pixel row of the tile, 4-stage ring, 4 CTAs per SM) issued 67 warp instructions
+// per pixel, 28 of them the fp64 arithmetic the parity contract fixes, and ran at 70 % issue-slot utilisation and
+// 0.83 of the HBM copy rate; this layout issues about 47 and reaches 0.94.  A warp in which some thread's 4 pixels
+// cross a row end (about one warp-group in ten at W = 1242) or need another frame's pose takes the per-pixel path.
+//
+// Measured on B200 (C2, 4 500 frames per launch; tools/k1_probe.py, profiles/r1_k1_vec_sweep.jsonl), fraction of the
+// measured HBM copy rate: groups x stages x CTAs/SM = 2x2x3 0.94 (default) | 3x2x2 0.94 | 2x4x2 0.93 | 1x4x3 0.91 |
+// 2x3x3 0.88 | 1x2x4 0.86 | 1x2x3 0.85 | 2x1x3 0.71; tiles interleaved across CTAs instead of one contiguous run per
+// CTA 0.81; three output buffers 0.85.
+#ifndef K1V_GROUPS
+#define K1V_GROUPS 2
+#endif
+#ifndef K1V_STAGES
+#define K1V_STAGES 2
+#endif
+#ifndef K1V_MINB
+#define K1V_MINB 3
+#endif
+#ifndef K1V_OUTBUFS
+#define K1V_OUTBUFS 2
+#endif
+#ifndef K1V_INTERLEAVE
+#define K1V_INTERLEAVE 0
+#endif
+constexpr int K1V_GROUP = K1_THREADS * 4;       // 1024 pixels
+
+template <typename DepthT> struct SampleVec;
+template <> struct SampleVec<unsigned char> { using type = unsigned; };
+template <> struct SampleVec<unsigned short> { using type = uint2; };
+template <> struct SampleVec<float> { using type = uint4; };
+
+__device__ __forceinline__ void store_records4(float* dst, const float (&o)[12]) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    d[0] = make_float4(o[0], o[1], o[2], o[3]);
+    d[1] = make_float4(o[4], o[5], o[6], o[7]);
+    d[2] = make_float4(o[8], o[9], o[10], o[11]);
+}
+__device__ __forceinline__ void store_records4(double*, const double (&)[3]) {}
+
+template <typename DepthT, typename OutT, bool kWorld, int kMode, int kGroups>
+__global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_vec(const K1Args a) {
+    constexpr int kStages = K1V_STAGES, kOutBufs = K1V_OUTBUFS;
+    constexpr int kTile = K1V_GROUP * kGroups;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // K1_STAGES mbarriers
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // kStages mbarriers
     double* col = reinterpret_cast<double*>(smem + 128);
-    double* row = col + a.W;
-    size_t off = 128 + ((size_t)(a.W + a.H) * 8 + 127) / 128 * 128;
-    DepthT* in_s = reinterpret_cast<DepthT*>(smem + off);               // K1_STAGES x K1_TILE
-    off += (size_t)K1_STAGES * K1_TILE * sizeof(DepthT);
-    OutT* out_s = reinterpret_cast<OutT*>(smem + off);                  // kOutBufs x K1_TILE x 3
+    double* row = col + ((a.W + 1u) & ~1u);                             // 16-byte aligned
+    size_t off = 128 + ((size_t)(a.W + 1 + a.H) * 8 + 127) / 128 * 128;
+    DepthT* in_s = reinterpret_cast<DepthT*>(smem + off);               // kStages x kTile
+    off += (size_t)kStages * kTile * sizeof(DepthT);
+    OutT* out_s = reinterpret_cast<OutT*>(smem + off);                  // kOutBufs x kTile x 3
 
     const unsigned tid = threadIdx.x;
-    constexpr uint32_t kInBytes = K1_TILE * sizeof(DepthT);
-    constexpr uint32_t kOutBytes = K1_TILE * 3 * sizeof(OutT);
+    constexpr uint32_t kInBytes = kTile * sizeof(DepthT);
+    constexpr uint32_t kOutBytes = kTile * 3 * sizeof(OutT);
 
-    // contiguous run of tiles for this CTA
+#if K1V_INTERLEAVE
+    const unsigned long long tstep = gridDim.x;                         // tile t0 + k * gridDim.x
+    const unsigned long long t0 = blockIdx.x, t1 = a.n_tiles;
+#else
+    const unsigned long long tstep = 1;                                 // contiguous run of tiles
     const unsigned long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
     const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
     unsigned long long t1 = t0 + per;
     if (t1 > a.n_tiles) t1 = a.n_tiles;
+#endif
 
     if (tid == 0) {
-        for (int s = 0; s < K1_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
     k1_tables(a, col, row);
@@ -175,62 +226,107 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_bulk(const K1Args a) {
     const DepthT* gin = reinterpret_cast<const DepthT*>(a.depth);
     OutT* gout = reinterpret_cast<OutT*>(a.out);
     if (tid == 0) {
-        for (int s = 0; s < K1_STAGES; ++s) {
-            if (t0 + s < t1) {
+        for (int s = 0; s < kStages; ++s) {
+            if (t0 + s * tstep < t1) {
                 mbar_arrive_expect_tx(&full[s], kInBytes);
-                bulk_load(in_s + (size_t)s * K1_TILE, gin + (t0 + s) * K1_TILE, kInBytes, &full[s]);
+                bulk_load(in_s + (size_t)s * kTile, gin + (t0 + s * tstep) * kTile, kInBytes, &full[s]);
             }
         }
     }
 
-    // (frame, row, column) of this thread's first pixel of the tile, advanced incrementally: no division in the loop
-    const unsigned long long px0 = t0 * K1_TILE + tid;
+    // (frame, row, column) of the first of this thread's 4 pixels in the current group, advanced by 1024 per group
+    const unsigned long long px0 = t0 * kTile + tid * 4u;
     unsigned f0 = (unsigned)(px0 / a.WH);
     const unsigned r0 = (unsigned)(px0 - (unsigned long long)f0 * a.WH);
     unsigned v0 = r0 / a.W, u0 = r0 - v0 * a.W;
     const unsigned W = a.W, H = a.H;
-    const unsigned q_tile = K1_TILE / W, r_tile = K1_TILE - q_tile * W;      // +1024 pixels
+    const unsigned q_grp = K1V_GROUP / W, r_grp = K1V_GROUP - q_grp * W;
+#if K1V_INTERLEAVE
+    // a tile step skips (gridDim.x - 1) tiles after the kGroups group steps
+    const unsigned long long skip = (tstep - 1) * kTile;
+    const unsigned skip_f = (unsigned)(skip / a.WH);
+    const unsigned skip_r = (unsigned)(skip - (unsigned long long)skip_f * a.WH);
+    const unsigned skip_v = skip_r / W, skip_u = skip_r - skip_v * W;
+#endif
     unsigned pose_frame = 0xffffffffu;
     Pose pose;
 
     unsigned stage = 0, parity = 0, ob = 0;
-    for (unsigned long long t = t0; t < t1; ++t) {
+    for (unsigned long long t = t0; t < t1; t += tstep) {
         mbar_wait(&full[stage], parity);
-        const DepthT* tin = in_s + (size_t)stage * K1_TILE + tid;
-        OutT* tout = out_s + (size_t)ob * K1_TILE * 3 + tid * 3;
-        unsigned u = u0, v = v0;
-        if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
+        const DepthT* tin = in_s + (size_t)stage * kTile + tid * 4u;
+        OutT* tout = out_s + (size_t)ob * kTile * 3 + tid * 12u;
 #pragma unroll 1
-        for (int j = 0; j < K1_PPT; ++j) {
-            OutT x, y, z;
-            k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(tin[j * K1_THREADS]), col[u], row[v], pose, x, y, z);
-            tout[j * K1_THREADS * 3 + 0] = x; tout[j * K1_THREADS * 3 + 1] = y; tout[j * K1_THREADS * 3 + 2] = z;
-            u += K1_THREADS;                       // W >= 256: at most one column wrap
-            if (u >= W) {
-                u -= W;
-                if (++v == H) {                    // next frame (rare): switch pose
-                    v = 0;
-                    if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
+        for (int g = 0; g < kGroups; ++g) {
+            DepthT raw[4];
+            *reinterpret_cast<typename SampleVec<DepthT>::type*>(raw) =
+                *reinterpret_cast<const typename SampleVec<DepthT>::type*>(tin + g * K1V_GROUP);
+            OutT* const gdst = tout + g * K1V_GROUP * 3;
+            OutT o[sizeof(OutT) == 4 ? 12 : 3];                         // float: 12 values leave as three 16-byte stores
+            auto emit = [&](int j, OutT x, OutT y, OutT z) {           // double: stored pixel by pixel (registers)
+                if constexpr (sizeof(OutT) == 4) { o[3 * j] = x; o[3 * j + 1] = y; o[3 * j + 2] = z; }
+                else { gdst[3 * j] = x; gdst[3 * j + 1] = y; gdst[3 * j + 2] = z; }
+            };
+            if (__all_sync(0xffffffffu, (u0 + 3u < W) & (!kWorld | (f0 == pose_frame)))) {
+                // no thread of the warp crosses a row end or needs another pose: one row coefficient, column
+                // coefficients by pairs.  (The pose reload sits on the other path because the compiler predicates
+                // its 12 loads instead of branching around them: 12 issue slots per group when it is in line.)
+                const double bv = row[v0];
+                double au[4];
+                if ((u0 & 1u) == 0) {
+                    const double2 c01 = *reinterpret_cast<const double2*>(col + u0);
+                    const double2 c23 = *reinterpret_cast<const double2*>(col + u0 + 2);
+                    au[0] = c01.x; au[1] = c01.y; au[2] = c23.x; au[3] = c23.y;
+                } else {
+                    au[0] = col[u0]; au[1] = col[u0 + 1]; au[2] = col[u0 + 2]; au[3] = col[u0 + 3];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    OutT x, y, z;
+                    k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(raw[j]), au[j], bv, pose, x, y, z);
+                    emit(j, x, y, z);
+                }
+            } else {
+                if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
+                unsigned u = u0, v = v0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    OutT x, y, z;
+                    k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(raw[j]), col[u], row[v], pose, x, y, z);
+                    emit(j, x, y, z);
+                    if (++u == W) {
+                        u = 0;
+                        if (++v == H) {                // next frame (rare): switch pose
+                            v = 0;
+                            if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
+                        }
+                    }
                 }
             }
+            if constexpr (sizeof(OutT) == 4) store_records4(gdst, o);
+            u0 += r_grp; v0 += q_grp;
+            if (u0 >= W) { u0 -= W; ++v0; }
+            if (v0 >= H) { v0 -= H; ++f0; }
         }
         // the bulk store issued kOutBufs-1 tiles ago must have finished reading the buffer the NEXT tile writes
         if (tid == 0) bulk_wait_read<kOutBufs - 2>();
         fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) {
-            bulk_store(gout + t * (unsigned long long)K1_TILE * 3, out_s + (size_t)ob * K1_TILE * 3, kOutBytes);
+            bulk_store(gout + t * (unsigned long long)kTile * 3, out_s + (size_t)ob * kTile * 3, kOutBytes);
             bulk_commit();
-            const unsigned long long tn = t + K1_STAGES;
+            const unsigned long long tn = t + kStages * tstep;
             if (tn < t1) {   // every thread is past its reads of this stage (barrier above): refill it
                 mbar_arrive_expect_tx(&full[stage], kInBytes);
-                bulk_load(in_s + (size_t)stage * K1_TILE, gin + tn * K1_TILE, kInBytes, &full[stage]);
+                bulk_load(in_s + (size_t)stage * kTile, gin + tn * kTile, kInBytes, &full[stage]);
             }
         }
-        u0 += r_tile; v0 += q_tile;
+#if K1V_INTERLEAVE
+        u0 += skip_u; v0 += skip_v; f0 += skip_f;
         if (u0 >= W) { u0 -= W; ++v0; }
         if (v0 >= H) { v0 -= H; ++f0; }
-        if (++stage == K1_STAGES) { stage = 0; parity ^= 1u; }
+#endif
+        if (++stage == kStages) { stage = 0; parity ^= 1u; }
         if (++ob == kOutBufs) ob = 0;
     }
     if (tid == 0) bulk_wait_all<0>();
@@ -654,12 +750,13 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
         return R3D_OK;
     }
     unsigned long long done = 0;
-    if (bulk_ok && total >= K1_TILE) {
-        constexpr int kOutBufs = 2;   // 2 x 12 KB (float): 46 KB per CTA -> 4 CTAs per SM
-        a.n_tiles = total / K1_TILE;
-        const size_t smem = 128 + table_bytes + (size_t)K1_STAGES * K1_TILE * sizeof(DepthT) +
-                            (size_t)kOutBufs * K1_TILE * 3 * sizeof(OutT);
-        auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk<DepthT, OutT, kWorld, 0, kOutBufs> : k1_bulk<DepthT, OutT, kWorld, 1, kOutBufs>;
+    constexpr int kGroups = sizeof(OutT) == 4 ? K1V_GROUPS : 1;      // 24 KB (float) / 24 KB (double) of records per tile
+    constexpr int kTileV = K1V_GROUP * kGroups;
+    if (bulk_ok && total >= (unsigned long long)kTileV) {
+        a.n_tiles = total / kTileV;
+        const size_t tables_v = ((size_t)(a.W + 1 + a.H) * 8 + 127) / 128 * 128;
+        const size_t smem = 128 + tables_v + (size_t)K1V_STAGES * kTileV * sizeof(DepthT) + (size_t)K1V_OUTBUFS * kTileV * 3 * sizeof(OutT);
+        auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk_vec<DepthT, OutT, kWorld, 0, kGroups> : k1_bulk_vec<DepthT, OutT, kWorld, 1, kGroups>;
         R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem));
@@ -668,7 +765,7 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
         if (grid > a.n_tiles) grid = a.n_tiles;
         kern<<<(unsigned)grid, K1_THREADS, smem, st>>>(a);
         ctx->launches++;
-        done = a.n_tiles * K1_TILE;
+        done = a.n_tiles * kTileV;
     }
     if (done < total) {
         a.px_begin = done;
@@ -711,7 +808,8 @@ static int launch_k1(r3d_ctx* ctx, cudaStream_t st, const void* d_depth, int dty
     const size_t es = elem_size(dtype);
     const size_t osz = out_dtype == R3D_OUT_F32 ? 4 : 8;
     const bool bulk_ok = W >= K1_THREADS && H >= 8 && pitch == (size_t)W * es && ((uintptr_t)d_depth % 16 == 0) && ((uintptr_t)d_out % 16 == 0) &&
-                         ((size_t)(W + H) * 8 + (size_t)K1_STAGES * K1_TILE * es + 3 * (size_t)K1_TILE * 3 * osz < 200 * 1024);
+                         ((size_t)(W + H) * 8 + (size_t)K1_STAGES * K1_TILE * es + 3 * (size_t)K1_TILE * 3 * osz < 200 * 1024) &&
+                         (size_t)(W + H) * 8 < 100 * 1024;
     switch (dtype) {
         case R3D_U8: return launch_k1_depth<unsigned char>(ctx, st, a, bulk_ok, compact, out_dtype, total);
         case R3D_U16: return launch_k1_depth<unsigned short>(ctx, st, a, bulk_ok, compact, out_dtype, total);

@@ -180,12 +180,16 @@ __device__ __forceinline__ bool cell_of_key(const ScanArgs& a, int kx, int ky, i
     return (ux < a.gdim) & (uy < a.gdim) & (uz < a.gdim);
 }
 
+#ifndef K3_VARIANT
+#define K3_VARIANT 0
+#endif
 // Per-lane state of the dense walker.
 struct DenseLane {
     int kx, ky, kz, ex, ey, ez, sx, sy, sz;
     double tmx, tmy, tmz, tdx, tdy, tdz, length;
     int csx, csy, csz;   // cell-index change of one brick step along each axis
     int axis;
+    int mx, my, mz;      // (K3_VARIANT 1) the axis of the next step as 0/1 integers
     uint32_t cell;       // grid cell of the current brick
     uint32_t widx;       // index of the current sub-block's free word in the 64-bit view of cmasks
     uint64_t mask;       // cells of that sub-block visited by this ray
@@ -201,7 +205,24 @@ struct DenseLane {
 // ago.  A ray that leaves a sub-block earlier publishes its cells without knowing the word (a redundant red.or).
 __device__ __forceinline__ bool dense_step(const ScanArgs& a, uint64_t* masks64, uint8_t* touched, DenseLane& L, uint64_t& stage) {
     if (L.age == 1) L.seen = stage;      // requested two iterations ago, into this same register
-    // ---- one DDA step along `axis` (ray_advance), then pick the next axis (ray_select)
+    // ---- one DDA step along the chosen axis (ray_advance), then pick the next axis (ray_select).
+#if K3_VARIANT & 1
+    // The axis is carried as three 0/1 integers and applied by multiplication: selects run on the integer / select pipe,
+    // which bounds this kernel, multiplies on the FMA and fp64 pipes.  x * 1.0 and t + 0.0 are exact, so the tMax update
+    // tm + m * td is bit-identical to "tm + td on the chosen axis, untouched elsewhere".
+    const int okx = L.kx, oky = L.ky, okz = L.kz;
+    L.kx += L.mx * L.sx; L.ky += L.my * L.sy; L.kz += L.mz * L.sz;
+    const int cstep = L.mx * L.csx + L.my * L.csy + L.mz * L.csz;
+    L.tmx = dadd(L.tmx, dmul((double)L.mx, L.tdx));
+    L.tmy = dadd(L.tmy, dmul((double)L.my, L.tdy));
+    L.tmz = dadd(L.tmz, dmul((double)L.mz, L.tdz));
+    const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
+    const bool selx = xy & xz, sely = (!xy) & yz;
+    const double tsel = selx ? L.tmx : (sely ? L.tmy : L.tmz);
+    L.mx = selx ? 1 : 0; L.my = sely ? 1 : 0; L.mz = 1 - L.mx - L.my;
+    const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | (tsel > L.length);
+    const int diff = (L.kx ^ okx) | (L.ky ^ oky) | (L.kz ^ okz);
+#else
     const bool ax = L.axis == 0, ay = L.axis == 1, az = L.axis == 2;
     const double nx = dadd(L.tmx, L.tdx), ny = dadd(L.tmy, L.tdy), nz = dadd(L.tmz, L.tdz);
     const int kold = ax ? L.kx : (ay ? L.ky : L.kz);
@@ -215,6 +236,7 @@ __device__ __forceinline__ bool dense_step(const ScanArgs& a, uint64_t* masks64,
     L.axis = selx ? 0 : (sely ? 1 : 2);
     const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | (tsel > L.length);
     const int diff = knew ^ kold;            // only one coordinate moved
+#endif
     const bool new_sub = (diff >> 2) != 0;
     // ---- leaving the sub-block (or the ray): publish its cells unless all of them are known to be set
     if ((done | new_sub) && (L.mask & ~L.seen) != 0) {
@@ -298,6 +320,7 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_raycast_dense(const Scan
                     ++L.steps;
                     double t;
                     L.axis = ray_select(r, t);
+                    L.mx = L.axis == 0; L.my = L.axis == 1; L.mz = L.axis == 2;
                 }
             }
             continue;
