@@ -166,12 +166,6 @@ __device__ __forceinline__ void k1_tables(const K1Args& a, double* col, double* 
 #ifndef K1V_MINB
 #define K1V_MINB 3
 #endif
-#ifndef K1V_OUTBUFS
-#define K1V_OUTBUFS 2
-#endif
-#ifndef K1V_INTERLEAVE
-#define K1V_INTERLEAVE 0
-#endif
 constexpr int K1V_GROUP = K1_THREADS * 4;       // 1024 pixels
 
 template <typename DepthT> struct SampleVec;
@@ -187,15 +181,74 @@ __device__ __forceinline__ void store_records4(float* dst, const float (&o)[12])
 }
 __device__ __forceinline__ void store_records4(double*, const double (&)[3]) {}
 
+// The 4 consecutive pixels of one thread: (u0, v0, f0) is the first one.  emit(j, x, y, z) receives the records in
+// pixel order.  Returns the index of the pixel that is the last one of its frame (f0's), or -1.
+template <typename DepthT, typename OutT, bool kWorld, int kMode, typename Emit>
+__device__ __forceinline__ int k1_group4(const K1Args& a, const double* col, const double* row, const DepthT (&raw)[4], unsigned u0,
+                                         unsigned v0, unsigned f0, unsigned& pose_frame, Pose& pose, Emit&& emit) {
+    const unsigned W = a.W, H = a.H;
+    int last = -1;
+    if (__all_sync(0xffffffffu, (u0 + 3u < W) & (!kWorld | (f0 == pose_frame)))) {
+        // no thread of the warp crosses a row end or needs another pose: one row coefficient, column coefficients by
+        // pairs.  (The pose reload sits on the other path because the compiler predicates its 12 loads instead of
+        // branching around them: 12 issue slots per group when it is in line.)
+        const double bv = row[v0];
+        double au[4];
+        if ((u0 & 1u) == 0) {
+            const double2 c01 = *reinterpret_cast<const double2*>(col + u0);
+            const double2 c23 = *reinterpret_cast<const double2*>(col + u0 + 2);
+            au[0] = c01.x; au[1] = c01.y; au[2] = c23.x; au[3] = c23.y;
+        } else {
+            au[0] = col[u0]; au[1] = col[u0 + 1]; au[2] = col[u0 + 2]; au[3] = col[u0 + 3];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            OutT x, y, z;
+            k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(raw[j]), au[j], bv, pose, x, y, z);
+            emit(j, x, y, z);
+        }
+        if ((u0 + 4u == W) & (v0 + 1u == H)) last = 3;
+    } else {
+        if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
+        unsigned u = u0, v = v0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            OutT x, y, z;
+            k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(raw[j]), col[u], row[v], pose, x, y, z);
+            emit(j, x, y, z);
+            if (++u == W) {
+                u = 0;
+                if (++v == H) {                // next frame (rare): switch pose
+                    v = 0;
+                    last = j;
+                    if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
+                }
+            }
+        }
+    }
+    return last;
+}
+
+template <typename DepthT>
+__device__ __forceinline__ void load_samples4(const DepthT* p, DepthT (&raw)[4]) {
+    *reinterpret_cast<typename SampleVec<DepthT>::type*>(raw) = *reinterpret_cast<const typename SampleVec<DepthT>::type*>(p);
+}
+
+// Shared-memory carve-up of the two bulk kernels: [mbarriers + small arrays | col | row | input ring | output buffers]
+__device__ __forceinline__ size_t k1v_tables(const K1Args& a, unsigned char* smem, size_t head, double*& col, double*& row) {
+    col = reinterpret_cast<double*>(smem + head);
+    row = col + ((a.W + 1u) & ~1u);                                     // 16-byte aligned
+    return head + ((size_t)(a.W + 1 + a.H) * 8 + 127) / 128 * 128;
+}
+
 template <typename DepthT, typename OutT, bool kWorld, int kMode, int kGroups>
 __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_vec(const K1Args a) {
-    constexpr int kStages = K1V_STAGES, kOutBufs = K1V_OUTBUFS;
+    constexpr int kStages = K1V_STAGES, kOutBufs = 2;
     constexpr int kTile = K1V_GROUP * kGroups;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);                 // kStages mbarriers
-    double* col = reinterpret_cast<double*>(smem + 128);
-    double* row = col + ((a.W + 1u) & ~1u);                             // 16-byte aligned
-    size_t off = 128 + ((size_t)(a.W + 1 + a.H) * 8 + 127) / 128 * 128;
+    double *col, *row;
+    size_t off = k1v_tables(a, smem, 128, col, row);
     DepthT* in_s = reinterpret_cast<DepthT*>(smem + off);               // kStages x kTile
     off += (size_t)kStages * kTile * sizeof(DepthT);
     OutT* out_s = reinterpret_cast<OutT*>(smem + off);                  // kOutBufs x kTile x 3
@@ -204,16 +257,11 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_vec(const K1Args
     constexpr uint32_t kInBytes = kTile * sizeof(DepthT);
     constexpr uint32_t kOutBytes = kTile * 3 * sizeof(OutT);
 
-#if K1V_INTERLEAVE
-    const unsigned long long tstep = gridDim.x;                         // tile t0 + k * gridDim.x
-    const unsigned long long t0 = blockIdx.x, t1 = a.n_tiles;
-#else
-    const unsigned long long tstep = 1;                                 // contiguous run of tiles
+    // contiguous run of tiles for this CTA (tiles interleaved across CTAs measured 0.81 against 0.94 of the copy rate)
     const unsigned long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
     const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
     unsigned long long t1 = t0 + per;
     if (t1 > a.n_tiles) t1 = a.n_tiles;
-#endif
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
@@ -227,9 +275,9 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_vec(const K1Args
     OutT* gout = reinterpret_cast<OutT*>(a.out);
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
-            if (t0 + s * tstep < t1) {
+            if (t0 + s < t1) {
                 mbar_arrive_expect_tx(&full[s], kInBytes);
-                bulk_load(in_s + (size_t)s * kTile, gin + (t0 + s * tstep) * kTile, kInBytes, &full[s]);
+                bulk_load(in_s + (size_t)s * kTile, gin + (t0 + s) * kTile, kInBytes, &full[s]);
             }
         }
     }
@@ -241,68 +289,24 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_vec(const K1Args
     unsigned v0 = r0 / a.W, u0 = r0 - v0 * a.W;
     const unsigned W = a.W, H = a.H;
     const unsigned q_grp = K1V_GROUP / W, r_grp = K1V_GROUP - q_grp * W;
-#if K1V_INTERLEAVE
-    // a tile step skips (gridDim.x - 1) tiles after the kGroups group steps
-    const unsigned long long skip = (tstep - 1) * kTile;
-    const unsigned skip_f = (unsigned)(skip / a.WH);
-    const unsigned skip_r = (unsigned)(skip - (unsigned long long)skip_f * a.WH);
-    const unsigned skip_v = skip_r / W, skip_u = skip_r - skip_v * W;
-#endif
     unsigned pose_frame = 0xffffffffu;
     Pose pose;
 
     unsigned stage = 0, parity = 0, ob = 0;
-    for (unsigned long long t = t0; t < t1; t += tstep) {
+    for (unsigned long long t = t0; t < t1; ++t) {
         mbar_wait(&full[stage], parity);
         const DepthT* tin = in_s + (size_t)stage * kTile + tid * 4u;
         OutT* tout = out_s + (size_t)ob * kTile * 3 + tid * 12u;
 #pragma unroll 1
         for (int g = 0; g < kGroups; ++g) {
             DepthT raw[4];
-            *reinterpret_cast<typename SampleVec<DepthT>::type*>(raw) =
-                *reinterpret_cast<const typename SampleVec<DepthT>::type*>(tin + g * K1V_GROUP);
+            load_samples4(tin + g * K1V_GROUP, raw);
             OutT* const gdst = tout + g * K1V_GROUP * 3;
             OutT o[sizeof(OutT) == 4 ? 12 : 3];                         // float: 12 values leave as three 16-byte stores
-            auto emit = [&](int j, OutT x, OutT y, OutT z) {           // double: stored pixel by pixel (registers)
+            k1_group4<DepthT, OutT, kWorld, kMode>(a, col, row, raw, u0, v0, f0, pose_frame, pose, [&](int j, OutT x, OutT y, OutT z) {
                 if constexpr (sizeof(OutT) == 4) { o[3 * j] = x; o[3 * j + 1] = y; o[3 * j + 2] = z; }
-                else { gdst[3 * j] = x; gdst[3 * j + 1] = y; gdst[3 * j + 2] = z; }
-            };
-            if (__all_sync(0xffffffffu, (u0 + 3u < W) & (!kWorld | (f0 == pose_frame)))) {
-                // no thread of the warp crosses a row end or needs another pose: one row coefficient, column
-                // coefficients by pairs.  (The pose reload sits on the other path because the compiler predicates
-                // its 12 loads instead of branching around them: 12 issue slots per group when it is in line.)
-                const double bv = row[v0];
-                double au[4];
-                if ((u0 & 1u) == 0) {
-                    const double2 c01 = *reinterpret_cast<const double2*>(col + u0);
-                    const double2 c23 = *reinterpret_cast<const double2*>(col + u0 + 2);
-                    au[0] = c01.x; au[1] = c01.y; au[2] = c23.x; au[3] = c23.y;
-                } else {
-                    au[0] = col[u0]; au[1] = col[u0 + 1]; au[2] = col[u0 + 2]; au[3] = col[u0 + 3];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    OutT x, y, z;
-                    k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(raw[j]), au[j], bv, pose, x, y, z);
-                    emit(j, x, y, z);
-                }
-            } else {
-                if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
-                unsigned u = u0, v = v0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    OutT x, y, z;
-                    k1_pixel_pose<OutT, kWorld, kMode>(a, raw_to_double(raw[j]), col[u], row[v], pose, x, y, z);
-                    emit(j, x, y, z);
-                    if (++u == W) {
-                        u = 0;
-                        if (++v == H) {                // next frame (rare): switch pose
-                            v = 0;
-                            if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
-                        }
-                    }
-                }
-            }
+                else { gdst[3 * j] = x; gdst[3 * j + 1] = y; gdst[3 * j + 2] = z; }   // double: pixel by pixel (registers)
+            });
             if constexpr (sizeof(OutT) == 4) store_records4(gdst, o);
             u0 += r_grp; v0 += q_grp;
             if (u0 >= W) { u0 -= W; ++v0; }
@@ -315,17 +319,12 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_vec(const K1Args
         if (tid == 0) {
             bulk_store(gout + t * (unsigned long long)kTile * 3, out_s + (size_t)ob * kTile * 3, kOutBytes);
             bulk_commit();
-            const unsigned long long tn = t + kStages * tstep;
+            const unsigned long long tn = t + kStages;
             if (tn < t1) {   // every thread is past its reads of this stage (barrier above): refill it
                 mbar_arrive_expect_tx(&full[stage], kInBytes);
                 bulk_load(in_s + (size_t)stage * kTile, gin + tn * kTile, kInBytes, &full[stage]);
             }
         }
-#if K1V_INTERLEAVE
-        u0 += skip_u; v0 += skip_v; f0 += skip_f;
-        if (u0 >= W) { u0 -= W; ++v0; }
-        if (v0 >= H) { v0 -= H; ++f0; }
-#endif
         if (++stage == kStages) { stage = 0; parity ^= 1u; }
         if (++ob == kOutBufs) ob = 0;
     }
@@ -515,138 +514,184 @@ __global__ void __launch_bounds__(K1_THREADS) k1_count_tiles(const K1Args a) {
     }
 }
 
-// pass 2: k1_bulk with in-tile compaction.  The tile's records are packed in shared memory in pixel order (warp
-// ballots + a 32-entry scan over the (row-of-256, warp) counts) at the same 16-byte phase as their destination, the
-// 16-byte aligned middle leaves through one cp.async.bulk store, the (<= 3 float) head and tail through scalar stores.
-template <typename DepthT, typename OutT, bool kWorld, int kMode>
-__global__ void __launch_bounds__(K1_THREADS, 3) k1_bulk_compact(const K1Args a) {
-    constexpr int kOutBufs = 2;
+// 12 consecutive floats of one lane to an address that is S (1..3) words past a 16-byte boundary, when the lanes of the
+// warp hold consecutive 12-word blocks: every 16-byte group that straddles two lanes is assembled with one shuffle per
+// word and written by the lower lane; lane 0 writes its first 4 - S words and lane 31 its last S words as scalars.
+template <int S>
+__device__ __forceinline__ void store_records4_shifted(float* dst, const float (&o)[12], unsigned lane) {
+    float nb[4 - S];
+#pragma unroll
+    for (int k = 0; k < 4 - S; ++k) nb[k] = __shfl_down_sync(0xffffffffu, o[k], 1);
+    float4* g = reinterpret_cast<float4*>(dst - S);
+    g[1] = make_float4(o[4 - S], o[5 - S], o[6 - S], o[7 - S]);
+    g[2] = make_float4(o[8 - S], o[9 - S], o[10 - S], o[11 - S]);
+    if (lane != 31u) {
+        float w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = k < S ? o[12 - S + k] : nb[k - S < 0 ? 0 : k - S];
+        g[3] = make_float4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < S; ++k) dst[12 - S + k] = o[12 - S + k];
+    }
+    if (lane == 0u) {
+#pragma unroll
+        for (int k = 0; k < 4 - S; ++k) dst[k] = o[k];
+    }
+}
+
+// pass 2: k1_bulk_vec with in-tile compaction.  A tile is kGroups of the 1024-pixel tiles pass 1 counted, so the
+// output offset of the tile comes from the scan of those counts.  Phase A: every thread decodes the validity of its 4
+// consecutive pixels of each group, a warp scan + a 32-entry scan over the (group, warp) totals give every thread the
+// position of its first record.  Phase B: the records are computed as in k1_bulk_vec and packed in shared memory in
+// pixel order at the 16-byte phase of their destination; a warp whose 128 pixels are all valid (the common case) writes
+// its 384 words with 16-byte stores whatever their alignment (store_records4_shifted), other warps store word by word.
+// The 16-byte aligned middle of the tile leaves through one cp.async.bulk store, the (<= 3 float) head and tail
+// through scalar stores.
+template <typename DepthT, typename OutT, bool kWorld, int kMode, int kGroups>
+__global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_compact(const K1Args a) {
+    constexpr int kStages = K1V_STAGES, kOutBufs = 2;
+    constexpr int kTile = K1V_GROUP * kGroups;
     constexpr int kPerWord = 16 / (int)sizeof(OutT);                    // output elements per 16 bytes
+    static_assert(kGroups * (K1_THREADS / 32) <= 32, "one warp scans the (group, warp) totals");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-    unsigned* part = reinterpret_cast<unsigned*>(smem + 64);             // [K1_PPT][8] warp counts
-    double* col = reinterpret_cast<double*>(smem + 256);
-    double* row = col + a.W;
-    size_t off = 256 + ((size_t)(a.W + a.H) * 8 + 127) / 128 * 128;
+    unsigned* part = reinterpret_cast<unsigned*>(smem + 64);            // [kGroups][8] valid pixels per (group, warp)
+    double *col, *row;
+    size_t off = k1v_tables(a, smem, 256, col, row);
     DepthT* in_s = reinterpret_cast<DepthT*>(smem + off);
-    off += (size_t)K1_STAGES * K1_TILE * sizeof(DepthT);
-    OutT* out_s = reinterpret_cast<OutT*>(smem + off);                   // kOutBufs x (K1_TILE * 3 + kPerWord)
-    constexpr size_t kOutStride = (size_t)K1_TILE * 3 + kPerWord;
+    off += (size_t)kStages * kTile * sizeof(DepthT);
+    OutT* out_s = reinterpret_cast<OutT*>(smem + off);                  // kOutBufs x (kTile * 3 + kPerWord)
+    constexpr size_t kOutStride = (size_t)kTile * 3 + kPerWord;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    constexpr uint32_t kInBytes = K1_TILE * sizeof(DepthT);
+    constexpr uint32_t kInBytes = kTile * sizeof(DepthT);
     const unsigned long long per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
     const unsigned long long t0 = (unsigned long long)blockIdx.x * per;
     unsigned long long t1 = t0 + per;
     if (t1 > a.n_tiles) t1 = a.n_tiles;
     if (tid == 0) {
-        for (int s = 0; s < K1_STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
         fence_mbar_init();
     }
+    if (tid < 32) part[tid] = 0;
     k1_tables(a, col, row);
     __syncthreads();
     if (t0 >= t1) return;
     const DepthT* gin = reinterpret_cast<const DepthT*>(a.depth);
     OutT* gout = reinterpret_cast<OutT*>(a.out);
     if (tid == 0) {
-        for (int s = 0; s < K1_STAGES; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             if (t0 + s < t1) {
                 mbar_arrive_expect_tx(&full[s], kInBytes);
-                bulk_load(in_s + (size_t)s * K1_TILE, gin + (t0 + s) * K1_TILE, kInBytes, &full[s]);
+                bulk_load(in_s + (size_t)s * kTile, gin + (t0 + s) * kTile, kInBytes, &full[s]);
             }
         }
     }
-    const unsigned long long px0 = t0 * K1_TILE + tid;
+    const unsigned long long px0 = t0 * kTile + tid * 4u;
     unsigned f0 = (unsigned)(px0 / a.WH);
     const unsigned r0 = (unsigned)(px0 - (unsigned long long)f0 * a.WH);
     unsigned v0 = r0 / a.W, u0 = r0 - v0 * a.W;
     const unsigned W = a.W, H = a.H;
-    const unsigned q_tile = K1_TILE / W, r_tile = K1_TILE - q_tile * W;
+    const unsigned q_grp = K1V_GROUP / W, r_grp = K1V_GROUP - q_grp * W;
     unsigned pose_frame = 0xffffffffu;
     Pose pose;
     unsigned stage = 0, parity = 0, ob = 0;
     for (unsigned long long t = t0; t < t1; ++t) {
         mbar_wait(&full[stage], parity);
-        const DepthT* tin = in_s + (size_t)stage * K1_TILE + tid;
-        unsigned u = u0, v = v0, f = f0;
-        if (kWorld && f0 != pose_frame) { pose_frame = f0; pose_load(a.rt + (size_t)f0 * 12, pose); }
-        OutT rx[K1_PPT], ry[K1_PPT], rz[K1_PPT];
-        unsigned rank[K1_PPT];
-        bool ok[K1_PPT], last_of_frame[K1_PPT];
-        unsigned fr[K1_PPT];
+        const DepthT* tin = in_s + (size_t)stage * kTile + tid * 4u;
+        // ---- phase A: validity nibble and warp-exclusive record count of this thread, per group (16 bits each)
+        unsigned long long meta = 0;
 #pragma unroll
-        for (int j = 0; j < K1_PPT; ++j) {
-            bool valid;
-            const double raw = raw_to_double(tin[j * K1_THREADS]);
-            const double Z = decode_z(raw, kMode, a.depth_scale, a.fB, valid);
-            const double X = dmul(col[u], Z), Y = dmul(row[v], Z);
-            if (kWorld) {
-                double wx, wy, wz;
-                pose_apply(pose, X, Y, Z, wx, wy, wz);
-                rx[j] = out_cast<OutT>(wx); ry[j] = out_cast<OutT>(wy); rz[j] = out_cast<OutT>(wz);
-            } else {
-                rx[j] = out_cast<OutT>(X); ry[j] = out_cast<OutT>(Y); rz[j] = out_cast<OutT>(Z);
+        for (int g = 0; g < kGroups; ++g) {
+            DepthT raw[4];
+            load_samples4(tin + g * K1V_GROUP, raw);
+            unsigned m = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bool valid;
+                decode_z(raw_to_double(raw[j]), kMode, a.depth_scale, a.fB, valid);
+                m |= valid ? (1u << j) : 0u;
             }
-            ok[j] = valid;
-            fr[j] = f;
-            last_of_frame[j] = (u == W - 1) & (v == H - 1);
-            const unsigned b = __ballot_sync(0xffffffffu, valid);
-            rank[j] = __popc(b & ((1u << lane) - 1u));
-            if (lane == 0) part[j * 8 + warp] = __popc(b);
-            u += K1_THREADS;
-            if (u >= W) {
-                u -= W;
-                if (++v == H) {
-                    v = 0;
-                    ++f;
-                    if (kWorld && ++pose_frame < a.n_frames) pose_load(a.rt + (size_t)pose_frame * 12, pose);
-                }
-            }
+            const unsigned c = __popc(m);
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
+            if (lane == 31u) part[g * 8 + warp] = incl;
+            meta |= (unsigned long long)(m | ((incl - c) << 4)) << (16 * g);
         }
         // the bulk store issued from the buffer we are about to fill must have finished reading it
         if (tid == 0) bulk_wait_read<kOutBufs - 2>();
         __syncthreads();                                                // part[] complete, buffer free
-        // exclusive scan of the 32 (j, warp) counts, redundantly in every warp
+        // exclusive scan of the (group, warp) totals, redundantly in every warp
         unsigned c = part[lane], incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
         const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
         const unsigned excl = incl - c;
-        const unsigned long long base = a.tile_offsets[t];              // records before this tile
+        const unsigned long long base = a.tile_offsets[t * kGroups];    // records before this tile
         const unsigned skew = (unsigned)((base * 3ull) % (unsigned)kPerWord);
-        OutT* buf = out_s + (size_t)ob * kOutStride;
+        OutT* buf = out_s + (size_t)ob * kOutStride + skew;
+        // ---- phase B: records, packed
+#pragma unroll 1
+        for (int g = 0; g < kGroups; ++g) {
+            const unsigned mg = (unsigned)(meta >> (16 * g)) & 0xffffu;
+            const unsigned m = mg & 15u;
+            const unsigned pos0 = __shfl_sync(0xffffffffu, excl, g * 8 + (int)warp) + (mg >> 4);   // first record of this thread
+            DepthT raw[4];
+            load_samples4(tin + g * K1V_GROUP, raw);
+            OutT* const dst = buf + pos0 * 3u;
+            OutT o[sizeof(OutT) == 4 ? 12 : 3];
+            unsigned rank = 0;
+            const int last = k1_group4<DepthT, OutT, kWorld, kMode>(a, col, row, raw, u0, v0, f0, pose_frame, pose, [&](int j, OutT x, OutT y, OutT z) {
+                if constexpr (sizeof(OutT) == 4) { o[3 * j] = x; o[3 * j + 1] = y; o[3 * j + 2] = z; }
+                else {                                                  // double: word by word
+                    if ((m >> j) & 1u) { dst[3 * rank] = x; dst[3 * rank + 1] = y; dst[3 * rank + 2] = z; ++rank; }
+                }
+            });
+            if constexpr (sizeof(OutT) == 4) {
+                if (__all_sync(0xffffffffu, m == 15u)) {
+                    // the warp's 384 words are consecutive: 16-byte stores at any alignment
+                    switch ((unsigned)((uintptr_t)dst >> 2) & 3u) {
+                        case 0: store_records4(dst, o); break;
+                        case 1: store_records4_shifted<1>(dst, o, lane); break;
+                        case 2: store_records4_shifted<2>(dst, o, lane); break;
+                        default: store_records4_shifted<3>(dst, o, lane); break;
+                    }
+                } else {
 #pragma unroll
-        for (int j = 0; j < K1_PPT; ++j) {
-            const unsigned before = __shfl_sync(0xffffffffu, excl, j * 8 + (int)warp);
-            const unsigned pos = before + rank[j];
-            if (ok[j]) { OutT* o = buf + skew + pos * 3u; o[0] = rx[j]; o[1] = ry[j]; o[2] = rz[j]; }
-            if (last_of_frame[j]) a.frame_ends[fr[j]] = base + pos + (ok[j] ? 1u : 0u);
+                    for (int j = 0; j < 4; ++j)
+                        if ((m >> j) & 1u) { dst[3 * rank] = o[3 * j]; dst[3 * rank + 1] = o[3 * j + 1]; dst[3 * rank + 2] = o[3 * j + 2]; ++rank; }
+                }
+            }
+            if (last >= 0) a.frame_ends[f0] = base + pos0 + __popc(m & ((2u << last) - 1u));
+            u0 += r_grp; v0 += q_grp;
+            if (u0 >= W) { u0 -= W; ++v0; }
+            if (v0 >= H) { v0 -= H; ++f0; }
         }
         fence_proxy_async_smem();
         __syncthreads();                                                // records packed
         // split [skew, skew + 3 total) into head | 16-byte aligned middle | tail (element indices in the staging buffer)
+        OutT* const buf0 = buf - skew;
         const unsigned first = skew, end = skew + total * 3u;
         unsigned mid0 = (first + kPerWord - 1) / kPerWord * kPerWord, mid1 = end / kPerWord * kPerWord;
         if (mid1 < mid0) { mid0 = end; mid1 = end; }
         OutT* gdst = gout + base * 3ull - skew;                         // 16-byte aligned
         if (tid == 0) {
-            if (mid1 > mid0) bulk_store(gdst + mid0, buf + mid0, (mid1 - mid0) * (unsigned)sizeof(OutT));
+            if (mid1 > mid0) bulk_store(gdst + mid0, buf0 + mid0, (mid1 - mid0) * (unsigned)sizeof(OutT));
             bulk_commit();
-            const unsigned long long tn = t + K1_STAGES;
+            const unsigned long long tn = t + kStages;
             if (tn < t1) {
                 mbar_arrive_expect_tx(&full[stage], kInBytes);
-                bulk_load(in_s + (size_t)stage * K1_TILE, gin + tn * K1_TILE, kInBytes, &full[stage]);
+                bulk_load(in_s + (size_t)stage * kTile, gin + tn * kTile, kInBytes, &full[stage]);
             }
         }
         if (tid >= 32 && tid < 32 + (unsigned)kPerWord) {               // head and tail: a few scalar stores by warp 1
             const unsigned k = tid - 32;
-            if (first + k < mid0 && first + k < end) gdst[first + k] = buf[first + k];
-            if (mid1 + k < end && mid1 >= mid0 && mid1 + k >= mid0) gdst[mid1 + k] = buf[mid1 + k];
+            if (first + k < mid0 && first + k < end) gdst[first + k] = buf0[first + k];
+            if (mid1 + k < end && mid1 >= mid0 && mid1 + k >= mid0) gdst[mid1 + k] = buf0[mid1 + k];
         }
-        u0 += r_tile; v0 += q_tile;
-        if (u0 >= W) { u0 -= W; ++v0; }
-        if (v0 >= H) { v0 -= H; ++f0; }
-        if (++stage == K1_STAGES) { stage = 0; parity ^= 1u; }
+        if (++stage == kStages) { stage = 0; parity ^= 1u; }
         if (++ob == kOutBufs) ob = 0;
     }
     if (tid == 0) bulk_wait_all<0>();
@@ -723,19 +768,31 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
         R3D_CUDA_OK(ctx, cub::DeviceScan::ExclusiveSum(ctx->scratch[SCR_CUBTMP], tmp_bytes, counts, offsets, (int)n_tiles, st));
         ctx->launches++;
         if (fast) {
-            const size_t smem = 256 + table_bytes + (size_t)K1_STAGES * K1_TILE * sizeof(DepthT) + 2 * ((size_t)K1_TILE * 3 + 16 / sizeof(OutT)) * sizeof(OutT);
-            auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk_compact<DepthT, OutT, kWorld, 0> : k1_bulk_compact<DepthT, OutT, kWorld, 1>;
-            R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int per_sm = 0;
-            R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem));
-            if (per_sm < 1) return set_error(ctx, R3D_ERR_UNSUPPORTED, "image %ux%u needs %zu B of shared memory per CTA", a.W, a.H, smem);
-            unsigned long long g2 = (unsigned long long)ctx->sm_count * per_sm;
-            if (g2 > a.n_tiles) g2 = a.n_tiles;
-            kern<<<(unsigned)g2, K1_THREADS, smem, st>>>(a);
-            ctx->launches++;
-            if (a.n_tiles < n_tiles) {
+            constexpr int kGroups = sizeof(OutT) == 4 ? K1V_GROUPS : 1;
+            const unsigned long long n_full = a.n_tiles;                 // full 1024-pixel tiles (counted by pass 1)
+            const unsigned long long n_super = n_full / kGroups;
+            if (n_super) {
+                K1Args m = a;
+                m.n_tiles = n_super;
+                const size_t tables_v = ((size_t)(a.W + 1 + a.H) * 8 + 127) / 128 * 128;
+                const size_t smem = 256 + tables_v + (size_t)K1V_STAGES * K1V_GROUP * kGroups * sizeof(DepthT) +
+                                    2 * ((size_t)K1V_GROUP * kGroups * 3 + 16 / sizeof(OutT)) * sizeof(OutT);
+                auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk_compact<DepthT, OutT, kWorld, 0, kGroups> : k1_bulk_compact<DepthT, OutT, kWorld, 1, kGroups>;
+                R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                R3D_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, smem));
+                if (per_sm < 1) return set_error(ctx, R3D_ERR_UNSUPPORTED, "image %ux%u needs %zu B of shared memory per CTA", a.W, a.H, smem);
+                unsigned long long g2 = (unsigned long long)ctx->sm_count * per_sm;
+                if (g2 > n_super) g2 = n_super;
+                kern<<<(unsigned)g2, K1_THREADS, smem, st>>>(m);
+                ctx->launches++;
+            }
+            if (n_super * kGroups < n_tiles) {
+                // the 1024-pixel tiles after the last whole bulk tile, and the partial last one
+                K1Args tail = a;
+                tail.n_tiles = n_super * kGroups;
                 R3D_CUDA_OK(ctx, cudaFuncSetAttribute(k1_compact<DepthT, OutT, kWorld>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table_bytes));
-                k1_compact<DepthT, OutT, kWorld><<<1, K1_THREADS, table_bytes, st>>>(a);
+                k1_compact<DepthT, OutT, kWorld><<<1, K1_THREADS, table_bytes, st>>>(tail);
                 ctx->launches++;
             }
             k1_frame_counts<<<(a.n_frames + 255) / 256, 256, 0, st>>>(a.frame_ends, a.n_frames, a.frame_counts);
@@ -755,7 +812,7 @@ static int launch_k1_typed(r3d_ctx* ctx, cudaStream_t st, K1Args a, bool bulk_ok
     if (bulk_ok && total >= (unsigned long long)kTileV) {
         a.n_tiles = total / kTileV;
         const size_t tables_v = ((size_t)(a.W + 1 + a.H) * 8 + 127) / 128 * 128;
-        const size_t smem = 128 + tables_v + (size_t)K1V_STAGES * kTileV * sizeof(DepthT) + (size_t)K1V_OUTBUFS * kTileV * 3 * sizeof(OutT);
+        const size_t smem = 128 + tables_v + (size_t)K1V_STAGES * kTileV * sizeof(DepthT) + (size_t)2 * kTileV * 3 * sizeof(OutT);
         auto kern = a.mode == R3D_MODE_DEPTH ? k1_bulk_vec<DepthT, OutT, kWorld, 0, kGroups> : k1_bulk_vec<DepthT, OutT, kWorld, 1, kGroups>;
         R3D_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -880,13 +937,16 @@ extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, in
             d_rt = (const double*)ctx->scratch[SCR_POSE];
         }
     }
-    // per-frame counters (compaction) live in device scratch slot 1 after the pose table
+    // per-frame counters (compaction): written straight into the caller's array when that is device memory
     unsigned long long* d_counts = nullptr;
     cudaError_t ce;
     if (compact) {
-        ce = cudaMalloc((void**)&d_counts, (size_t)n_frames * 8);
-        if (ce != cudaSuccess) return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(frame counts) failed: %s", cudaGetErrorString(ce));
-        cudaMemsetAsync(d_counts, 0, (size_t)n_frames * 8, ctx->stream);
+        if (counts_dev) d_counts = (unsigned long long*)out_counts;
+        else {
+            R3D_TRY(scratch_reserve(ctx, SCR_MISC, (size_t)n_frames * 8 + 64));
+            d_counts = (unsigned long long*)ctx->scratch[SCR_MISC];
+        }
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(d_counts, 0, (size_t)n_frames * 8, ctx->stream));
     }
     int rc = R3D_OK;
     if (depth_dev && out_dev) {
@@ -899,12 +959,12 @@ extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, in
         void *d_in = nullptr, *d_out = nullptr;
         if (!depth_dev) {
             ce = cudaMalloc(&d_in, frame_in * n_frames);
-            if (ce != cudaSuccess) { cudaFree(d_counts); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(depth staging) failed: %s", cudaGetErrorString(ce)); }
+            if (ce != cudaSuccess) return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(depth staging) failed: %s", cudaGetErrorString(ce));
             cudaMemcpyAsync(d_in, depth, frame_in * n_frames, cudaMemcpyHostToDevice, ctx->stream);
         }
         if (!out_dev) {
             ce = cudaMalloc(&d_out, frame_out * n_frames);
-            if (ce != cudaSuccess) { cudaFree(d_in); cudaFree(d_counts); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(xyz staging) failed: %s", cudaGetErrorString(ce)); }
+            if (ce != cudaSuccess) { cudaFree(d_in); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(xyz staging) failed: %s", cudaGetErrorString(ce)); }
         }
         rc = launch_k1(ctx, ctx->stream, depth_dev ? depth : d_in, dtype, W, H, pitch, n_frames, intr, d_rt, mode, depth_scale,
                        fB, compact, out_dtype, out_dev ? out_xyz : d_out, d_counts);
@@ -921,36 +981,50 @@ extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, in
         cudaStreamSynchronize(ctx->stream);
         cudaFree(d_in); cudaFree(d_out);
     } else {
-        // host-side buffers: chunked H2D -> kernel -> D2H pipeline on two streams with two device slots
-        size_t per_frame = (depth_dev ? 0 : frame_in) + (out_dev ? 0 : frame_out);
-        int chunk = (int)((size_t)(192u << 20) / (per_frame ? per_frame : 1));
+        // host-side buffers: a ring of device slots; uploads, kernels and read-backs run on three streams chained by
+        // events, so the read-back engine (the bound: 12 of the 14 bytes per pixel) never waits for an upload
+        const size_t per_frame = (depth_dev ? 0 : frame_in) + (out_dev ? 0 : frame_out);
+        int chunk = (int)(ctx->stage_chunk_bytes / (per_frame ? per_frame : 1));
         if (chunk < 1) chunk = 1;
         if (chunk > n_frames) chunk = n_frames;
-        for (int s = 0; s < 2 && rc == R3D_OK; ++s) {
-            if (!depth_dev) rc = scratch_reserve(ctx, SCR_IN0 + s, frame_in * chunk);
-            if (rc == R3D_OK && !out_dev) rc = scratch_reserve(ctx, SCR_OUT0 + s, frame_out * chunk);
-        }
+        int slots = ctx->stage_slots;
+        if ((long long)slots * chunk > (long long)n_frames + chunk - 1) slots = (n_frames + chunk - 1) / chunk;
+        if (!depth_dev) rc = scratch_reserve(ctx, SCR_IN0, frame_in * chunk * slots);
+        if (rc == R3D_OK && !out_dev) rc = scratch_reserve(ctx, SCR_OUT0, frame_out * chunk * slots);
+        cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
         for (int f0 = 0, c = 0; f0 < n_frames && rc == R3D_OK; f0 += chunk, ++c) {
-            const int s = c & 1;
+            const int s = c % slots;
             const int nf = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
-            cudaStream_t st = ctx->copy_stream[s];
-            const void* din = depth_dev ? (const void*)((const char*)depth + (size_t)f0 * frame_in) : ctx->scratch[SCR_IN0 + s];
-            void* dout = out_dev ? (void*)((char*)out_xyz + (size_t)f0 * frame_out) : ctx->scratch[SCR_OUT0 + s];
-            if (!depth_dev)
-                cudaMemcpyAsync(ctx->scratch[SCR_IN0 + s], (const char*)depth + (size_t)f0 * frame_in, frame_in * nf, cudaMemcpyHostToDevice, st);
-            rc = launch_k1(ctx, st, din, dtype, W, H, pitch, nf, intr, d_rt ? d_rt + (size_t)f0 * 12 : nullptr, mode, depth_scale,
+            const void* din = depth_dev ? (const void*)((const char*)depth + (size_t)f0 * frame_in)
+                                        : (const void*)((const char*)ctx->scratch[SCR_IN0] + (size_t)s * frame_in * chunk);
+            void* dout = out_dev ? (void*)((char*)out_xyz + (size_t)f0 * frame_out) : (void*)((char*)ctx->scratch[SCR_OUT0] + (size_t)s * frame_out * chunk);
+            if (!depth_dev) {
+                if (c >= slots) cudaStreamWaitEvent(s_in, ctx->ev_k[s], 0);      // the kernel that read this slot is done
+                cudaMemcpyAsync((void*)din, (const char*)depth + (size_t)f0 * frame_in, frame_in * nf, cudaMemcpyHostToDevice, s_in);
+                cudaEventRecord(ctx->ev_in[s], s_in);
+                cudaStreamWaitEvent(s_k, ctx->ev_in[s], 0);
+            }
+            if (!out_dev && c >= slots) cudaStreamWaitEvent(s_k, ctx->ev_out[s], 0);   // the slot's records have been read back
+            rc = launch_k1(ctx, s_k, din, dtype, W, H, pitch, nf, intr, d_rt ? d_rt + (size_t)f0 * 12 : nullptr, mode, depth_scale,
                            fB, 0, out_dtype, dout, nullptr);
-            if (rc == R3D_OK && !out_dev)
-                cudaMemcpyAsync((char*)out_xyz + (size_t)f0 * frame_out, dout, frame_out * nf, cudaMemcpyDeviceToHost, st);
+            cudaEventRecord(ctx->ev_k[s], s_k);
+            if (rc == R3D_OK && !out_dev) {
+                cudaStreamWaitEvent(s_out, ctx->ev_k[s], 0);
+                cudaMemcpyAsync((char*)out_xyz + (size_t)f0 * frame_out, dout, frame_out * nf, cudaMemcpyDeviceToHost, s_out);
+                cudaEventRecord(ctx->ev_out[s], s_out);
+            }
         }
-        cudaStreamSynchronize(ctx->copy_stream[0]);
-        cudaStreamSynchronize(ctx->copy_stream[1]);
+        cudaStreamSynchronize(s_in);
+        cudaStreamSynchronize(s_k);
+        cudaStreamSynchronize(s_out);
     }
-    if (rc != R3D_OK) { cudaFree(d_counts); return rc; }
+    if (rc != R3D_OK) return rc;
     if (out_counts) {
         if (compact) {
-            cudaMemcpyAsync(out_counts, d_counts, (size_t)n_frames * 8, counts_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
+            if (!counts_dev) {
+                cudaMemcpyAsync(out_counts, d_counts, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, ctx->stream);
+                cudaStreamSynchronize(ctx->stream);
+            }
         } else if (!counts_dev) {
             for (int i = 0; i < n_frames; ++i) out_counts[i] = (uint64_t)W * H;
         } else {
@@ -960,7 +1034,6 @@ extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, in
             free(h);
         }
     }
-    if (d_counts) { cudaStreamSynchronize(ctx->stream); cudaFree(d_counts); }
     rc = finish(ctx);
     if (rc == R3D_OK && depth_dev && out_dev && ctx->blocking) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
     return rc;

@@ -16,7 +16,11 @@ struct r3d_ctx {
     cudaStream_t stream = nullptr;   // every kernel of this context
     cudaStream_t copy_stream[2] = {nullptr, nullptr};  // host-pointer staging pipeline
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-    cudaEvent_t stage_done[2] = {nullptr, nullptr};
+    // staging ring of r3d_backproject_rt with host buffers: per slot "input uploaded", "kernel done", "output read back"
+    static constexpr int kMaxStageSlots = 4;
+    cudaEvent_t ev_in[kMaxStageSlots] = {}, ev_k[kMaxStageSlots] = {}, ev_out[kMaxStageSlots] = {};
+    int stage_slots = 3;             // R3D_STAGE_SLOTS
+    size_t stage_chunk_bytes = 192u << 20;   // R3D_STAGE_CHUNK_MB: host bytes (in + out) per chunk
     float last_kernel_ms = 0.f;
     uint64_t launches = 0;
     char err[1024] = {0};

@@ -95,8 +95,20 @@ extern "C" r3d_ctx* r3d_create(int device) {
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int s = 0; s < 2 && ok; ++s) {
-        ok = cudaStreamCreateWithFlags(&ctx->copy_stream[s], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->stage_done[s], cudaEventDisableTiming) == cudaSuccess;
+        ok = cudaStreamCreateWithFlags(&ctx->copy_stream[s], cudaStreamNonBlocking) == cudaSuccess;
+    }
+    for (int s = 0; s < r3d_ctx::kMaxStageSlots && ok; ++s) {
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_k[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (const char* v = getenv("R3D_STAGE_SLOTS")) {
+        const int n = atoi(v);
+        if (n >= 1 && n <= r3d_ctx::kMaxStageSlots) ctx->stage_slots = n;
+    }
+    if (const char* v = getenv("R3D_STAGE_CHUNK_MB")) {
+        const long mb = atol(v);
+        if (mb >= 1 && mb <= 8192) ctx->stage_chunk_bytes = (size_t)mb << 20;
     }
     ok = ok && cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
     if (const char* gb = getenv("R3D_SCAN_SCRATCH_GB")) {
@@ -123,9 +135,12 @@ extern "C" void r3d_destroy(r3d_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-    for (int s = 0; s < 2; ++s) {
-        if (ctx->stage_done[s]) cudaEventDestroy(ctx->stage_done[s]);
+    for (int s = 0; s < 2; ++s)
         if (ctx->copy_stream[s]) cudaStreamDestroy(ctx->copy_stream[s]);
+    for (int s = 0; s < r3d_ctx::kMaxStageSlots; ++s) {
+        if (ctx->ev_in[s]) cudaEventDestroy(ctx->ev_in[s]);
+        if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
+        if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -117,6 +117,23 @@ def test_disparity_mode(ctx):
     assert np.array_equal(got64, world_ref)
 
 
+@pytest.mark.parametrize("holes", [0, 1, 2, 3, 5])
+def test_compaction_all_valid_warps_every_alignment(ctx, holes):
+    """Warps whose 128 pixels are all valid write their records with 16-byte stores at whatever alignment the records
+    before them leave: `holes` invalid pixels at the start shift everything after them by 3 * holes words."""
+    rng = np.random.default_rng(300 + holes)
+    n, H, W = 3, 40, 1026
+    depths = rng.integers(1, 65535, size=(n, H, W)).astype(np.uint16)
+    depths[0, 0, :holes] = 0
+    depths[1, 20, 500] = 0                                 # one more shift in the middle of the batch
+    rt = random_rt(n, rng)
+    _, world_ref = oracle_batch(depths, po.KITTI_INTRINSICS, rt, 0, 1.0 / 256.0)
+    mask = np.concatenate([po.valid_mask(depths[k], 0, 1.0 / 256.0).ravel() for k in range(n)])
+    got, counts = ctx.backproject(depths, po.KITTI_INTRINSICS, rt=rt, depth_scale=1.0 / 256.0, compact=True)
+    assert counts.tolist() == [H * W - holes, H * W - 1, H * W]
+    assert np.array_equal(got, world_ref[mask].astype(np.float32))
+
+
 def test_compaction_keeps_order_and_counts(ctx):
     rng = np.random.default_rng(5)
     shape = (4, 375, 1242)
