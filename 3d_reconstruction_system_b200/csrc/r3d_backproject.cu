@@ -30,6 +30,7 @@ struct K1Args {
     unsigned long long pitch;      // bytes per row
     double fx, fy, cx, cy, depth_scale, fB;
     int mode;
+    int valid_fast;                // validity is "sample > 0 (and finite)": depth_scale cannot under- or overflow a sample
     // compaction
     const unsigned long long* tile_offsets;  // exclusive scan of valid counts per tile
     unsigned long long* tile_counts;
@@ -88,6 +89,19 @@ __device__ __forceinline__ void bulk_wait_all() {
 // ------------------------------------------------------------------ per-pixel arithmetic
 template <typename DepthT>
 __device__ __forceinline__ double raw_to_double(DepthT v) { return (double)v; }
+
+// Validity of a sample (decode_z's rule: d = raw * depth_scale, d > 0 and finite).  With depth_scale in [1e-250, 1e250]
+// no sample of these types can under- or overflow the product, and the rule is a compare on the sample itself.
+template <typename DepthT>
+__device__ __forceinline__ bool sample_valid(const K1Args& a, DepthT raw, int mode) {
+    if (a.valid_fast) {
+        if constexpr (sizeof(DepthT) == 4) return raw > 0.0f && raw <= 3.402823466e+38f;
+        else return raw != 0;
+    }
+    bool valid;
+    decode_z(raw_to_double(raw), mode, a.depth_scale, a.fB, valid);
+    return valid;
+}
 
 template <typename OutT>
 __device__ __forceinline__ OutT out_cast(double v);
@@ -484,33 +498,28 @@ __global__ void __launch_bounds__(K1_THREADS) k1_compact(const K1Args a) {
 }
 
 // ------------------------------------------------------------------ fast compaction (bulk-eligible input)
-// pass 1: valid pixels per full 1024-pixel tile; one 8-byte (u16) / 4-byte (u8) / 16-byte (f32) load per thread
+// pass 1: valid pixels per full 1024-pixel tile.  One warp per tile, 16-byte loads, no block-level reduction.
 template <typename DepthT>
 __global__ void __launch_bounds__(K1_THREADS) k1_count_tiles(const K1Args a) {
-    __shared__ unsigned warp_cnt[K1_THREADS / 32];
+    constexpr int kPer = 16 / (int)sizeof(DepthT);                      // samples per 16-byte load
+    constexpr int kLoads = K1_TILE / (32 * kPer);                       // loads per lane per tile
     const DepthT* gin = reinterpret_cast<const DepthT*>(a.depth);
-    for (unsigned long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-        const DepthT* p = gin + t * K1_TILE + threadIdx.x * K1_PPT;
-        DepthT v[K1_PPT];
-        if (sizeof(DepthT) == 2) *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(p);
-        else if (sizeof(DepthT) == 1) *reinterpret_cast<unsigned*>(v) = *reinterpret_cast<const unsigned*>(p);
-        else *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(p);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long warps = (unsigned long long)gridDim.x * (K1_THREADS / 32);
+    for (unsigned long long t = (unsigned long long)blockIdx.x * (K1_THREADS / 32) + (threadIdx.x >> 5); t < a.n_tiles; t += warps) {
+        const uint4* p = reinterpret_cast<const uint4*>(gin + t * K1_TILE) + lane;
+        uint4 v[kLoads];
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k) v[k] = __ldcs(p + k * 32);
         unsigned mine = 0;
 #pragma unroll
-        for (int j = 0; j < K1_PPT; ++j) {
-            bool valid;
-            decode_z(raw_to_double(v[j]), a.mode, a.depth_scale, a.fB, valid);
-            mine += valid ? 1u : 0u;
+        for (int k = 0; k < kLoads; ++k) {
+            const DepthT* e = reinterpret_cast<const DepthT*>(&v[k]);
+#pragma unroll
+            for (int j = 0; j < kPer; ++j) mine += sample_valid(a, e[j], a.mode) ? 1u : 0u;
         }
-        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-        if ((threadIdx.x & 31u) == 0) warp_cnt[threadIdx.x >> 5] = mine;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned sum = 0;
-            for (int w = 0; w < K1_THREADS / 32; ++w) sum += warp_cnt[w];
-            a.tile_counts[t] = sum;
-        }
-        __syncthreads();
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0) a.tile_counts[t] = mine;
     }
 }
 
@@ -600,75 +609,102 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_compact(const K1
     for (unsigned long long t = t0; t < t1; ++t) {
         mbar_wait(&full[stage], parity);
         const DepthT* tin = in_s + (size_t)stage * kTile + tid * 4u;
-        // ---- phase A: validity nibble and warp-exclusive record count of this thread, per group (16 bits each)
-        unsigned long long meta = 0;
+        // what pass 1 counted in this tile: all-valid and all-invalid tiles skip the position bookkeeping
+        unsigned tile_valid = 0;
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) {
-            DepthT raw[4];
-            load_samples4(tin + g * K1V_GROUP, raw);
-            unsigned m = 0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                bool valid;
-                decode_z(raw_to_double(raw[j]), kMode, a.depth_scale, a.fB, valid);
-                m |= valid ? (1u << j) : 0u;
-            }
-            const unsigned c = __popc(m);
-            unsigned incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
-            if (lane == 31u) part[g * 8 + warp] = incl;
-            meta |= (unsigned long long)(m | ((incl - c) << 4)) << (16 * g);
-        }
-        // the bulk store issued from the buffer we are about to fill must have finished reading it
-        if (tid == 0) bulk_wait_read<kOutBufs - 2>();
-        __syncthreads();                                                // part[] complete, buffer free
-        // exclusive scan of the (group, warp) totals, redundantly in every warp
-        unsigned c = part[lane], incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
-        const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-        const unsigned excl = incl - c;
+        for (int g = 0; g < kGroups; ++g) tile_valid += (unsigned)a.tile_counts[t * kGroups + g];
         const unsigned long long base = a.tile_offsets[t * kGroups];    // records before this tile
         const unsigned skew = (unsigned)((base * 3ull) % (unsigned)kPerWord);
         OutT* buf = out_s + (size_t)ob * kOutStride + skew;
-        // ---- phase B: records, packed
-#pragma unroll 1
-        for (int g = 0; g < kGroups; ++g) {
-            const unsigned mg = (unsigned)(meta >> (16 * g)) & 0xffffu;
-            const unsigned m = mg & 15u;
-            const unsigned pos0 = __shfl_sync(0xffffffffu, excl, g * 8 + (int)warp) + (mg >> 4);   // first record of this thread
-            DepthT raw[4];
-            load_samples4(tin + g * K1V_GROUP, raw);
-            OutT* const dst = buf + pos0 * 3u;
-            OutT o[sizeof(OutT) == 4 ? 12 : 3];
-            unsigned rank = 0;
-            const int last = k1_group4<DepthT, OutT, kWorld, kMode>(a, col, row, raw, u0, v0, f0, pose_frame, pose, [&](int j, OutT x, OutT y, OutT z) {
-                if constexpr (sizeof(OutT) == 4) { o[3 * j] = x; o[3 * j + 1] = y; o[3 * j + 2] = z; }
-                else {                                                  // double: word by word
-                    if ((m >> j) & 1u) { dst[3 * rank] = x; dst[3 * rank + 1] = y; dst[3 * rank + 2] = z; ++rank; }
-                }
-            });
-            if constexpr (sizeof(OutT) == 4) {
-                if (__all_sync(0xffffffffu, m == 15u)) {
-                    // the warp's 384 words are consecutive: 16-byte stores at any alignment
-                    switch ((unsigned)((uintptr_t)dst >> 2) & 3u) {
-                        case 0: store_records4(dst, o); break;
-                        case 1: store_records4_shifted<1>(dst, o, lane); break;
-                        case 2: store_records4_shifted<2>(dst, o, lane); break;
-                        default: store_records4_shifted<3>(dst, o, lane); break;
-                    }
-                } else {
+        unsigned long long meta = 0;
+        unsigned excl = 0, total = tile_valid;
+        const bool mixed = tile_valid != 0u && tile_valid != (unsigned)kTile;
+        if (mixed) {
+            // ---- phase A: validity nibble and warp-exclusive record count of this thread, per group (16 bits each)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if ((m >> j) & 1u) { dst[3 * rank] = o[3 * j]; dst[3 * rank + 1] = o[3 * j + 1]; dst[3 * rank + 2] = o[3 * j + 2]; ++rank; }
-                }
+            for (int g = 0; g < kGroups; ++g) {
+                DepthT raw[4];
+                load_samples4(tin + g * K1V_GROUP, raw);
+                unsigned m = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) m |= sample_valid(a, raw[j], kMode) ? (1u << j) : 0u;
+                const unsigned c = __popc(m);
+                unsigned incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
+                if (lane == 31u) part[g * 8 + warp] = incl;
+                meta |= (unsigned long long)(m | ((incl - c) << 4)) << (16 * g);
             }
-            if (last >= 0) a.frame_ends[f0] = base + pos0 + __popc(m & ((2u << last) - 1u));
-            u0 += r_grp; v0 += q_grp;
-            if (u0 >= W) { u0 -= W; ++v0; }
-            if (v0 >= H) { v0 -= H; ++f0; }
+            __syncthreads();                                            // part[] complete
+            // exclusive scan of the (group, warp) totals, redundantly in every warp
+            const unsigned c = part[lane];
+            unsigned incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += n; }
+            excl = incl - c;
         }
+        // ---- phase B: records, packed
+        if (tile_valid != 0u) {
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                unsigned m = 15u, pos0 = (unsigned)g * K1V_GROUP + tid * 4u;   // all-valid tile: every pixel keeps its place
+                if (mixed) {
+                    const unsigned mg = (unsigned)(meta >> (16 * g)) & 0xffffu;
+                    m = mg & 15u;
+                    pos0 = __shfl_sync(0xffffffffu, excl, g * 8 + (int)warp) + (mg >> 4);   // first record of this thread
+                }
+                if (mixed && __all_sync(0xffffffffu, m == 0u)) {
+                    // 128 invalid pixels in a row (sky): no record to compute, only a frame end to report
+                    if (v0 + 1u == H && W - u0 <= 4u) a.frame_ends[f0] = base + pos0;
+                    u0 += r_grp; v0 += q_grp;
+                    if (u0 >= W) { u0 -= W; ++v0; }
+                    if (v0 >= H) { v0 -= H; ++f0; }
+                    continue;
+                }
+                DepthT raw[4];
+                load_samples4(tin + g * K1V_GROUP, raw);
+                OutT* const dst = buf + pos0 * 3u;
+                OutT o[sizeof(OutT) == 4 ? 12 : 3];
+                unsigned rank = 0;
+                const int last = k1_group4<DepthT, OutT, kWorld, kMode>(a, col, row, raw, u0, v0, f0, pose_frame, pose, [&](int j, OutT x, OutT y, OutT z) {
+                    if constexpr (sizeof(OutT) == 4) { o[3 * j] = x; o[3 * j + 1] = y; o[3 * j + 2] = z; }
+                    else {                                              // double: word by word
+                        if ((m >> j) & 1u) { dst[3 * rank] = x; dst[3 * rank + 1] = y; dst[3 * rank + 2] = z; ++rank; }
+                    }
+                });
+                if constexpr (sizeof(OutT) == 4) {
+                    if (__all_sync(0xffffffffu, m == 15u)) {
+                        // the warp's 384 words are consecutive: 16-byte stores at any alignment
+                        switch ((unsigned)((uintptr_t)dst >> 2) & 3u) {
+                            case 0: store_records4(dst, o); break;
+                            case 1: store_records4_shifted<1>(dst, o, lane); break;
+                            case 2: store_records4_shifted<2>(dst, o, lane); break;
+                            default: store_records4_shifted<3>(dst, o, lane); break;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if ((m >> j) & 1u) { dst[3 * rank] = o[3 * j]; dst[3 * rank + 1] = o[3 * j + 1]; dst[3 * rank + 2] = o[3 * j + 2]; ++rank; }
+                    }
+                }
+                if (last >= 0) a.frame_ends[f0] = base + pos0 + __popc(m & ((2u << last) - 1u));
+                u0 += r_grp; v0 += q_grp;
+                if (u0 >= W) { u0 -= W; ++v0; }
+                if (v0 >= H) { v0 -= H; ++f0; }
+            }
+        } else {
+            // no valid pixel in the tile: nothing to compute; frames that end inside it still report their record count
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+                const unsigned to_row_end = W - u0;                     // pixels from this thread's first one to the end of its row
+                if (v0 + 1u == H && to_row_end <= 4u) a.frame_ends[f0] = base;
+                u0 += r_grp; v0 += q_grp;
+                if (u0 >= W) { u0 -= W; ++v0; }
+                if (v0 >= H) { v0 -= H; ++f0; }
+            }
+        }
+        // the bulk store issued from the other buffer must have finished reading it before the next tile fills it
+        if (tid == 0) bulk_wait_read<kOutBufs - 2>();
         fence_proxy_async_smem();
         __syncthreads();                                                // records packed
         // split [skew, skew + 3 total) into head | 16-byte aligned middle | tail (element indices in the staging buffer)
@@ -860,6 +896,7 @@ static int launch_k1(r3d_ctx* ctx, cudaStream_t st, const void* d_depth, int dty
     a.pitch = pitch;
     a.fx = intr[0]; a.fy = intr[1]; a.cx = intr[2]; a.cy = intr[3];
     a.depth_scale = depth_scale; a.fB = fB; a.mode = mode;
+    a.valid_fast = (depth_scale >= 1e-250 && depth_scale <= 1e250) ? 1 : 0;
     a.frame_counts = d_frame_counts;
     const unsigned long long total = (unsigned long long)n_frames * a.WH;
     const size_t es = elem_size(dtype);

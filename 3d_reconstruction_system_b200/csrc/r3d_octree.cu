@@ -181,7 +181,7 @@ __device__ __forceinline__ bool cell_of_key(const ScanArgs& a, int kx, int ky, i
 }
 
 #ifndef K3_VARIANT
-#define K3_VARIANT 0
+#define K3_VARIANT 1
 #endif
 // Per-lane state of the dense walker.
 struct DenseLane {

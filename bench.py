@@ -320,7 +320,7 @@ def compaction_section(torch, ctx, dev, depth, rt, n=1024):
     px = n * H * W
     return {"frames": n, "ms": ms, "input_pixels_per_s": px / (ms * 1e-3), "valid_fraction": valid / px,
             "algorithmic_gbs": (px * 2 + valid * 12) / (ms * 1e-3) / 1e9,
-            "kernels": "k1_count_tiles + CUB scan + k1_bulk_compact (warp ballots, in-tile packing in shared memory, bulk stores)"}
+            "kernels": "k1_count_tiles (warp per tile) + CUB scan + k1_bulk_compact (validity nibbles + warp scan, in-tile packing in shared memory, 16-byte stores for all-valid warps, empty tiles / warps skipped, bulk stores)"}
 
 
 def png_decode_section(n_frames=64):
@@ -572,7 +572,7 @@ def run_gpu_arm(args):
                        "frames_per_gpu": n_frames, "pixels_per_step_per_gpu": px, "l2": "inputs+outputs %.1f GB per step >> 126 MB L2" % (px * 14 / 1e9),
                        "parity_sample_ok": parity_ok},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "peak_source": peak_src, "kernel": "k1_bulk<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
+                         "peak_source": peak_src, "kernel": "k1_bulk_vec<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
                          "kernel_ms": kernel_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo, "png_decode": png, "compact_mode": compaction,
         }

@@ -134,6 +134,29 @@ def test_compaction_all_valid_warps_every_alignment(ctx, holes):
     assert np.array_equal(got, world_ref[mask].astype(np.float32))
 
 
+def test_compaction_frames_ending_in_empty_tiles(ctx):
+    """Tiles without a valid pixel are skipped by the bulk compaction kernel; frames that end inside one still get
+    their counts (two empty frames in the middle, an empty one at the start)."""
+    rng = np.random.default_rng(41)
+    n, H, W = 5, 40, 1026                                  # frames end in the middle of 2048-pixel tiles
+    depths = rng.integers(1, 65535, size=(n, H, W)).astype(np.uint16)
+    depths[0] = 0
+    depths[2] = 0
+    depths[3] = 0
+    rt = random_rt(n, rng)
+    _, world_ref = oracle_batch(depths, po.KITTI_INTRINSICS, rt, 0, 1.0 / 256.0)
+    mask = np.concatenate([po.valid_mask(depths[k], 0, 1.0 / 256.0).ravel() for k in range(n)])
+    got, counts = ctx.backproject(depths, po.KITTI_INTRINSICS, rt=rt, depth_scale=1.0 / 256.0, compact=True)
+    assert counts.tolist() == [0, H * W, 0, 0, H * W]
+    assert np.array_equal(got, world_ref[mask].astype(np.float32))
+    # a scale outside the range where validity is a compare on the sample: the exact fp64 rule decides (1e-320 * raw
+    # is a positive denormal, so every non-zero sample stays valid)
+    got2, counts2 = ctx.backproject(depths[:2], po.KITTI_INTRINSICS, rt=rt[:2], depth_scale=1e-320, compact=True, out_dtype=np.float64)
+    assert counts2.tolist() == [0, H * W]
+    _, wref2 = oracle_batch(depths[:2], po.KITTI_INTRINSICS, rt[:2], 0, 1e-320)
+    assert np.array_equal(got2, wref2[mask[:2 * H * W]])
+
+
 def test_compaction_keeps_order_and_counts(ctx):
     rng = np.random.default_rng(5)
     shape = (4, 375, 1242)
