@@ -282,7 +282,8 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
         un_runs.append(e2.elapsed_time(e3))
     un_ms = float(np.median(un_runs))
     out["update_node"] = {"metric": "updateNode(point, True) points/s (the reference scripts' mode)", "value": n_un / (un_ms * 1e-3), "unit": "points/s",
-                          "points": n_un, "ms": un_ms, "ms_runs": un_runs, "voxels": un.numVoxels()}
+                          "points": n_un, "ms": un_ms, "ms_runs": un_runs, "voxels": un.numVoxels(),
+                          "note": "median of 5 passes, each into a cleared tree; the first pass also allocates the staging buffers for this batch size"}
     if with_cpu:
         w0 = world[:H * W].cpu().numpy()
         out["cpu_baseline"] = octomap_cpu_baseline(w0, origins[0], maxrange, res)
@@ -330,6 +331,59 @@ def compaction_section(torch, ctx, dev, depth, rt, n=1024):
     return {"frames": n, "ms": ms, "input_pixels_per_s": px / (ms * 1e-3), "valid_fraction": valid / px,
             "algorithmic_gbs": (px * 2 + valid * 12) / (ms * 1e-3) / 1e9,
             "kernels": "k1_count_tiles (warp per tile) + CUB scan + k1_bulk_compact (validity nibbles + warp scan, in-tile packing in shared memory, 16-byte stores for all-valid warps, empty tiles / warps skipped, bulk stores)"}
+
+
+def text_section(torch, ctx, dev, depth, rt, n=16, with_cpu=True):
+    """K6 beside K1: the ASCII the reference scripts actually write.  World points of n frames (float64,
+    device resident) -> genply's "%.4f %.4f %.4f \n" rows and the txt files' str(float64) rows, device to device.
+    Timed with CUDA events on the context stream (each call contains one 8-byte size read-back)."""
+    import ctypes as C
+    from oracle import points_oracle as po
+    n = min(n, depth.shape[0])
+    npts = n * H * W
+    pts = torch.empty((npts, 3), dtype=torch.float64, device=dev)
+    ctx.backproject(depth[:n], po.KITTI_INTRINSICS, rt=rt[:n], depth_scale=DEPTH_SCALE, out=pts, shape=(n, H, W), counts=np.zeros(n, np.uint64))
+    cap = npts * 80
+    buf = torch.empty(cap, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    p0 = pts.data_ptr()
+    need = C.c_size_t(0)
+    out = {"points": npts}
+    for name in ("ply", "txt"):
+        def call():
+            if name == "ply":
+                rc = ctx.lib.r3d_format_ply_rows(ctx.handle, p0, p0 + 8, p0 + 16, 3, npts, None, buf.data_ptr(), cap, C.byref(need))
+            else:
+                rc = ctx.lib.r3d_format_txt_rows(ctx.handle, p0, p0 + 8, p0 + 16, 3, npts, 0, buf.data_ptr(), cap, C.byref(need))
+            if rc != 0:
+                raise RuntimeError("K6 %s rows failed: rc %d" % (name, rc))
+        call()
+        ctx.synchronize()
+        ms = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            call()
+            e1.record(stream)
+            ctx.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        m = float(np.median(ms))
+        out[name] = {"ms": m, "points_per_s": npts / (m * 1e-3), "text_bytes": int(need.value), "text_gbs": need.value / (m * 1e-3) / 1e9,
+                     "algorithmic_gbs": (npts * 24 * 2 + need.value) / (m * 1e-3) / 1e9}
+        if with_cpu:
+            k = 200000                                   # the reference's own loop (camera_to_world.py:117-121 / :103), one core
+            h = pts[:k].cpu().numpy()
+            t0 = time.perf_counter()
+            if name == "ply":
+                ref = "".join("%.4f %.4f %.4f \n" % (a, b, c) for a, b, c in h).encode()
+            else:
+                ref = "".join(str(a) + "," + str(b) + "," + str(c) + "\n" for a, b, c in h).encode()
+            sec = time.perf_counter() - t0
+            got = bytes(buf[:len(ref)].cpu().numpy())
+            out[name]["cpu_baseline"] = {"value": k / sec, "unit": "points/s", "cores": 1, "kind": "reference",
+                                         "sample": "%d points through the reference's Python formatting expression" % k}
+            out[name]["parity_ok"] = bool(got == ref)
+    return out
 
 
 def png_decode_section(n_frames=64):
@@ -552,6 +606,12 @@ def run_gpu_arm(args):
     lib.r3d_host_free(h_out)
 
     compaction = compaction_section(torch, ctx, dev, depth, rt) if world == 1 else None
+    text = None
+    if world == 1:
+        try:
+            text = text_section(torch, ctx, dev, depth, rt, with_cpu=not args.no_cpu_baseline)
+        except Exception as exc:                      # a secondary figure must not take the headline line down
+            text = {"error": str(exc)[:200]}
     octo = None
     if args.octomap_scans > 0:
         del out
@@ -583,7 +643,7 @@ def run_gpu_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k1_bulk_vec<u16,f32,world>", "bytes_per_pixel": BYTES_PER_PX,
                          "kernel_ms": kernel_ms},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo, "png_decode": png, "compact_mode": compaction,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "octomap": octo, "png_decode": png, "compact_mode": compaction, "text_rows": text,
         }
         print(json.dumps(line))
     if dist is not None:
