@@ -93,7 +93,11 @@ extern "C" r3d_ctx* r3d_create(int device) {
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // the context stream gets the highest priority: the scan pipeline runs its ray casts on side streams (default,
+    // lowest priority) and the short list / emit / apply kernels of the previous scan must not queue behind them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    bool ok = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     for (int s = 0; s < 2 && ok; ++s) {
         ok = cudaStreamCreateWithFlags(&ctx->copy_stream[s], cudaStreamNonBlocking) == cudaSuccess;
     }

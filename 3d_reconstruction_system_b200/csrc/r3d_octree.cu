@@ -1012,7 +1012,13 @@ static int pipe_reserve(r3d_tree* t, uint64_t cap) {
     if (!t->pipe_counters) {
         R3D_CUDA_OK(ctx, cudaMalloc(&t->pipe_counters, 2 * CNT_COUNT * sizeof(uint32_t)));
         R3D_CUDA_OK(ctx, cudaMemsetAsync(t->pipe_counters, 0, 2 * CNT_COUNT * sizeof(uint32_t), ctx->stream));
-        for (int i = 0; i < 2; ++i) R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_done[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) {
+            R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_done[i], cudaEventDisableTiming));
+            R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->rc_done[i], cudaEventDisableTiming));
+            R3D_CUDA_OK(ctx, cudaStreamCreateWithFlags(&t->rc_stream[i], cudaStreamNonBlocking));
+        }
+        R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_start, cudaEventDisableTiming));
+        if (const char* v = getenv("R3D_PIPE_OVERLAP")) t->pipe_overlap = atoi(v) != 0;
     }
     if (t->delta_cap < cap) R3D_TRY(tree_reserve_delta(t, cap));
     if (t->delta_b_cap < t->delta_cap) {
@@ -1035,6 +1041,7 @@ static int pipe_reserve(r3d_tree* t, uint64_t cap) {
 struct PipeScan {
     ScanArgs a;
     bool timed;
+    bool overlap;    // ray cast on the slot's own stream (the scan has its own cell cube)
 };
 
 static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
@@ -1044,16 +1051,28 @@ static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
     a.counters = cnt;
     uint32_t* abort_flag = t->counters + CNT_ABORT;
     if (cast) {
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, CNT_COUNT * sizeof(uint32_t), ctx->stream));
+        cudaStream_t rs = ctx->stream;
+        if (ps.overlap) {
+            // the slot's stream starts after the batch's set-up and after the slot's previous scan has been emitted and its
+            // counters read back (that scan used the same cube, counters and mailbox)
+            rs = t->rc_stream[slot];
+            R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, t->pipe_start, 0));
+            if (t->pipe_done_valid[slot]) R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, t->pipe_done[slot], 0));
+        }
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, CNT_COUNT * sizeof(uint32_t), rs));
         if (a.n) {
             raycast_blocks(t, a.n);
             unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
             const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
             if (blocks > need) blocks = need;
-            if (ps.timed) cudaEventRecord(ctx->ev_a, ctx->stream);
-            k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, reinterpret_cast<unsigned long long*>(cnt + CNT_RAY_LO), abort_flag);
-            if (ps.timed) cudaEventRecord(ctx->ev_b, ctx->stream);
+            if (ps.timed) cudaEventRecord(ctx->ev_a, rs);
+            k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, rs>>>(a, reinterpret_cast<unsigned long long*>(cnt + CNT_RAY_LO), abort_flag);
+            if (ps.timed) cudaEventRecord(ctx->ev_b, rs);
             ctx->launches++;
+        }
+        if (ps.overlap) {
+            R3D_CUDA_OK(ctx, cudaEventRecord(t->rc_done[slot], rs));
+            R3D_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, t->rc_done[slot], 0));
         }
     } else {
         R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt + CNT_DELTA, 0, sizeof(uint32_t), ctx->stream));
@@ -1071,6 +1090,7 @@ static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
     // upper bound of it tight without a synchronising read-back
     R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)ctx->pinned + 1024 + 256 * slot + 128, t->counters + CNT_POOL_USED, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_done[slot], ctx->stream));
+    t->pipe_done_valid[slot] = true;
     return R3D_OK;
 }
 
@@ -1096,11 +1116,24 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
         scans[s].timed = s + 1 == n_scans;
         off += n_points[s];
     }
-    R3D_TRY(ctx_reserve_cells(ctx, gcells_max));
     R3D_TRY(pipe_reserve(t, t->delta_cap < (1u << 16) ? (1u << 16) : t->delta_cap));
+    // two cell cubes (one per pipeline slot) when the scratch budget allows: the next scan's ray cast then overlaps this
+    // scan's tail, list, emit and apply
+    const uint64_t cube_cells = ((uint64_t)gcells_max / 4 + 1) * 4;
+    const bool overlap = t->pipe_overlap && n_scans > 1 && 2 * cube_cells * 128ull <= ctx->cell_budget_bytes;
+    R3D_TRY(ctx_reserve_cells(ctx, overlap ? 2 * cube_cells : gcells_max));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
-    for (uint32_t s = 0; s < n_scans; ++s) { scans[s].a.cmasks = ctx->cell_masks; scans[s].a.ctouched = ctx->cell_touched; }
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        const uint64_t cube = overlap ? (uint64_t)(s & 1u) * cube_cells : 0;
+        scans[s].a.cmasks = ctx->cell_masks + cube * 32;
+        scans[s].a.ctouched = ctx->cell_touched + cube / 4;
+        scans[s].overlap = overlap;
+    }
     ctx->cells_dirty = true;
+    if (overlap) {
+        R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_start, ctx->stream));   // cubes cleared, abort flag reset, scans resident
+        t->pipe_done_valid[0] = t->pipe_done_valid[1] = false;
+    }
     R3D_TRY(pipe_enqueue(t, scans[0], 0, true));
     uint64_t prev_records = 0;      // records of the apply queued last (not yet reflected in the cursor read back below)
     for (uint32_t s = 0; s < n_scans; ++s) {
@@ -1115,8 +1148,13 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
             // records of scan s did not fit: nothing after its list kernel has run (abort flag).  Grow, clear, list again,
             // and queue scan s+1 again.
             R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            if (overlap) {   // a ray cast that started before the flag was raised may still be running
+                R3D_CUDA_OK(ctx, cudaStreamSynchronize(t->rc_stream[0]));
+                R3D_CUDA_OK(ctx, cudaStreamSynchronize(t->rc_stream[1]));
+            }
             R3D_TRY(pipe_reserve(t, (uint64_t)hc[CNT_DELTA] * 2));   // the other slot's records were applied already
             R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
+            if (overlap) R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_start, ctx->stream));   // ray casts queued from here on see the cleared flag
             R3D_TRY(pipe_enqueue(t, scans[s], slot, false));
             if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
         }
@@ -1279,7 +1317,12 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
     cudaFree(t->delta_b); cudaFree(t->pipe_counters); cudaFree(t->pipe_list);
-    for (int i = 0; i < 2; ++i) if (t->pipe_done[i]) cudaEventDestroy(t->pipe_done[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (t->rc_stream[i]) { cudaStreamSynchronize(t->rc_stream[i]); cudaStreamDestroy(t->rc_stream[i]); }
+        if (t->pipe_done[i]) cudaEventDestroy(t->pipe_done[i]);
+        if (t->rc_done[i]) cudaEventDestroy(t->rc_done[i]);
+    }
+    if (t->pipe_start) cudaEventDestroy(t->pipe_start);
     delete t;
 }
 

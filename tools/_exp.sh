@@ -1,8 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --frames 256 --steps 3 --warmup 3 --octomap-scans 0 > gpurun_out/bench_text.json 2> gpurun_out/bench_text.err; echo "bench exit $?"; tail -3 gpurun_out/bench_text.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_text.json'))
-print(json.dumps(d['text_rows'])[:1800])
+timeout 900 python -m pytest tests/test_octree_gpu.py tests/test_multigpu_gpu.py tests/test_scripts_gpu.py -m gpu -q -x 2>&1 | tail -4
+for ov in 1 0 1 0; do
+R3D_PIPE_OVERLAP=$ov timeout 600 python bench.py --frames 64 --steps 3 --warmup 3 --no-cpu-baseline --octomap-scans 32 > gpurun_out/bench_k3.json 2> gpurun_out/bench_k3.err
+python - $ov <<'PY'
+import json,sys
+d=json.load(open('gpurun_out/bench_k3.json'))['octomap']
+print('overlap',sys.argv[1],'scans/s',round(d['value']),'ms/scan runs',[round(x,3) for x in d['ms_per_scan_runs']],'kernel ms',round(d['raycast_kernel_ms_last_scan'],3))
 PY
+done
