@@ -182,3 +182,16 @@ def test_shortest_repr_rows_match_python_repr(hm):
     y[:, 2] = np.random.default_rng(1).integers(0, 65536, size=5000)
     n = hm.hm_txt_rows(y.ctypes.data, y.shape[0], 1, out)
     assert out.raw[:n].decode("ascii") == "".join("%r,%r,%d\n" % (a, b, int(c)) for a, b, c in y.tolist())
+
+
+def test_axis_as_multiplier_update_is_exact():
+    """The dense ray walker applies the chosen axis by multiplication (tMax + m * tDelta, m in {0.0, 1.0}; r3d_octree.cu,
+    K3_VARIANT 1).  That equals "tMax + tDelta on the chosen axis, untouched elsewhere" bit for bit, including upstream's
+    DBL_MAX sentinels for axes the ray does not move along."""
+    import numpy as np
+    rng = np.random.default_rng(9)
+    tm = np.concatenate([rng.uniform(0, 1e3, 4096), [np.finfo(np.float64).max, 0.0, 5e-324, 1e-310]])
+    td = np.concatenate([rng.uniform(1e-3, 1e3, 4096), [np.finfo(np.float64).max, np.finfo(np.float64).max, 5e-324, 0.1]])
+    with np.errstate(over="ignore"):
+        assert np.array_equal((tm + 1.0 * td).view(np.uint64), (tm + td).view(np.uint64))
+        assert np.array_equal((tm + 0.0 * td).view(np.uint64), tm.view(np.uint64))
