@@ -600,7 +600,7 @@ def run_gpu_arm(args):
         e2e_ok = bool(np.array_equal(np_out[k * H * W:(k + 1) * H * W], ref)) if k < e2e_frames else None
         e2e = {"value": world * e2e_frames * H * W * e_steps / wall, "unit": "points/s", "h2d_bytes_per_step": in_bytes + e2e_frames * 96,
                "d2h_bytes_per_step": out_bytes, "frames": e2e_frames, "steps": e_steps, "parity_ok": e2e_ok,
-               "path": "r3d_backproject_rt with pinned host buffers (chunked H2D -> kernel -> D2H on two streams)"}
+               "path": "r3d_backproject_rt with pinned host buffers (ring of three device slots: uploads, kernels and read-backs on three streams)"}
         del np_in, np_out
     lib.r3d_host_free(h_in)
     lib.r3d_host_free(h_out)
