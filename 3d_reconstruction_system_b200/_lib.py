@@ -69,6 +69,7 @@ SIGNATURES = {
     "r3d_tree_import_bricks": (_i32, [_vp, _vp, _u64]),
     "r3d_delta_expand_keys": (_i32, [_vp, _u64, _vp, _u64, _u64p, _vp, _u64, _u64p]),
     "r3d_tree_last_scan_stats": (_i32, [_vp, _vp]),
+    "r3d_tree_pipeline_stats": (_i32, [_vp, _vp]),
     "r3d_tree_update_inner_occupancy": (_i32, [_vp]),
     "r3d_tree_write_bt": (_i32, [_vp, C.c_char_p]),
     "r3d_tree_write_bt_mem": (_i32, [_vp, _vp, _sz, C.POINTER(_sz)]),

@@ -16,6 +16,7 @@ struct r3d_ctx {
     cudaStream_t stream = nullptr;   // every kernel of this context
     cudaStream_t copy_stream[2] = {nullptr, nullptr};  // host-pointer staging pipeline
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    cudaStream_t rc_stream[2] = {nullptr, nullptr};   // scan pipeline: one ray-cast stream per slot (created on first use)
     // staging ring of r3d_backproject_rt with host buffers: per slot "input uploaded", "kernel done", "output read back"
     static constexpr int kMaxStageSlots = 4;
     cudaEvent_t ev_in[kMaxStageSlots] = {}, ev_k[kMaxStageSlots] = {}, ev_out[kMaxStageSlots] = {};

@@ -146,6 +146,8 @@ extern "C" void r3d_destroy(r3d_ctx* ctx) {
         if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
         if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
     }
+    for (int s = 0; s < 2; ++s)
+        if (ctx->rc_stream[s]) cudaStreamDestroy(ctx->rc_stream[s]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

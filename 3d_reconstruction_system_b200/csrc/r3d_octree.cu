@@ -16,6 +16,8 @@
 //     to the store by the clamped log-odds kernel (K4).  Records are what multi-GPU runs exchange.
 #include <vector>
 
+#include <time.h>
+
 #include "r3d_octree.cuh"
 
 namespace r3d {
@@ -1015,11 +1017,13 @@ static int pipe_reserve(r3d_tree* t, uint64_t cap) {
         for (int i = 0; i < 2; ++i) {
             R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_done[i], cudaEventDisableTiming));
             R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->rc_done[i], cudaEventDisableTiming));
-            R3D_CUDA_OK(ctx, cudaStreamCreateWithFlags(&t->rc_stream[i], cudaStreamNonBlocking));
         }
         R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_start, cudaEventDisableTiming));
         if (const char* v = getenv("R3D_PIPE_OVERLAP")) t->pipe_overlap = atoi(v) != 0;
     }
+    // the ray-cast streams belong to the context (creating a stream costs milliseconds; trees come and go)
+    for (int i = 0; i < 2; ++i)
+        if (!ctx->rc_stream[i]) R3D_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->rc_stream[i], cudaStreamNonBlocking));
     if (t->delta_cap < cap) R3D_TRY(tree_reserve_delta(t, cap));
     if (t->delta_b_cap < t->delta_cap) {
         R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1055,7 +1059,7 @@ static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
         if (ps.overlap) {
             // the slot's stream starts after the batch's set-up and after the slot's previous scan has been emitted and its
             // counters read back (that scan used the same cube, counters and mailbox)
-            rs = t->rc_stream[slot];
+            rs = ctx->rc_stream[slot];
             R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, t->pipe_start, 0));
             if (t->pipe_done_valid[slot]) R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, t->pipe_done[slot], 0));
         }
@@ -1134,6 +1138,9 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
         R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_start, ctx->stream));   // cubes cleared, abort flag reset, scans resident
         t->pipe_done_valid[0] = t->pipe_done_valid[1] = false;
     }
+    auto now_ns = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; };
+    t->pipe_wait_ns = t->pipe_work_ns = t->pipe_max_turn_ns = t->pipe_scans = 0;
+    uint64_t t_mark = now_ns();
     R3D_TRY(pipe_enqueue(t, scans[0], 0, true));
     uint64_t prev_records = 0;      // records of the apply queued last (not yet reflected in the cursor read back below)
     for (uint32_t s = 0; s < n_scans; ++s) {
@@ -1141,7 +1148,13 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
         if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
         uint32_t hc[CNT_COUNT];
         for (int attempt = 0;; ++attempt) {
+            const uint64_t t_wait = now_ns();
             R3D_CUDA_OK(ctx, cudaEventSynchronize(t->pipe_done[slot]));
+            const uint64_t t_got = now_ns();
+            t->pipe_work_ns += t_wait - t_mark;
+            if (t_wait - t_mark > t->pipe_max_turn_ns) t->pipe_max_turn_ns = t_wait - t_mark;
+            t->pipe_wait_ns += t_got - t_wait;
+            t_mark = t_got;
             memcpy(hc, (char*)ctx->pinned + 1024 + 256 * slot, sizeof hc);
             if (hc[CNT_DELTA] <= t->delta_cap) break;
             if (attempt >= 8) return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the record buffer");
@@ -1149,8 +1162,8 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
             // and queue scan s+1 again.
             R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
             if (overlap) {   // a ray cast that started before the flag was raised may still be running
-                R3D_CUDA_OK(ctx, cudaStreamSynchronize(t->rc_stream[0]));
-                R3D_CUDA_OK(ctx, cudaStreamSynchronize(t->rc_stream[1]));
+                R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->rc_stream[0]));
+                R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->rc_stream[1]));
             }
             R3D_TRY(pipe_reserve(t, (uint64_t)hc[CNT_DELTA] * 2));   // the other slot's records were applied already
             R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
@@ -1176,6 +1189,7 @@ static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_
         *steps_out += (uint64_t)hc[CNT_STEPS_LO] | ((uint64_t)hc[CNT_STEPS_HI] << 32);
         t->delta_n = hc[CNT_DELTA];
         *done_out = s + 1;
+        t->pipe_scans = s + 1;
         if (scans[s].timed && scans[s].a.n) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
     }
     if ((n_scans & 1u) == 0u) {   // the last scan used slot 1: keep t->delta = "records of the last scan"
@@ -1318,7 +1332,7 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
     cudaFree(t->delta_b); cudaFree(t->pipe_counters); cudaFree(t->pipe_list);
     for (int i = 0; i < 2; ++i) {
-        if (t->rc_stream[i]) { cudaStreamSynchronize(t->rc_stream[i]); cudaStreamDestroy(t->rc_stream[i]); }
+        if (t->ctx->rc_stream[i]) cudaStreamSynchronize(t->ctx->rc_stream[i]);
         if (t->pipe_done[i]) cudaEventDestroy(t->pipe_done[i]);
         if (t->rc_done[i]) cudaEventDestroy(t->rc_done[i]);
     }
@@ -1575,6 +1589,12 @@ extern "C" int r3d_delta_expand_keys(const void* records_host, uint64_t n_record
 extern "C" int r3d_tree_last_scan_stats(r3d_tree* t, uint64_t out[4]) {
     if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
     out[0] = t->last_scan_rays; out[1] = t->last_scan_steps; out[2] = t->delta_n; out[3] = t->pool_used;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_pipeline_stats(r3d_tree* t, uint64_t out[4]) {
+    if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    out[0] = t->pipe_wait_ns; out[1] = t->pipe_work_ns; out[2] = t->pipe_max_turn_ns; out[3] = t->pipe_scans;
     return R3D_OK;
 }
 

@@ -62,11 +62,11 @@ struct r3d_tree {
     cudaEvent_t pipe_done[2] = {nullptr, nullptr};
     // overlapped ray casting (two cell cubes): scan s+1's ray cast runs on its own stream beside scan s's tail, list,
     // emit and apply.  R3D_PIPE_OVERLAP=0 keeps everything on the context stream with one cube.
-    cudaStream_t rc_stream[2] = {nullptr, nullptr};
     cudaEvent_t rc_done[2] = {nullptr, nullptr};
     cudaEvent_t pipe_start = nullptr;
     bool pipe_done_valid[2] = {false, false};
     int pipe_overlap = 1;
+    uint64_t pipe_wait_ns = 0, pipe_work_ns = 0, pipe_max_turn_ns = 0, pipe_scans = 0;   // host clock of the last batch
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};

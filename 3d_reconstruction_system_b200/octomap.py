@@ -121,6 +121,12 @@ class OcTree:
         check(self._lib.r3d_tree_last_scan_stats(self._h, a), self._ctx.handle)
         return {"rays": int(a[0]), "steps": int(a[1]), "records": int(a[2]), "bricks": int(a[3])}
 
+    def pipelineStats(self):
+        """dict(wait_ms, work_ms, max_turnaround_ms, scans): the host's side of the last pipelined insertPointClouds batch."""
+        a = (C.c_uint64 * 4)()
+        check(self._lib.r3d_tree_pipeline_stats(self._h, a), self._ctx.handle)
+        return {"wait_ms": a[0] / 1e6, "work_ms": a[1] / 1e6, "max_turnaround_ms": a[2] / 1e6, "scans": int(a[3])}
+
     def updateInnerOccupancy(self):
         self._flush()
         check(self._lib.r3d_tree_update_inner_occupancy(self._h), self._ctx.handle)

@@ -238,7 +238,7 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
     del warm
     # the timed batch, three times on a fresh tree (median): one pass is ~30 ms and the scan pipeline has a host turnaround
     # per scan, so a single pass is at the mercy of one descheduled host thread
-    ms_runs, launches_run = [], 0
+    ms_runs, host_runs, launches_run = [], [], 0
     for _ in range(3):
         tree = octomap.OcTree(res, ctx=ctx)
         tree.reserve(1 << 17)            # capacity hint (277 MB): no pool regrowth inside the timed region
@@ -253,6 +253,7 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
         ctx.synchronize()
         ctx.set_blocking(True)
         ms_runs.append(e0.elapsed_time(e1))
+        host_runs.append(tree.pipelineStats())
         launches_run = ctx.launch_count() - launches0
     ms = float(np.median(ms_runs))
     t0 = time.perf_counter()
@@ -262,7 +263,7 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
            "scans": n_scans, "rays_per_scan": rays // n_scans, "dda_steps_per_scan": steps // n_scans,
            "rays_per_s": rays / (ms * 1e-3), "dda_steps_per_s": steps / (ms * 1e-3), "ms_per_scan": ms / n_scans,
            "voxels": tree.numVoxels(), "bricks": tree.numBricks(), "bt_bytes": len(bt), "bt_write_s": bt_s,
-           "gpu_launches": launches_run, "ms_per_scan_runs": [m / n_scans for m in ms_runs],
+           "gpu_launches": launches_run, "ms_per_scan_runs": [m / n_scans for m in ms_runs], "host_pipeline_runs": host_runs,
            "raycast_kernel_ms_last_scan": float(k3_ms[-1]), "raycast_steps_per_s_in_kernel": (steps / n_scans) / max(k3_ms[-1], 1e-9) * 1e3,
            "workload": "C3: %d consecutive KITTI-shape %s scans (1242x375 rays each, Z=0 sky pixels included as rays to the sensor origin)" % (n_scans, args.depth_kind)}
     # the mode the reference's own OctoMap scripts use: updateNode(point, True) per point (octomap/txt_transfer_octomap.py:25)

@@ -256,6 +256,10 @@ int r3d_delta_expand_keys(const void *records_host, uint64_t n_records, uint16_t
 /* Statistics of the last scan delta: out[0] rays cast, out[1] free-cell visits (DDA steps), out[2] delta records,
  * out[3] bricks in the map as of the last counter read-back (r3d_tree_num_bricks is exact). */
 int r3d_tree_last_scan_stats(r3d_tree *tree, uint64_t out[4]);
+/* Host-side clock of the last pipelined r3d_tree_insert_scans batch, in nanoseconds: out[0] time the host spent blocked
+ * on scan counters (the GPU was the slower side), out[1] time it spent queueing work, out[2] the longest single
+ * turnaround between a scan's counters arriving and the next wait, out[3] scans that went through the pipeline. */
+int r3d_tree_pipeline_stats(r3d_tree *tree, uint64_t out[4]);
 
 /* tree.updateInnerOccupancy() (octomap/txt_transfer_octomap.py:35): inner values are derived on demand. */
 int r3d_tree_update_inner_occupancy(r3d_tree *tree);
