@@ -1026,15 +1026,17 @@ extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, in
         if (chunk > n_frames) chunk = n_frames;
         int slots = ctx->stage_slots;
         if ((long long)slots * chunk > (long long)n_frames + chunk - 1) slots = (n_frames + chunk - 1) / chunk;
-        if (!depth_dev) rc = scratch_reserve(ctx, SCR_IN0, frame_in * chunk * slots);
-        if (rc == R3D_OK && !out_dev) rc = scratch_reserve(ctx, SCR_OUT0, frame_out * chunk * slots);
+        // slot strides rounded up to 256 bytes: every slot starts 16-byte aligned, which the bulk-copy kernel needs
+        const size_t slot_in = (frame_in * chunk + 255) / 256 * 256, slot_out = (frame_out * chunk + 255) / 256 * 256;
+        if (!depth_dev) rc = scratch_reserve(ctx, SCR_IN0, slot_in * slots);
+        if (rc == R3D_OK && !out_dev) rc = scratch_reserve(ctx, SCR_OUT0, slot_out * slots);
         cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
         for (int f0 = 0, c = 0; f0 < n_frames && rc == R3D_OK; f0 += chunk, ++c) {
             const int s = c % slots;
             const int nf = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
             const void* din = depth_dev ? (const void*)((const char*)depth + (size_t)f0 * frame_in)
-                                        : (const void*)((const char*)ctx->scratch[SCR_IN0] + (size_t)s * frame_in * chunk);
-            void* dout = out_dev ? (void*)((char*)out_xyz + (size_t)f0 * frame_out) : (void*)((char*)ctx->scratch[SCR_OUT0] + (size_t)s * frame_out * chunk);
+                                        : (const void*)((const char*)ctx->scratch[SCR_IN0] + (size_t)s * slot_in);
+            void* dout = out_dev ? (void*)((char*)out_xyz + (size_t)f0 * frame_out) : (void*)((char*)ctx->scratch[SCR_OUT0] + (size_t)s * slot_out);
             if (!depth_dev) {
                 if (c >= slots) cudaStreamWaitEvent(s_in, ctx->ev_k[s], 0);      // the kernel that read this slot is done
                 cudaMemcpyAsync((void*)din, (const char*)depth + (size_t)f0 * frame_in, frame_in * nf, cudaMemcpyHostToDevice, s_in);
