@@ -45,6 +45,7 @@ SIGNATURES = {
     "r3d_backproject": (_i32, [_vp, _vp, _i32, _i32, _i32, _sz, _i32, _vp, _vp, _i32, _dbl, _dbl, _i32, _vp, _vp]),
     "r3d_transform_points": (_i32, [_vp, _vp, _u64, _vp, _vp]),
     "r3d_pose_apply_points": (_i32, [_vp, _vp, _u64, _vp, _vp]),
+    "r3d_inflate": (_i32, [_vp, _sz, _vp, _sz]),
     "r3d_format_ply_rows": (_i32, [_vp, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _sz, C.POINTER(_sz)]),
     "r3d_format_txt_rows": (_i32, [_vp, _vp, _vp, _vp, _sz, _u64, _i32, _vp, _sz, C.POINTER(_sz)]),
     "r3d_tree_create": (_i32, [_vp, _dbl, C.POINTER(_vp)]),

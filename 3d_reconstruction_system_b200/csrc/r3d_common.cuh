@@ -77,6 +77,9 @@ bool is_device_ptr(const void* p, bool* pinned = nullptr);
 int device_set(r3d_ctx* ctx);
 int finish(r3d_ctx* ctx);   // sync if blocking, surface async errors
 
+// r3d_inflate.cu: one zlib stream of exactly known output size; 0 on success, negative on a malformed stream
+int inflate_zlib(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len);
+
 struct DeviceSetter {
     int prev = -1;
     explicit DeviceSetter(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }

@@ -98,15 +98,41 @@ inline int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
+// Sub filter: cur[i] += cur[i - bpp].  Written naively the chain runs through memory (store -> load forwarding, ~5 cycles
+// per byte and lane); with the bpp running values carried in registers it is one add per byte and lane.
+template <int BPP>
+inline void unfilter_sub_n(uint8_t* cur, size_t rb) {
+    uint8_t acc[BPP];
+    for (int k = 0; k < BPP; ++k) acc[k] = 0;
+    size_t i = 0;
+    for (; i + BPP <= rb; i += BPP)
+        for (int k = 0; k < BPP; ++k) { acc[k] = (uint8_t)(acc[k] + cur[i + k]); cur[i + k] = acc[k]; }
+    for (int k = 0; i + k < rb; ++k) cur[i + k] = (uint8_t)(acc[k] + cur[i + k]);
+}
+inline void unfilter_sub(uint8_t* cur, size_t rb, size_t bpp) {
+    switch (bpp) {
+        case 1: unfilter_sub_n<1>(cur, rb); break;
+        case 2: unfilter_sub_n<2>(cur, rb); break;
+        case 3: unfilter_sub_n<3>(cur, rb); break;
+        case 4: unfilter_sub_n<4>(cur, rb); break;
+        case 6: unfilter_sub_n<6>(cur, rb); break;
+        case 8: unfilter_sub_n<8>(cur, rb); break;
+        default: for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - bpp]);
+    }
+}
+
 // inflate + un-filter in place: raw = H rows of (1 + rowbytes); afterwards row y's samples start at raw[y*(1+rb)+1]
 bool inflate_unfilter(const PngHeader& h, const std::vector<uint8_t>& idat, std::vector<uint8_t>& raw, std::string& err) {
     const size_t bits = (size_t)h.channels() * h.depth;
     const size_t rb = ((size_t)h.W * bits + 7) / 8;
     const size_t bpp = bits >= 8 ? bits / 8 : 1;
     raw.resize((size_t)h.H * (rb + 1));
-    uLongf dlen = (uLongf)raw.size();
-    const int zr = uncompress(raw.data(), &dlen, idat.data(), (uLong)idat.size());
-    if (zr != Z_OK || dlen != raw.size()) { err = "zlib inflate failed or image data has the wrong size"; return false; }
+    if (r3d::inflate_zlib(idat.data(), idat.size(), raw.data(), raw.size()) != 0) {
+        // anything the in-tree inflate does not take (it is strict about sizes and trailers) gets zlib's verdict
+        uLongf dlen = (uLongf)raw.size();
+        const int zr = uncompress(raw.data(), &dlen, idat.data(), (uLong)idat.size());
+        if (zr != Z_OK || dlen != raw.size()) { err = "zlib inflate failed or image data has the wrong size"; return false; }
+    }
     for (uint32_t y = 0; y < h.H; ++y) {
         uint8_t* row = &raw[(size_t)y * (rb + 1)];
         const int ft = row[0];
@@ -114,7 +140,7 @@ bool inflate_unfilter(const PngHeader& h, const std::vector<uint8_t>& idat, std:
         const uint8_t* up = y ? cur - (rb + 1) : nullptr;
         switch (ft) {
             case 0: break;
-            case 1: for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - bpp]); break;
+            case 1: unfilter_sub(cur, rb, bpp); break;
             case 2: if (up) for (size_t i = 0; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + up[i]); break;
             case 3:
                 if (up) {
@@ -233,7 +259,10 @@ bool convert(const PngHeader& h, const std::vector<uint8_t>& raw, const std::vec
 }
 
 bool decode_one(const char* path, int mode, int channel, void* out, int elem_bytes, int W, int H, std::string& err) {
-    std::vector<uint8_t> file, idat, plte, raw;
+    // per-thread buffers, kept between files (a fresh 1 MB vector is an mmap + page faults + zero fill every time)
+    static thread_local std::vector<uint8_t> file, idat, plte, raw;
+    idat.clear();
+    plte.clear();
     PngHeader h;
     bool trns = false;
     if (!read_file(path, file, err)) return false;

@@ -151,6 +151,10 @@ int r3d_pose_apply_points(r3d_ctx *ctx, const double *xyz, uint64_t n, const dou
  */
 int r3d_transform_points(r3d_ctx *ctx, const double *xyz, uint64_t n, const double T[16], double *out_xyz);
 
+/* The PNG decoder's own zlib-stream inflate (RFC 1950 / 1951, output size known in advance), exposed for tests:
+ * same bytes as zlib's uncompress() for every stream it accepts, an error for truncated / corrupted ones. */
+int r3d_inflate(const void *src, size_t src_len, void *dst, size_t dst_len);
+
 /* ------------------------------------------------------------------ K6: text --- */
 /*
  * The vertex rows of genply / genply_RGB (transfer/camera_to_world.py:112-134, transfer/pixel_to_camera.py:98-124):
