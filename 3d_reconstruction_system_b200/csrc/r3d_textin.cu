@@ -2,9 +2,10 @@
 //
 // txt_read of octomap/txt_transfer_octomap.py:16-28 parses every `x,y,z` line with float() in a Python loop, the PLY
 // twin (octomap/ply_transfer_octomap.py:16-40) skips 8 lines, splits on whitespace and stops after point 5 400 000.
-// Here the file is split at line boundaries into one piece per worker; every piece is parsed with strtod (correctly
-// rounded, like Python's float()) in two passes -- count the rows, then write them at their final offsets -- so the
-// points come out in file order.
+// Here the file is split at line boundaries into one piece per worker; every piece is parsed (r3d_strtod.cuh: correctly
+// rounded like Python's float(), strtod for whatever is not a plain decimal literal) once, and the pieces' rows are then
+// copied to their final offsets, so the points come out in file order.
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -16,16 +17,70 @@
 #include <vector>
 
 #include "r3d_common.cuh"
+#include "r3d_strtod.cuh"
 
 namespace {
 
 using r3d::set_error;
 
+inline bool is_digit(char c) { return (unsigned)(c - '0') < 10u; }
+
+// [sign] (digits [. [digits]] | . digits) [(e|E) [sign] digits]: the decimal part of Python's float() grammar
+bool decimal_syntax(const char* p, const char* e) {
+    if (p < e && (*p == '+' || *p == '-')) ++p;
+    int nd = 0;
+    while (p < e && is_digit(*p)) { ++p; ++nd; }
+    if (p < e && *p == '.') {
+        ++p;
+        while (p < e && is_digit(*p)) { ++p; ++nd; }
+    }
+    if (nd == 0) return false;
+    if (p < e && (*p == 'e' || *p == 'E')) {
+        ++p;
+        if (p < e && (*p == '+' || *p == '-')) ++p;
+        if (p >= e || !is_digit(*p)) return false;
+        while (p < e && is_digit(*p)) ++p;
+    }
+    return p == e;
+}
+
+// One field (no surrounding blanks) with float()'s verdict: the value, or false where float() raises ValueError.
+bool parse_field(const char* p, const char* e, double* v) {
+    if (r3d::parse_double(p, e, v)) return true;            // plain decimal literal of <= 19 digits, normal result
+    if (p >= e) return false;
+    // inf / infinity / nan, any case, optional sign
+    {
+        const char* q = p;
+        bool neg = false;
+        if (*q == '+' || *q == '-') { neg = *q == '-'; ++q; }
+        const size_t n = (size_t)(e - q);
+        auto ieq = [&](const char* w) { if (strlen(w) != n) return false; for (size_t i = 0; i < n; ++i) if ((q[i] | 0x20) != w[i]) return false; return true; };
+        if (ieq("inf") || ieq("infinity")) { *v = neg ? -HUGE_VAL : HUGE_VAL; return true; }
+        if (ieq("nan")) { *v = neg ? -NAN : NAN; return true; }
+    }
+    // PEP 515 underscores (only between digits) are dropped; what remains must be a decimal literal -- strtod would also
+    // take hexadecimal floats and "nan(...)", which float() rejects
+    std::string tmp;
+    tmp.reserve((size_t)(e - p));
+    for (const char* q = p; q < e; ++q) {
+        if (*q == '_') {
+            if (q == p || q + 1 == e || !is_digit(q[-1]) || !is_digit(q[1])) return false;
+            continue;
+        }
+        tmp.push_back(*q);
+    }
+    const char* b = tmp.c_str();
+    if (!decimal_syntax(b, b + tmp.size())) return false;
+    if (r3d::parse_double(b, b + tmp.size(), v)) return true;
+    char* end = nullptr;
+    *v = strtod(b, &end);                                    // long digit strings, subnormal / overflowing results
+    return end == b + tmp.size();
+}
+
 // parses up to three numbers from [p, e) (one line, no newline); comma_mode: fields separated by ',' (surrounding blanks
 // allowed, like float(" 1.5 ")), else by runs of blanks.  Returns the number of leading numeric fields (0..3).
 inline int parse_row(const char* p, const char* e, bool comma_mode, double v[3]) {
     int got = 0;
-    char buf[64];
     while (got < 3 && p < e) {
         while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
         const char* q = p;
@@ -33,14 +88,8 @@ inline int parse_row(const char* p, const char* e, bool comma_mode, double v[3])
         else { while (q < e && *q != ' ' && *q != '\t' && *q != '\r') ++q; }
         const char* te = q;
         while (te > p && (te[-1] == ' ' || te[-1] == '\t' || te[-1] == '\r')) --te;
-        const size_t len = (size_t)(te - p);
-        if (len == 0 || len >= sizeof buf) break;
-        memcpy(buf, p, len);
-        buf[len] = 0;
-        char* end = nullptr;
-        const double d = strtod(buf, &end);
-        if (end != buf + len) break;     // not a number (float() would raise)
-        v[got++] = d;
+        if (te == p || !parse_field(p, te, &v[got])) break;     // empty or not a number (float() would raise)
+        ++got;
         p = (comma_mode && q < e) ? q + 1 : q;
     }
     return got;
@@ -100,26 +149,31 @@ extern "C" int r3d_read_xyz_text(const char* path, int skip_lines, int comma_mod
         b = e;
     }
     const bool comma = comma_mode != 0;
-    auto scan = [&](Piece& pc, double* dst, uint64_t limit) {
+    // pass 1: every piece parses its lines once; the rows are kept per piece when there is somewhere to put them
+    const bool keep = out != nullptr && capacity > 0;
+    std::vector<std::vector<double>> rows_of((size_t)nt);
+    auto scan = [&](int t) {
+        Piece& pc = pieces[(size_t)t];
+        std::vector<double>& mine = rows_of[(size_t)t];
+        if (keep) mine.reserve((pc.end - pc.begin) / 16 + 16);
         uint64_t rows = 0;
         size_t p = pc.begin;
-        while (p < pc.end && rows < limit) {
+        while (p < pc.end) {
             const void* nl = memchr(base + p, '\n', pc.end - p);
             const size_t le = nl ? (size_t)((const char*)nl - base) : pc.end;
             double v[3];
             if (parse_row(base + p, base + le, comma, v) == 3) {
-                if (dst) { dst[3 * rows] = v[0]; dst[3 * rows + 1] = v[1]; dst[3 * rows + 2] = v[2]; }
+                if (keep) mine.insert(mine.end(), v, v + 3);
                 ++rows;
             }
             p = le + 1;
         }
-        return rows;
+        pc.rows = rows;
     };
-    // pass 1: rows per piece
     {
         std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back([&, t] { pieces[(size_t)t].rows = scan(pieces[(size_t)t], nullptr, ~0ull); });
-        pieces[0].rows = scan(pieces[0], nullptr, ~0ull);
+        for (int t = 1; t < nt; ++t) pool.emplace_back(scan, t);
+        scan(0);
         for (auto& th : pool) th.join();
     }
     uint64_t total = 0;
@@ -127,13 +181,14 @@ extern "C" int r3d_read_xyz_text(const char* path, int skip_lines, int comma_mod
     if (max_points && total > max_points) total = max_points;
     *n_points = total;
     if (!out || capacity < total) return R3D_OK;
-    // pass 2: parse into place (pieces beyond the cap write nothing)
+    // pass 2: the pieces' rows to their final offsets, file order kept (pieces beyond the cap write nothing)
     {
         std::vector<std::thread> pool;
         auto fill = [&](int t) {
-            Piece& pc = pieces[(size_t)t];
+            const Piece& pc = pieces[(size_t)t];
             if (pc.first >= total) return;
-            scan(pc, out + 3 * pc.first, total - pc.first);
+            const uint64_t n = pc.rows < total - pc.first ? pc.rows : total - pc.first;
+            if (n) memcpy(out + 3 * pc.first, rows_of[(size_t)t].data(), (size_t)n * 24);
         };
         for (int t = 1; t < nt; ++t) pool.emplace_back(fill, t);
         fill(0);

@@ -205,16 +205,26 @@ def _read_text_points(path, skip_lines, comma, max_points, n_threads=0):
     lib = _lib.load()
     n = C.c_uint64(0)
     bp = os.fsencode(path)
-    rc = lib.r3d_read_xyz_text(bp, int(skip_lines), 1 if comma else 0, int(max_points), None, 0, C.byref(n), int(n_threads))
+    # one call: a row is at least 6 bytes ("0,0,0\n"), so size // 6 + 1 rows always fit (untouched pages cost nothing)
+    try:
+        bound = os.path.getsize(path) // 6 + 1
+    except OSError:
+        bound = 0
+    if max_points:
+        bound = min(bound, int(max_points))
+    out = np.empty((bound, 3), dtype=np.float64)
+    rc = lib.r3d_read_xyz_text(bp, int(skip_lines), 1 if comma else 0, int(max_points), out.ctypes.data if bound else None, bound, C.byref(n),
+                               int(n_threads))
     if rc != 0:
         msg = lib.r3d_last_error(None).decode("utf-8", "replace")
         raise FileNotFoundError(msg) if "cannot open" in msg else ValueError(msg)
-    out = np.empty((n.value, 3), dtype=np.float64)
-    if n.value:
+    if n.value > bound:          # cannot happen (see the bound); kept as the ABI's two-call protocol
+        out = np.empty((n.value, 3), dtype=np.float64)
         rc = lib.r3d_read_xyz_text(bp, int(skip_lines), 1 if comma else 0, int(max_points), out.ctypes.data, n.value, C.byref(n), int(n_threads))
         if rc != 0:
             raise ValueError(lib.r3d_last_error(None).decode("utf-8", "replace"))
-    return out
+        return out
+    return out[:n.value].copy()
 
 
 def read_xyz_txt(path):
