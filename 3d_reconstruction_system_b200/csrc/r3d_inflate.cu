@@ -18,8 +18,11 @@ namespace {
 
 constexpr int kLitBits = 11, kDistBits = 8;
 constexpr int kMaxLitSyms = 288, kMaxDistSyms = 32, kMaxCodeLen = 15;
-// worst-case table sizes (primary + all sub-tables), as enumerated by zlib's enough.c for these root widths
-constexpr int kLitTableSize = 2342, kDistTableSize = 402;
+// table sizes (primary + all sub-tables).  A sub-table of width w belongs to a complete prefix subtree of depth w, which
+// has at least w + 1 leaves, so sub-tables cost at most 2^w / (w + 1) entries per symbol: 16 / 5 for the 286 literal /
+// length symbols under an 11-bit root (2048 + 915), 128 / 8 for the 30 distance symbols under an 8-bit root (256 + 480).
+// build_table() checks the capacity anyway.
+constexpr int kLitTableSize = 3072, kDistTableSize = 768;
 
 // table entry: [4:0] bits to consume, [8:5] extra bits (or sub-table width), [11:9] kind, [30:16] value, [31] literal.
 // A literal entry of the literal/length root table may carry TWO literals when both codewords fit the root width
