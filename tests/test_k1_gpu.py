@@ -336,3 +336,22 @@ def test_fast_compaction_paths(ctx, dtype, scale, out_dtype, world):
                                       out_dtype=np.float64)
         _, wref = oracle_batch(depths, po.AIRSIM_INTRINSICS, rt, po.MODE_DISPARITY, scale, 67.375)
         assert np.array_equal(got, wref[mask])
+
+
+@pytest.mark.parametrize("shape", [(6, 8, 256), (5, 9, 257), (3, 40, 300), (3, 12, 1000), (2, 8, 4097), (40, 8, 258)])
+def test_narrow_and_short_images_through_the_bulk_kernels(ctx, shape):
+    """The narrowest / shortest images the bulk kernels take (W >= 256, H >= 8): several row wraps per 1 024-pixel group,
+    frame ends every few tiles; plain and compaction mode, both record types, two sample types."""
+    rng = np.random.default_rng(5 + shape[2])
+    n, H, W = shape
+    for dtype, scale in ((np.uint16, 1.0 / 256.0), (np.float32, 1.0)):
+        depths = (rng.integers(0, 60000, size=shape) * (rng.random(shape) > 0.2)).astype(dtype)
+        rt = random_rt(n, rng)
+        _, world_ref = oracle_batch(depths, po.REF_INTRINSICS, rt, 0, scale)
+        mask = np.concatenate([po.valid_mask(depths[k], 0, scale).ravel() for k in range(n)])
+        for od in (np.float32, np.float64):
+            got, _ = ctx.backproject(depths, po.REF_INTRINSICS, rt=rt, depth_scale=scale, out_dtype=od)
+            assert np.array_equal(got, world_ref.astype(od))
+            gc, counts = ctx.backproject(depths, po.REF_INTRINSICS, rt=rt, depth_scale=scale, compact=True, out_dtype=od)
+            assert counts.tolist() == [int(po.valid_mask(depths[k], 0, scale).sum()) for k in range(n)]
+            assert np.array_equal(gc, world_ref[mask].astype(od))
