@@ -185,6 +185,12 @@ __device__ __forceinline__ bool cell_of_key(const ScanArgs& a, int kx, int ky, i
 #ifndef K3_VARIANT
 #define K3_VARIANT 1
 #endif
+// key += step and tMax += tDelta (round to nearest, no contraction) when axis == which, as predicated instructions: written
+// as C++ conditionals the compiler turns the three mutually exclusive updates into a chain of divergent branches
+__device__ __forceinline__ void step_axis_if(int axis, int which, int& k, int s, double& tm, double td) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.s32 %0, %0, %4;\n\t@p add.rn.f64 %1, %1, %5;\n\t}"
+        : "+r"(k), "+d"(tm) : "r"(axis), "r"(which), "r"(s), "d"(td));
+}
 // Per-lane state of the dense walker.
 struct DenseLane {
     int kx, ky, kz, ex, ey, ez, sx, sy, sz;
@@ -208,7 +214,24 @@ struct DenseLane {
 __device__ __forceinline__ bool dense_step(const ScanArgs& a, uint64_t* masks64, uint8_t* touched, DenseLane& L, uint64_t& stage) {
     if (L.age == 1) L.seen = stage;      // requested two iterations ago, into this same register
     // ---- one DDA step along the chosen axis (ray_advance), then pick the next axis (ray_select).
-#if K3_VARIANT & 1
+#if K3_VARIANT == 2
+    // (candidate, not measured yet: built with -DK3_VARIANT=2)  The axis is carried as an integer; the three updates are
+    // written as conditional statements so that they compile to predicated DADD / IADD (no selects, no multiplies), and
+    // "min(tMax) > length" is evaluated as "every tMax > length": three chained compares on the fp64 pipe instead of a
+    // select tree on the ALU pipe (the minimum itself is never needed).
+    const bool ax = L.axis == 0, ay = L.axis == 1;
+    const int okx = L.kx, oky = L.ky, okz = L.kz;
+    step_axis_if(L.axis, 0, L.kx, L.sx, L.tmx, L.tdx);
+    step_axis_if(L.axis, 1, L.ky, L.sy, L.tmy, L.tdy);
+    step_axis_if(L.axis, 2, L.kz, L.sz, L.tmz, L.tdz);
+    const int cstep = ax ? L.csx : (ay ? L.csy : L.csz);
+    const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
+    const bool selx = xy & xz, sely = (!xy) & yz;
+    L.axis = selx ? 0 : (sely ? 1 : 2);
+    const bool past = (L.tmx > L.length) & (L.tmy > L.length) & (L.tmz > L.length);
+    const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | past;
+    const int diff = (L.kx ^ okx) | (L.ky ^ oky) | (L.kz ^ okz);
+#elif K3_VARIANT & 1
     // The axis is carried as three 0/1 integers and applied by multiplication: selects run on the integer / select pipe,
     // which bounds this kernel, multiplies on the FMA and fp64 pipes.  x * 1.0 and t + 0.0 are exact, so the tMax update
     // tm + m * td is bit-identical to "tm + td on the chosen axis, untouched elsewhere".
