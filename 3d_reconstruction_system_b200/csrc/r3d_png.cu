@@ -109,6 +109,46 @@ inline void unfilter_sub_n(uint8_t* cur, size_t rb) {
         for (int k = 0; k < BPP; ++k) { acc[k] = (uint8_t)(acc[k] + cur[i + k]); cur[i + k] = acc[k]; }
     for (int k = 0; i + k < rb; ++k) cur[i + k] = (uint8_t)(acc[k] + cur[i + k]);
 }
+// Average and Paeth with the row above: the same idea, the left (and upper-left) neighbours of every lane stay in registers
+template <int BPP>
+inline void unfilter_avg_n(uint8_t* cur, const uint8_t* up, size_t rb) {
+    unsigned a[BPP];
+    for (int k = 0; k < BPP; ++k) a[k] = 0;
+    size_t i = 0;
+    for (; i + BPP <= rb; i += BPP)
+        for (int k = 0; k < BPP; ++k) { a[k] = (cur[i + k] + ((a[k] + up[i + k]) >> 1)) & 255u; cur[i + k] = (uint8_t)a[k]; }
+    for (int k = 0; i + k < rb; ++k) cur[i + k] = (uint8_t)(cur[i + k] + ((a[k] + up[i + k]) >> 1));
+}
+template <int BPP>
+inline void unfilter_paeth_n(uint8_t* cur, const uint8_t* up, size_t rb) {
+    int a[BPP], c[BPP];
+    for (int k = 0; k < BPP; ++k) a[k] = c[k] = 0;
+    size_t i = 0;
+    auto one = [&](size_t idx, int k) {
+        const int b = up[idx];
+        const int pb = a[k] - c[k], pa = b - c[k];           // p - b, p - a with p = a + b - c
+        const int pc = pa + pb;
+        const int apa = pa < 0 ? -pa : pa, apb = pb < 0 ? -pb : pb, apc = pc < 0 ? -pc : pc;
+        const int pred = (apa <= apb && apa <= apc) ? a[k] : (apb <= apc ? b : c[k]);
+        a[k] = (cur[idx] + pred) & 255;
+        c[k] = b;
+        cur[idx] = (uint8_t)a[k];
+    };
+    for (; i + BPP <= rb; i += BPP)
+        for (int k = 0; k < BPP; ++k) one(i + k, k);
+    for (int k = 0; i + k < rb; ++k) one(i + k, k);
+}
+#define R3D_BPP_SWITCH(fn, bpp, generic, ...)      \
+    switch (bpp) {                                 \
+        case 1: fn<1>(__VA_ARGS__); break;         \
+        case 2: fn<2>(__VA_ARGS__); break;         \
+        case 3: fn<3>(__VA_ARGS__); break;         \
+        case 4: fn<4>(__VA_ARGS__); break;         \
+        case 6: fn<6>(__VA_ARGS__); break;         \
+        case 8: fn<8>(__VA_ARGS__); break;         \
+        default: generic;                          \
+    }
+
 inline void unfilter_sub(uint8_t* cur, size_t rb, size_t bpp) {
     switch (bpp) {
         case 1: unfilter_sub_n<1>(cur, rb); break;
@@ -144,16 +184,20 @@ bool inflate_unfilter(const PngHeader& h, const std::vector<uint8_t>& idat, std:
             case 2: if (up) for (size_t i = 0; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + up[i]); break;
             case 3:
                 if (up) {
-                    for (size_t i = 0; i < bpp && i < rb; ++i) cur[i] = (uint8_t)(cur[i] + (up[i] >> 1));
-                    for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + ((cur[i - bpp] + up[i]) >> 1));
+                    R3D_BPP_SWITCH(unfilter_avg_n, bpp, {
+                        for (size_t i = 0; i < bpp && i < rb; ++i) cur[i] = (uint8_t)(cur[i] + (up[i] >> 1));
+                        for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + ((cur[i - bpp] + up[i]) >> 1));
+                    }, cur, up, rb)
                 } else {
                     for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + (cur[i - bpp] >> 1));
                 }
                 break;
             case 4:
                 if (up) {
-                    for (size_t i = 0; i < bpp && i < rb; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);      // paeth(0, b, 0) = b
-                    for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + paeth(cur[i - bpp], up[i], up[i - bpp]));
+                    R3D_BPP_SWITCH(unfilter_paeth_n, bpp, {
+                        for (size_t i = 0; i < bpp && i < rb; ++i) cur[i] = (uint8_t)(cur[i] + up[i]);      // paeth(0, b, 0) = b
+                        for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + paeth(cur[i - bpp], up[i], up[i - bpp]));
+                    }, cur, up, rb)
                 } else {
                     for (size_t i = bpp; i < rb; ++i) cur[i] = (uint8_t)(cur[i] + cur[i - bpp]);        // paeth(a, 0, 0) = a
                 }
