@@ -576,7 +576,8 @@ def run_gpu_arm(args):
     except Exception:
         avail = 64 << 30
     e2e_frames = n_frames
-    while e2e_frames > 64 and e2e_frames * H * W * 14 * 1.3 > avail * 0.5:
+    # every rank of the node pins its own host buffers: share half of the free memory between them
+    while e2e_frames > 64 and e2e_frames * H * W * 14 * 1.3 > avail * 0.5 / max(world, 1):
         e2e_frames //= 2
     lib = ctx.lib
     in_bytes, out_bytes = e2e_frames * H * W * 2, e2e_frames * H * W * 12
