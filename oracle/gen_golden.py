@@ -134,6 +134,47 @@ def main():
         cv2.imwrite(os.path.join(td, "v16.png"), v16)
         g = cv2.imread(os.path.join(td, "v16.png"), cv2.IMREAD_GRAYSCALE)
         meta["imread_gray_16bit_is_shift8"] = bool(np.array_equal(g, (v16 >> 8).astype(np.uint8)))
+    # ---- (5) BASELINE config 1 at its real shape: camera_to_world.main() on ONE 1242x375 KITTI-shape depth PNG ----
+    # (transfer/camera_to_world.py:178-180 -> get_file_name :138-174 -> gentxtcord :67-83, get_pointdata :86-105,
+    # genply :112-134).  The frame is frame 0 of the synthetic C2 sequence (oracle/points_oracle.py, seed 20261018 + 1),
+    # written as a 16-bit PNG; the reference reads it with IMREAD_GRAYSCALE, i.e. as uint8 = raw >> 8 (integer metres).
+    # ~25 s of reference time.  Outputs are 19 / 26 / 12 MB of text: committed as sha256 + a strided sample.
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import points_oracle as po
+    W1, H1 = 1242, 375
+    d16 = po.synth_depth_u16(W1, H1, po.KITTI_INTRINSICS, 20261018 + 1, "street")
+    q1, t1 = po.synth_pose(0, 4500)
+    with tempfile.TemporaryDirectory() as td:
+        os.chdir(td)
+        try:
+            for d in ("depth", "point", "point_world", "ply", "camera_pose"):
+                os.mkdir(d)
+            cv2.imwrite("depth/000000.png", d16)
+            pose_txt1 = "id,tx,ty,tz,qx,qy,qz,qw,name,extra\n" + "0,%r,%r,%r,%r,%r,%r,%r,000000.png,0\n" % (
+                tuple(float(v) for v in t1) + tuple(float(v) for v in q1))
+            with open("camera_pose/image_colmap_simi_2.txt", "w") as f:
+                f.write(pose_txt1)
+            c2w.main()
+            cam1 = open("point/000000.txt").read()
+            world1 = open("point_world/small_worldpoint_5_23_5.txt").read()
+            ply1 = open("ply/small_035_p8.ply").read()
+            seen8 = cv2.imread("depth/000000.png", cv2.IMREAD_GRAYSCALE)
+        finally:
+            os.chdir(cwd)
+    assert np.array_equal(seen8, (d16 >> 8).astype(np.uint8))
+    wl = world1.splitlines()
+    sel1 = np.arange(0, W1 * H1, 97)
+    world_sel = np.array([[float(v) for v in wl[i].split(',')] for i in sel1], dtype=np.float64)
+    cl = cam1.splitlines()
+    pl = ply1.split("end_header\n    ")[1].split("\n")
+    np.savez_compressed(os.path.join(OUT, "ref_c1_kitti.npz"), depth8=seen8, q=q1, t=t1, rinv=np.asarray(c2w.scipy_transfer(q1)),
+                        sel=sel1, world_sel=world_sel)
+    meta["c1_kitti"] = {"W": W1, "H": H1, "seed": 20261018 + 1, "pose_txt": pose_txt1,
+                        "depth16_sha256": sha(d16.tobytes()), "cam_txt_sha256": sha(cam1), "world_txt_sha256": sha(world1),
+                        "ply_sha256": sha(ply1), "cam_txt_bytes": len(cam1), "world_txt_bytes": len(world1), "ply_bytes": len(ply1),
+                        "cam_lines_sample": {str(i): cl[i] for i in (0, 1, 607, 232254, 465749)},
+                        "world_lines_sample": {str(i): wl[i] for i in (0, 1, 607, 232254, 465749)},
+                        "ply_rows_sample": {str(i): pl[i] for i in (0, 1, 607, 232254, 465749)}}
     with open(os.path.join(OUT, "ref_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)
     print("golden written to", os.path.abspath(OUT))

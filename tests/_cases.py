@@ -35,3 +35,18 @@ def repr_cases(seed=12, n=200000):
                        1.7976931348623157e308, 0.1, 0.2, 0.3, 1 / 3, 2 / 3, 123456.789, 1e15, 1e17, 4.35, 0.5, 1.0, -1.5, 9007199254740993.0, np.inf, -np.inf, np.nan, 2.0 ** 63]))
     out = np.concatenate(v)
     return out[np.isfinite(out) | (np.arange(out.size) >= out.size - 30)]
+
+
+def load_c1(golden_dir):
+    """BASELINE config 1 fixture (oracle/gen_golden.py section 5): (npz, meta, the 16-bit frame regenerated and checked)."""
+    import hashlib
+    import json
+    import os
+    from oracle import points_oracle as po
+    g = np.load(os.path.join(golden_dir, "ref_c1_kitti.npz"))
+    with open(os.path.join(golden_dir, "ref_meta.json")) as f:
+        meta = json.load(f)["c1_kitti"]
+    d16 = po.synth_depth_u16(meta["W"], meta["H"], po.KITTI_INTRINSICS, meta["seed"], "street")
+    assert hashlib.sha256(d16.tobytes()).hexdigest() == meta["depth16_sha256"]          # the generator still makes the same frame
+    assert np.array_equal((d16 >> 8).astype(np.uint8), g["depth8"])                      # what IMREAD_GRAYSCALE hands the reference
+    return g, meta, d16

@@ -27,16 +27,36 @@ def f32bits(v):
     return struct.unpack("<I", struct.pack("<f", float(v)))[0]
 
 
+def expand_leaves(rk, rv, rd):
+    """The oracle's (possibly pruned) leaves -> every depth-16 voxel they stand for: (packed keys sorted, values)."""
+    keys, vals = [], []
+    for d in np.unique(rd):
+        m = rd == d
+        side = 1 << (16 - int(d))
+        base = rk[m].astype(np.int64)
+        off = np.arange(side, dtype=np.int64)
+        ox, oy, oz = np.meshgrid(off, off, off, indexing="ij")
+        offs = np.stack([ox.ravel(), oy.ravel(), oz.ravel()], axis=1)
+        k = (base[:, None, :] + offs[None, :, :]).reshape(-1, 3).astype(np.uint64)
+        keys.append(k[:, 0] | (k[:, 1] << np.uint64(16)) | (k[:, 2] << np.uint64(32)))
+        vals.append(np.repeat(rv[m], side ** 3))
+    if not keys:
+        return np.zeros(0, np.uint64), np.zeros(0, np.float32)
+    keys, vals = np.concatenate(keys), np.concatenate(vals)
+    order = np.argsort(keys, kind="stable")
+    return keys[order], vals[order]
+
+
 def assert_same_tree(gpu, ref, check_size=True):
-    """Every GPU voxel has the oracle's log-odds bit for bit, the voxel counts agree, and the .bt bytes agree."""
-    keys, vals = gpu.voxels()
-    rk, rv, rd = ref.leaves()
-    # expand the oracle's (possibly pruned) leaves to depth-16 voxel count
-    n_ref = int(np.sum(8 ** (16 - rd.astype(np.int64))))
-    assert keys.shape[0] == n_ref
-    step = max(1, keys.shape[0] // 4000)
-    for k, v in zip(keys[::step], vals[::step]):
-        assert f32bits(ref.search(k)) == f32bits(v), (k, v, ref.search(k))
+    """EVERY voxel of the GPU map has the oracle's key and log-odds bit for bit (the whole arrays are compared, not a
+    sample), the voxel counts agree, and the .bt bytes agree."""
+    keys, vals = gpu.voxels()                      # sorted by packed key
+    rkeys, rvals = expand_leaves(*ref.leaves())
+    packed = oo.pack_keys(keys) if keys.shape[0] else np.zeros(0, np.uint64)
+    assert packed.shape[0] == rkeys.shape[0]
+    assert np.array_equal(packed, rkeys)
+    bad = np.flatnonzero(vals.view(np.uint32) != rvals.view(np.uint32))
+    assert bad.size == 0, (bad.size, keys[bad[:3]], vals[bad[:3]], rvals[bad[:3]])
     if check_size:
         assert gpu.size() == ref.size()
     assert gpu.writeBinary() == ref.write_binary_bytes()   # oracle call last: it mutates the oracle tree

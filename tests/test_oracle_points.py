@@ -7,6 +7,7 @@ import os
 import numpy as np
 
 from oracle import points_oracle as po
+from _cases import load_c1
 
 
 def _load(golden_dir):
@@ -103,3 +104,28 @@ def test_disparity_mode_is_fB_over_d():
     assert z[0, 1] == 269.5 * 0.25
     assert z[0, 2] == 269.5 * 0.25 / 2.0
     assert np.array_equal(po.valid_mask(raw, po.MODE_DISPARITY, 1 / 256.0), np.array([[False, True, True, True]]))
+
+
+# ---- BASELINE config 1 at its real shape: one 1242x375 frame through the reference's own main() (oracle/gen_golden.py section 5)
+def test_c1_kitti_frame_oracle_vs_reference_outputs(golden_dir):
+    g, meta, _ = load_c1(golden_dir)
+    d8 = g["depth8"]
+    X, Y, Z = po.backproject(po.raw_to_z(d8), po.REF_INTRINSICS)
+    cam_txt = po.txt_lines_camera(X, Y, d8)
+    assert len(cam_txt) == meta["cam_txt_bytes"]
+    assert hashlib.sha256(cam_txt.encode()).hexdigest() == meta["cam_txt_sha256"]        # 465 750 lines, byte-identical
+    assert np.array_equal(po.scipy_transfer(g["q"]), g["rinv"])
+    _, world = po.depth_to_world(d8, po.REF_INTRINSICS, g["rinv"], g["t"])
+    ref, got = g["world_sel"], world[g["sel"]]
+    # north_star tolerance (1e-5 relative or 1e-4 m absolute), and the BLAS-order bound actually observed: <= 2 ulp of the largest term
+    assert np.all((np.abs(got - ref) <= 1e-4) | (np.abs(got - ref) <= 1e-5 * np.abs(ref)))
+    scale = np.max(np.abs(world[g["sel"]]), axis=1, keepdims=True) + np.max(np.abs(g["t"]))
+    assert np.max(np.abs(got - ref) / scale) <= 4 * np.finfo(np.float64).eps
+    # float32 voxel keys at 0.1 m identical
+    assert np.array_equal(np.floor(10.0 * got.astype(np.float32).astype(np.float64)), np.floor(10.0 * ref.astype(np.float32).astype(np.float64)))
+    ply = po.genply_text(world[:, 0], world[:, 1], world[:, 2])
+    assert len(ply) == meta["ply_bytes"]
+    assert hashlib.sha256(ply.encode()).hexdigest() == meta["ply_sha256"]                # merged PLY, byte-identical
+    rows = ply.split("end_header\n    ")[1].split("\n")
+    for i, row in meta["ply_rows_sample"].items():
+        assert rows[int(i)] == row
