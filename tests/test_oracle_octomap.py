@@ -179,3 +179,62 @@ def test_leaves_roundtrip_matches_search():
     assert np.all(depths <= 16)
     for k, v in list(zip(keys, vals))[:50]:
         assert np.float32(t.search(k)) == v
+
+
+# ---- the pin against the real OctoMap library (oracle/pin_against_octomap.py)
+def _pin_tools():
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("pin_against_octomap", os.path.join(root, "oracle", "pin_against_octomap.py"))
+    pin = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pin)
+    from oracle import octomap_corpus
+    return pin, octomap_corpus
+
+
+def test_pin_corpus_replays_on_the_restatement():
+    """The corpus and the replay plumbing of the pin script, on the C restatement: the structural cases reproduce the
+    hand-derived .bt known answers above, so a golden file written by the same script from the real library compares
+    like with like."""
+    import hashlib
+    pin, corpus = _pin_tools()
+    cases = {c["name"]: c for c in corpus.cases(heavy=False)}
+    make = lambda res: pin.OracleTree(oo, res)
+    want = {"bt_single_occ": HDR % (17, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 14 + b"\x02\x00",
+            "bt_single_free_0.05": HDR % (17, b"0.05") + b"\x03\x00" + b"\x00\xc0" * 14 + b"\x00\x40",
+            "bt_eight_siblings": HDR % (16, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 13 + b"\x02\x00",
+            "bt_prune_quirk_a": HDR % (23, b"0.1") + b"\x00\xc0" + b"\x03\x00" * 13 + b"\xaa\xaa"}
+    for name, data in want.items():
+        rec = pin.replay(cases[name], make)
+        assert rec["bt_len"] == len(data) and rec["bt_sha256"] == hashlib.sha256(data).hexdigest(), name
+    lad = [pin.replay(cases["ladder_hits_%d" % k], make)["logodds_bits"][0] for k in range(1, 7)]
+    assert lad[0] == 0x3F58E883 and lad[4] == lad[5] == 0x4060B4BA and len(set(lad)) == 5
+    assert pin.replay(cases["ray_out_of_bounds_end"], make)["size"] == 0
+    assert pin.replay(cases["ray_same_voxel"], make)["bt_sha256"] == pin.replay(cases["bt_single_occ"], make)["bt_sha256"]
+
+
+def test_pinned_against_real_octomap(golden_dir):
+    """Replays the corpus against tests/golden/octomap_pin.json, the answers of the REAL octomap extension.  The file
+    can only be produced where `import octomap` works (not in the authoring image): until a maintainer has run
+    `python oracle/pin_against_octomap.py` once, the occupancy oracle is PARITY UNPINNED and this test skips."""
+    import json
+    import os
+    import pytest
+    path = os.path.join(golden_dir, "octomap_pin.json")
+    if not os.path.exists(path):
+        pytest.skip("parity unpinned: tests/golden/octomap_pin.json absent (run oracle/pin_against_octomap.py where `import octomap` works)")
+    pin, corpus = _pin_tools()
+    gold = json.load(open(path))
+    assert "SELF-CHECK" not in gold["info"]["library"], "the golden file must come from the real library"
+    heavy = os.environ.get("R3D_PIN_HEAVY", "0") == "1"
+    make = lambda res: pin.OracleTree(oo, res)
+    checked = 0
+    for case in corpus.cases(heavy=heavy):
+        if case["name"] not in gold["cases"]:
+            continue
+        want, got = gold["cases"][case["name"]], pin.replay(case, make)
+        for key in ("size", "logodds_bits", "bt_len", "bt_sha256"):
+            assert got[key] == want[key], (case["name"], key)
+        checked += 1
+    assert checked >= 40
