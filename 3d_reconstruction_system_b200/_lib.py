@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libr3d_b200.so")
+# R3D_LIB_PATH: load an experiment build (build.py, R3D_BUILD_TAG) instead of the product library
+LIB_PATH = os.environ.get("R3D_LIB_PATH") or os.path.join(HERE, "libr3d_b200.so")
 
 OK = 0
 U8, U16, F32 = 0, 1, 2

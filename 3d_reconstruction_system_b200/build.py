@@ -12,8 +12,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "libr3d_b200.so")
+# R3D_BUILD_TAG=<tag> (kernel experiments, together with R3D_NVCC_EXTRA) builds libr3d_b200_<tag>.so beside the product
+# library from its own object directory; R3D_LIB_PATH selects it at load time (_lib.py).  The default build is untagged.
+TAG = os.environ.get("R3D_BUILD_TAG", "")
+OBJ = os.path.join(CSRC, "_obj" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libr3d_b200%s.so" % ("_" + TAG if TAG else ""))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

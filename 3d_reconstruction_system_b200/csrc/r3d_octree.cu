@@ -159,7 +159,11 @@ struct ScanArgs {
 // cells per scan).  Different lanes cross sub-block and brick borders at different steps, so that bookkeeping is
 // written without divergent slow paths: some lane needs it on almost every iteration.
 constexpr int K3_THREADS = 256;
+#ifdef K3_REFILL_MIN_OVERRIDE
+constexpr int K3_REFILL_MIN = K3_REFILL_MIN_OVERRIDE;
+#else
 constexpr int K3_REFILL_MIN = 8;
+#endif
 
 __device__ __forceinline__ uint64_t ldcg_u64_if(const uint64_t* p, uint64_t otherwise, bool pred) {
     uint64_t v = otherwise;
