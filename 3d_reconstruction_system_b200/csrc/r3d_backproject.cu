@@ -109,6 +109,12 @@ template <>
 __device__ __forceinline__ float out_cast<float>(double v) { return __double2float_rn(v); }
 template <>
 __device__ __forceinline__ double out_cast<double>(double v) { return v; }
+// world coordinates: float64 records get the reference's +0.0 for sums of signed zeros (pose_canon)
+template <typename OutT>
+__device__ __forceinline__ OutT world_cast(double v) {
+    if constexpr (sizeof(OutT) == 8) return pose_canon(v);
+    else return __double2float_rn(v);
+}
 
 // One pixel: raw sample + table entries -> record.  `pose_frame` caches which frame `pose` holds.
 template <typename OutT, bool kWorld, int kMode = -1>
@@ -125,7 +131,7 @@ __device__ __forceinline__ bool k1_pixel(const K1Args& a, double raw, double au,
         }
         double wx, wy, wz;
         pose_apply(pose, X, Y, Z, wx, wy, wz);
-        ox = out_cast<OutT>(wx); oy = out_cast<OutT>(wy); oz = out_cast<OutT>(wz);
+        ox = world_cast<OutT>(wx); oy = world_cast<OutT>(wy); oz = world_cast<OutT>(wz);
     } else {
         ox = out_cast<OutT>(X); oy = out_cast<OutT>(Y); oz = out_cast<OutT>(Z);
     }
@@ -143,7 +149,7 @@ __device__ __forceinline__ void k1_pixel_pose(const K1Args& a, double raw, doubl
     if (kWorld) {
         double wx, wy, wz;
         pose_apply(pose, X, Y, Z, wx, wy, wz);
-        ox = out_cast<OutT>(wx); oy = out_cast<OutT>(wy); oz = out_cast<OutT>(wz);
+        ox = world_cast<OutT>(wx); oy = world_cast<OutT>(wy); oz = world_cast<OutT>(wz);
     } else {
         ox = out_cast<OutT>(X); oy = out_cast<OutT>(Y); oz = out_cast<OutT>(Z);
     }
@@ -747,7 +753,7 @@ __global__ void k_transform_points(const double* __restrict__ in, double* __rest
         const double x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-            out[3 * i + k] = dadd(dadd(dadd(dmul(T[4 * k], x), dmul(T[4 * k + 1], y)), dmul(T[4 * k + 2], z)), T[4 * k + 3]);
+            out[3 * i + k] = pose_canon(dadd(dadd(dadd(dmul(T[4 * k], x), dmul(T[4 * k + 1], y)), dmul(T[4 * k + 2], z)), T[4 * k + 3]));
     }
 }
 
@@ -760,7 +766,7 @@ __global__ void k_pose_apply_points(const double* __restrict__ in, double* __res
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         double wx, wy, wz;
         pose_apply(pose, in[3 * i], in[3 * i + 1], in[3 * i + 2], wx, wy, wz);
-        out[3 * i] = wx; out[3 * i + 1] = wy; out[3 * i + 2] = wz;
+        out[3 * i] = pose_canon(wx); out[3 * i + 1] = pose_canon(wy); out[3 * i + 2] = pose_canon(wz);
     }
 }
 

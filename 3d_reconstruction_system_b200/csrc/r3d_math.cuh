@@ -102,6 +102,11 @@ R3D_HD void pose_apply(const Pose& p, double X, double Y, double Z, double& wx, 
     wy = dadd(dadd(dmul(p.r10, d0), dmul(p.r11, d1)), dmul(p.r12, d2));
     wz = dadd(dadd(dmul(p.r20, d0), dmul(p.r21, d1)), dmul(p.r22, d2));
 }
+// The reference's sum is np.dot (BLAS): its accumulators start at +0.0, so a sum of signed zeros is +0.0, never -0.0
+// (e.g. the world x of a Z = 0 pixel under an axis-aligned pose: "0.0000" in the reference's PLY, not "-0.0000").
+// w + 0.0 is exact for every other value.  Applied where the float64 value is what the caller sees (text writers);
+// float32 records feed voxel keys, where the sign of zero is immaterial.
+R3D_HD double pose_canon(double w) { return dadd(w, 0.0); }
 // gentxtcord tables (transfer/camera_to_world.py:77-78): ((i - cx) / fx) and ((j - cy) / fy)
 R3D_HD double pixel_coeff(int i, double c, double f) { return ddiv(dsub((double)i, c), f); }
 

@@ -104,7 +104,8 @@ def point_camera(P, r_inverse, t):
     d2 = P[..., 2] - t[2]
     out = np.empty(P.shape, dtype=np.float64)
     for k in range(3):
-        out[..., k] = (r[k, 0] * d0 + r[k, 1] * d1) + r[k, 2] * d2
+        # "+ 0.0": np.dot's accumulators start at +0.0, so a sum of signed zeros is +0.0 in the reference (exact otherwise)
+        out[..., k] = ((r[k, 0] * d0 + r[k, 1] * d1) + r[k, 2] * d2) + 0.0
     return out
 
 

@@ -72,6 +72,7 @@ int hm_scan_point_end(const float* o, const float* p, double maxrange, float* e)
 void hm_pose_apply(const double* rt, const double* p, double* w) {
     Pose ps; pose_load(rt, ps);
     pose_apply(ps, p[0], p[1], p[2], w[0], w[1], w[2]);
+    for (int k = 0; k < 3; ++k) w[k] = pose_canon(w[k]);
 }
 double hm_pixel_coeff(int i, double c, double f) { return pixel_coeff(i, c, f); }
 double hm_decode_z(double raw, int mode, double scale, double fB, int* valid) { bool v; double z = decode_z(raw, mode, scale, fB, v); *valid = v; return z; }
