@@ -9,6 +9,8 @@
 #include "../../include/r3d.h"
 #include "r3d_math.cuh"
 
+namespace r3d { struct ScanPipe; }
+
 struct r3d_ctx {
     int device = 0;
     int sm_count = 148;
@@ -16,7 +18,7 @@ struct r3d_ctx {
     cudaStream_t stream = nullptr;   // every kernel of this context
     cudaStream_t copy_stream[2] = {nullptr, nullptr};  // host-pointer staging pipeline
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
-    cudaStream_t rc_stream[2] = {nullptr, nullptr};   // scan pipeline: one ray-cast stream per slot (created on first use)
+    r3d::ScanPipe* scan_pipe = nullptr;   // r3d_raycast.cu: streams, cubes and buffers of the scan pipeline (created on first use)
     // staging ring of r3d_backproject_rt with host buffers: per slot "input uploaded", "kernel done", "output read back"
     static constexpr int kMaxStageSlots = 4;
     cudaEvent_t ev_in[kMaxStageSlots] = {}, ev_k[kMaxStageSlots] = {}, ev_out[kMaxStageSlots] = {};
@@ -28,12 +30,7 @@ struct r3d_ctx {
     // reusable device scratch (grown on demand, freed in r3d_destroy)
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // direct-mapped scratch of the ray caster (dense mode): 32 mask words per brick cell + touched bitmap; zero between scans
-    uint32_t* cell_masks = nullptr;
-    uint32_t* cell_touched = nullptr;
-    uint64_t cell_cap = 0;
-    bool cells_dirty = false;
-    uint64_t cell_budget_bytes = 16ull << 30;   // larger grids use the hash table (R3D_SCAN_SCRATCH_GB overrides)
+    uint64_t cell_budget_bytes = 16ull << 30;   // cap of the ray caster's direct-mapped scratch (R3D_SCAN_SCRATCH_GB overrides)
     void* pinned = nullptr;          // small pinned mailbox for counters read back from the device
     size_t pinned_bytes = 0;
 };

@@ -1,7 +1,7 @@
 // r3d_context.cu -- context lifetime, error text, scratch memory, pointer classification.
 #include <stdlib.h>
 
-#include "r3d_common.cuh"
+#include "r3d_octree.cuh"
 
 namespace r3d {
 
@@ -134,8 +134,7 @@ extern "C" void r3d_destroy(r3d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < SCR_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
-    if (ctx->cell_masks) cudaFree(ctx->cell_masks);
-    if (ctx->cell_touched) cudaFree(ctx->cell_touched);
+    scan_pipe_destroy(ctx);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -146,8 +145,6 @@ extern "C" void r3d_destroy(r3d_ctx* ctx) {
         if (ctx->ev_k[s]) cudaEventDestroy(ctx->ev_k[s]);
         if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
     }
-    for (int s = 0; s < 2; ++s)
-        if (ctx->rc_stream[s]) cudaStreamDestroy(ctx->rc_stream[s]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -137,33 +137,16 @@ struct ScanArgs {
     uint32_t* smasks;   // per slot: 16 words occupied, 16 words free
     uint64_t scap;
     uint32_t* counters;
-    // dense mode (bounded reach): the masks are direct-mapped -- cell (cx, cy, cz) of a gdim^3 grid of bricks centred on
-    // the sensor origin owns words [32 * cell, 32 * cell + 32) of `cmasks`; `ctouched` has one bit per cell that holds
-    // anything, so that only touched cells are read back.  No lookup structure, no allocation, no dependent loads.
-    uint32_t* cmasks;
-    uint32_t* ctouched;
-    int gx0, gy0, gz0;  // brick coordinates of cell (0,0,0)
-    uint32_t gdim;      // cells per axis
-    uint32_t gcells;    // gdim^3
 };
 
-// computeUpdate (OccupancyOcTreeBase): per point, free cells along the ray, endpoint occupied when in range.
-//
-// Persistent warps; every lane walks one ray at a time and idle lanes are re-filled from a global ray counter as soon
-// as K3_REFILL_MIN of them are idle (rays of one image differ in length by orders of magnitude: sky pixels walk 0
-// cells, far ground pixels ~1000).  The walk is the branch-free form of computeRayKeys (r3d_math.cuh).  Free cells are
-// collected in a 64-bit register mask per 4x4x4 sub-block (the depth-14 node: 64 consecutive Morton voxels = one
-// aligned 64-bit word of the brick's free mask) and written with ONE red.or when the ray leaves the sub-block; the
-// word's current value is fetched (L2) when the ray enters the sub-block and only consulted when it leaves, so the load
-// latency overlaps the walk, and the atomic is skipped when every bit is already set (128 M visits -> 10 M distinct
-// cells per scan).  Different lanes cross sub-block and brick borders at different steps, so that bookkeeping is
-// written without divergent slow paths: some lane needs it on almost every iteration.
+// computeUpdate (OccupancyOcTreeBase) for an UNBOUNDED range (maxrange < 0), or a scan whose cube cannot be direct-mapped:
+// the masks of a brick sit in a per-scan hash table.  Bounded ranges -- every BASELINE configuration -- take the batched
+// direct-mapped pipeline of r3d_raycast.cu.  Persistent warps; every lane walks one ray at a time and idle lanes are
+// re-filled from a global ray counter as soon as K3_REFILL_MIN of them are idle.  The walk is the branch-free form of
+// computeRayKeys (r3d_math.cuh); free cells are collected in a 64-bit register mask per 4x4x4 sub-block (64 consecutive
+// Morton voxels = one aligned 64-bit word of the brick's free mask) and written with ONE red.or when the ray leaves it.
 constexpr int K3_THREADS = 256;
-#ifdef K3_REFILL_MIN_OVERRIDE
-constexpr int K3_REFILL_MIN = K3_REFILL_MIN_OVERRIDE;
-#else
 constexpr int K3_REFILL_MIN = 8;
-#endif
 
 __device__ __forceinline__ uint64_t ldcg_u64_if(const uint64_t* p, uint64_t otherwise, bool pred) {
     uint64_t v = otherwise;
@@ -177,242 +160,6 @@ __device__ __forceinline__ uint64_t sub_bit(int kx, int ky, int kz) {
     const unsigned x = kx & 3, y = ky & 3, z = kz & 3;
     const unsigned bit = (x & 1u) | ((y & 1u) << 1) | ((z & 1u) << 2) | ((x & 2u) << 2) | ((y & 2u) << 3) | ((z & 2u) << 4);
     return 1ull << bit;
-}
-
-// ---- dense mode
-__device__ __forceinline__ bool cell_of_key(const ScanArgs& a, int kx, int ky, int kz, uint32_t& cell) {
-    const uint32_t ux = (uint32_t)((kx >> 3) - a.gx0), uy = (uint32_t)((ky >> 3) - a.gy0), uz = (uint32_t)((kz >> 3) - a.gz0);
-    cell = (uz * a.gdim + uy) * a.gdim + ux;
-    return (ux < a.gdim) & (uy < a.gdim) & (uz < a.gdim);
-}
-
-#ifndef K3_VARIANT
-#define K3_VARIANT 1
-#endif
-// key += step and tMax += tDelta (round to nearest, no contraction) when axis == which, as predicated instructions: written
-// as C++ conditionals the compiler turns the three mutually exclusive updates into a chain of divergent branches
-__device__ __forceinline__ void step_axis_if(int axis, int which, int& k, int s, double& tm, double td) {
-    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.s32 %0, %0, %4;\n\t@p add.rn.f64 %1, %1, %5;\n\t}"
-        : "+r"(k), "+d"(tm) : "r"(axis), "r"(which), "r"(s), "d"(td));
-}
-// Per-lane state of the dense walker.
-struct DenseLane {
-    int kx, ky, kz, ex, ey, ez, sx, sy, sz;
-    double tmx, tmy, tmz, tdx, tdy, tdz, length;
-    int csx, csy, csz;   // cell-index change of one brick step along each axis
-    int axis;
-    int mx, my, mz;      // (K3_VARIANT 1) the axis of the next step as 0/1 integers
-    uint32_t cell;       // grid cell of the current brick
-    uint32_t widx;       // index of the current sub-block's free word in the 64-bit view of cmasks
-    uint64_t mask;       // cells of that sub-block visited by this ray
-    uint64_t seen;       // what the word held when the ray entered the sub-block; 0 = not known (yet)
-    unsigned age;        // iterations since the ray entered the sub-block (saturates at 3)
-    unsigned steps;
-};
-
-// One iteration of the walk for an active lane.  `stage` is the register the word fetched on entering a sub-block
-// lands in; the caller alternates between two of them, and a fetched word is moved into `seen` two iterations after
-// it was requested.  The warp therefore never waits on the load it has just issued (a scoreboard wait is warp-wide:
-// with ~28 active lanes some lane enters a sub-block on nearly every iteration), only on the one from two iterations
-// ago.  A ray that leaves a sub-block earlier publishes its cells without knowing the word (a redundant red.or).
-__device__ __forceinline__ bool dense_step(const ScanArgs& a, uint64_t* masks64, uint8_t* touched, DenseLane& L, uint64_t& stage) {
-    if (L.age == 1) L.seen = stage;      // requested two iterations ago, into this same register
-    // ---- one DDA step along the chosen axis (ray_advance), then pick the next axis (ray_select).
-#if K3_VARIANT == 2
-    // (candidate, not measured yet: built with -DK3_VARIANT=2)  The axis is carried as an integer; the three updates are
-    // written as conditional statements so that they compile to predicated DADD / IADD (no selects, no multiplies), and
-    // "min(tMax) > length" is evaluated as "every tMax > length": three chained compares on the fp64 pipe instead of a
-    // select tree on the ALU pipe (the minimum itself is never needed).
-    const bool ax = L.axis == 0, ay = L.axis == 1;
-    const int okx = L.kx, oky = L.ky, okz = L.kz;
-    step_axis_if(L.axis, 0, L.kx, L.sx, L.tmx, L.tdx);
-    step_axis_if(L.axis, 1, L.ky, L.sy, L.tmy, L.tdy);
-    step_axis_if(L.axis, 2, L.kz, L.sz, L.tmz, L.tdz);
-    const int cstep = ax ? L.csx : (ay ? L.csy : L.csz);
-    const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
-    const bool selx = xy & xz, sely = (!xy) & yz;
-    L.axis = selx ? 0 : (sely ? 1 : 2);
-    const bool past = (L.tmx > L.length) & (L.tmy > L.length) & (L.tmz > L.length);
-    const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | past;
-    const int diff = (L.kx ^ okx) | (L.ky ^ oky) | (L.kz ^ okz);
-#elif K3_VARIANT & 1
-    // The axis is carried as three 0/1 integers and applied by multiplication: selects run on the integer / select pipe,
-    // which bounds this kernel, multiplies on the FMA and fp64 pipes.  x * 1.0 and t + 0.0 are exact, so the tMax update
-    // tm + m * td is bit-identical to "tm + td on the chosen axis, untouched elsewhere".
-    const int okx = L.kx, oky = L.ky, okz = L.kz;
-    L.kx += L.mx * L.sx; L.ky += L.my * L.sy; L.kz += L.mz * L.sz;
-    const int cstep = L.mx * L.csx + L.my * L.csy + L.mz * L.csz;
-    L.tmx = dadd(L.tmx, dmul((double)L.mx, L.tdx));
-    L.tmy = dadd(L.tmy, dmul((double)L.my, L.tdy));
-    L.tmz = dadd(L.tmz, dmul((double)L.mz, L.tdz));
-    const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
-    const bool selx = xy & xz, sely = (!xy) & yz;
-    const double tsel = selx ? L.tmx : (sely ? L.tmy : L.tmz);
-    L.mx = selx ? 1 : 0; L.my = sely ? 1 : 0; L.mz = 1 - L.mx - L.my;
-    const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | (tsel > L.length);
-    const int diff = (L.kx ^ okx) | (L.ky ^ oky) | (L.kz ^ okz);
-#else
-    const bool ax = L.axis == 0, ay = L.axis == 1, az = L.axis == 2;
-    const double nx = dadd(L.tmx, L.tdx), ny = dadd(L.tmy, L.tdy), nz = dadd(L.tmz, L.tdz);
-    const int kold = ax ? L.kx : (ay ? L.ky : L.kz);
-    const int knew = kold + (ax ? L.sx : (ay ? L.sy : L.sz));
-    L.kx = ax ? knew : L.kx; L.ky = ay ? knew : L.ky; L.kz = az ? knew : L.kz;
-    L.tmx = ax ? nx : L.tmx; L.tmy = ay ? ny : L.tmy; L.tmz = az ? nz : L.tmz;
-    const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
-    const bool selx = xy & xz, sely = (!xy) & yz;
-    const double tsel = selx ? L.tmx : (sely ? L.tmy : L.tmz);
-    const int cstep = ax ? L.csx : (ay ? L.csy : L.csz);
-    L.axis = selx ? 0 : (sely ? 1 : 2);
-    const bool done = (((L.kx ^ L.ex) | (L.ky ^ L.ey) | (L.kz ^ L.ez)) == 0) | (tsel > L.length);
-    const int diff = knew ^ kold;            // only one coordinate moved
-#endif
-    const bool new_sub = (diff >> 2) != 0;
-    // ---- leaving the sub-block (or the ray): publish its cells unless all of them are known to be set
-    if ((done | new_sub) && (L.mask & ~L.seen) != 0) {
-        atomicOr(reinterpret_cast<unsigned long long*>(masks64 + L.widx), (unsigned long long)L.mask);
-        touched[L.widx >> 4] = 1;
-    }
-    // ---- entering the next one
-    const bool enter = new_sub & !done;
-    L.cell += (enter & ((diff >> 3) != 0)) ? (uint32_t)cstep : 0u;
-    if (enter) {
-        if (L.cell >= a.gcells) {          // memory-safety guard; the grid is sized so that it never trips
-            a.counters[CNT_GRID_MISS] = 1;
-            L.cell = 0;
-        }
-        L.widx = L.cell * 16u + 8u + sub_index(L.kx, L.ky, L.kz);
-        L.mask = 0;
-        L.seen = 0;
-    }
-    stage = ldcg_u64_if(masks64 + L.widx, stage, enter);
-    L.age = enter ? 0u : (L.age < 3u ? L.age + 1u : 3u);
-    L.mask |= sub_bit(L.kx, L.ky, L.kz);
-    L.steps += done ? 0u : 1u;
-    return !done;
-}
-
-__global__ void __launch_bounds__(K3_THREADS, 3) k_scan_raycast_dense(const ScanArgs a, unsigned long long* ray_counter, const uint32_t* abort_flag) {
-    if (__ldcg(abort_flag)) return;   // an earlier scan of the pipeline is waiting for the host: leave the scratch alone
-    const unsigned lane = threadIdx.x & 31u;
-    uint64_t* const masks64 = reinterpret_cast<uint64_t*>(a.cmasks);
-    uint8_t* const touched = reinterpret_cast<uint8_t*>(a.ctouched);
-    bool active = false, exhausted = false;
-    // (keys never wrap here: the host only picks this kernel when the whole grid lies inside the key range)
-    DenseLane L;
-    memset(&L, 0, sizeof L);
-    L.age = 3;
-    uint64_t stage_a = 0, stage_b = 0;
-    for (;;) {
-        const unsigned act = __ballot_sync(0xffffffffu, active);
-        const unsigned idle = ~act;
-        if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + __popc(idle) >= a.n) exhausted = true;
-            const unsigned long long i = base + __popc(idle & ((1u << lane) - 1u));
-            if (!active && i < a.n) {
-                const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
-                float fx, fy, fz;
-                const bool in_range = scan_point_end(a.ox, a.oy, a.oz, px, py, pz, a.maxrange, fx, fy, fz);
-                if (in_range) {
-                    uint16_t qx, qy, qz;
-                    if (coord_to_key3(a.res_factor, px, py, pz, qx, qy, qz)) {
-                        uint32_t c;
-                        if (cell_of_key(a, qx, qy, qz, c)) {
-                            const unsigned vox = brick_voxel_index(qx, qy, qz);
-                            uint32_t* w = a.cmasks + (size_t)c * 32 + (vox >> 5);
-                            const uint32_t bit = 1u << (vox & 31u);
-                            if (!(__ldcg(w) & bit)) {
-                                atomicOr(w, bit);
-                                touched[c] = 1;
-                            }
-                        } else {
-                            a.counters[CNT_GRID_MISS] = 1;
-                        }
-                    }
-                }
-                Ray r;
-                if (ray_setup(a.res, a.res_factor, a.ox, a.oy, a.oz, fx, fy, fz, r) == 1) {
-                    L.kx = r.kx; L.ky = r.ky; L.kz = r.kz; L.ex = r.ex; L.ey = r.ey; L.ez = r.ez; L.sx = r.sx; L.sy = r.sy; L.sz = r.sz;
-                    L.tmx = r.tmx; L.tmy = r.tmy; L.tmz = r.tmz; L.tdx = r.tdx; L.tdy = r.tdy; L.tdz = r.tdz;
-                    L.length = (double)r.length;
-                    L.csx = r.sx; L.csy = r.sy * (int)a.gdim; L.csz = r.sz * (int)(a.gdim * a.gdim);
-                    const bool ok = cell_of_key(a, L.kx, L.ky, L.kz, L.cell);
-                    if (!ok) a.counters[CNT_GRID_MISS] = 1;
-                    active = ok;
-                    // the origin cell is the first free cell; its word is read here (this path is long anyway)
-                    L.widx = (ok ? L.cell : 0u) * 16u + 8u + sub_index(L.kx, L.ky, L.kz);
-                    L.seen = ld_cg_u64(masks64 + L.widx);
-                    L.age = 3;
-                    L.mask = sub_bit(L.kx, L.ky, L.kz);
-                    ++L.steps;
-                    double t;
-                    L.axis = ray_select(r, t);
-                    L.mx = L.axis == 0; L.my = L.axis == 1; L.mz = L.axis == 2;
-                }
-            }
-            continue;
-        }
-        if (act == 0) break;   // no ray left anywhere in this warp
-        const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
-        do {
-            if (active) active = dense_step(a, masks64, touched, L, stage_a);
-            if (active) active = dense_step(a, masks64, touched, L, stage_b);
-        } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
-        // fetched words still on their way are dropped (their rays publish without them): the next round may start
-        // with either staging register
-        if (L.age < 2) L.age = 3;
-    }
-    // statistics only: free-cell visits of this scan
-    unsigned long long total = L.steps;
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(&a.counters[CNT_STEPS_LO]), total);
-}
-
-// dense mode read-back, step 1: list the touched cells (one byte per cell, four cells per thread and load)
-__global__ void k_cells_list(const uint32_t* __restrict__ touched, uint32_t n_words, uint32_t* list, uint32_t cap, uint32_t* counters,
-                             const uint32_t* abort_flag) {
-    if (__ldcg(abort_flag)) return;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += stride) {
-        const uint32_t w = touched[i];
-        if (!w) continue;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            if ((w >> (8 * b)) & 0xffu) {
-                const uint32_t q = atomicAdd(&counters[CNT_DELTA], 1u);
-                if (q < cap) list[q] = i * 4u + (uint32_t)b;
-            }
-        }
-    }
-}
-// step 2: one warp per listed cell -> record (free already minus occupied); clears the cell and its bit.  Does nothing
-// when the list overflowed (the host grows the buffers and runs both steps again: the masks are still intact).
-__global__ void __launch_bounds__(256) k_cells_emit(uint32_t* cmasks, uint8_t* touched, const uint32_t* __restrict__ list, uint32_t cap,
-                                                    const uint32_t* counters, DeltaRecord* out, int gx0, int gy0, int gz0, uint32_t gdim,
-                                                    uint32_t* abort_flag, int set_abort) {
-    if (__ldcg(abort_flag)) return;
-    const uint32_t n = counters[CNT_DELTA];
-    if (n > cap) {   // pipelined use: stop every queued scan kernel until the host has grown the buffers and listed again
-        if (set_abort && blockIdx.x == 0 && threadIdx.x == 0) atomicExch(abort_flag, 1u);
-        return;
-    }
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += warps) {
-        const uint32_t cell = list[q];
-        uint32_t w = cmasks[(size_t)cell * 32 + lane];
-        const uint32_t occ_w = __shfl_sync(0xffffffffu, w, lane & 15u);
-        if (lane >= 16) w &= ~occ_w;   // occupied wins
-        if (lane == 0) {
-            const uint32_t cx = cell % gdim, cy = (cell / gdim) % gdim, cz = cell / (gdim * gdim);
-            out[q].key = (uint64_t)(uint32_t)(gx0 + (int)cx) | ((uint64_t)(uint32_t)(gy0 + (int)cy) << 13) | ((uint64_t)(uint32_t)(gz0 + (int)cz) << 26);
-            touched[cell] = 0;
-        }
-        out[q].mask[lane] = w;
-        cmasks[(size_t)cell * 32 + lane] = 0;
-    }
 }
 
 // ---- hash mode
@@ -732,7 +479,7 @@ __global__ void __launch_bounds__(256) k_import_bricks(const BrickRecord* __rest
 }
 
 // ------------------------------------------------------------------ host side: memory management
-static unsigned grid_for(r3d_ctx* ctx, unsigned long long items, int block = 256, int per_sm = 8) {
+unsigned grid_for(r3d_ctx* ctx, unsigned long long items, int block, int per_sm) {
     unsigned long long b = (items + block - 1) / block;
     const unsigned long long cap = (unsigned long long)ctx->sm_count * per_sm;
     if (b > cap) b = cap;
@@ -830,15 +577,14 @@ static int tree_reserve_scratch(r3d_tree* t, uint64_t want_slots) {
     uint64_t need = 1ull << 17;
     while (need < want_slots) need <<= 1;
     if (need <= t->scap) return R3D_OK;
-    cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta);
-    t->skeys = nullptr; t->smasks = nullptr; t->delta = nullptr; t->scap = 0;
+    R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(t->skeys); cudaFree(t->smasks);
+    t->skeys = nullptr; t->smasks = nullptr; t->scap = 0;
     R3D_CUDA_OK(ctx, cudaMalloc(&t->skeys, need * sizeof(uint64_t)));
     R3D_CUDA_OK(ctx, cudaMalloc(&t->smasks, need * 32 * sizeof(uint32_t)));
-    R3D_CUDA_OK(ctx, cudaMalloc(&t->delta, (need / 2 + 1) * sizeof(DeltaRecord)));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->skeys, 0xff, need * sizeof(uint64_t), ctx->stream));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->smasks, 0, need * 32 * sizeof(uint32_t), ctx->stream));
     t->scap = need;
-    t->delta_cap = need / 2 + 1;
     return R3D_OK;
 }
 
@@ -909,56 +655,7 @@ static int update_points_impl(r3d_tree* t, const T* xyz, uint64_t n, float upd, 
     return finish(ctx);
 }
 
-// Grid geometry of the dense mode: a cube of (2*reach+1)^3 bricks centred on the origin's brick, reach = maxrange plus
-// a margin (every visited voxel contains a point of the ray no farther than the ray length from the origin; the margin
-// is 4 voxels + 2 bricks).  Returns non-zero when the scan cannot use it -- unbounded range, scratch over budget, origin
-// not finite, or the cube not completely inside the key range (keys would wrap like upstream's uint16) -- and the hash
-// table serves those.
-static int dense_grid_geometry(r3d_tree* t, const float origin[3], double maxrange, int* gx0, int* gy0, int* gz0, uint32_t* gdim) {
-    if (!(maxrange >= 0.0)) return 1;
-    const double reach_vox = ceil(maxrange * t->res_factor) + 4.0;
-    if (!(reach_vox < 8.0 * 4000.0)) return 1;
-    const int reach = (int)(reach_vox / 8.0) + 2;
-    const uint64_t g = (uint64_t)(2 * reach + 1);
-    if (g * g * g * 128ull > t->ctx->cell_budget_bytes || g * g * g > (1ull << 27)) return 1;
-    int o[3];
-    for (int i = 0; i < 3; ++i) {
-        const double f = floor(t->res_factor * (double)origin[i]);
-        if (!(f >= -32768.0 && f < 32768.0)) return 1;
-        o[i] = (((int)f + r3d::kTreeMaxVal) >> 3) - reach;
-        if (o[i] < 0 || o[i] + (int)g > 8192) return 1;
-    }
-    *gx0 = o[0]; *gy0 = o[1]; *gz0 = o[2];
-    *gdim = (uint32_t)g;
-    return 0;
-}
-
-// direct-mapped scan scratch of the context: `cells` x (32 mask words) + touched bitmap, all zero between scans
-static int ctx_reserve_cells(r3d_ctx* ctx, uint64_t cells) {
-    if (cells <= ctx->cell_cap && !ctx->cells_dirty) return R3D_OK;
-    if (cells > ctx->cell_cap) {
-        R3D_CUDA_OK(ctx, cudaDeviceSynchronize());
-        cudaFree(ctx->cell_masks); cudaFree(ctx->cell_touched);
-        ctx->cell_masks = nullptr; ctx->cell_touched = nullptr; ctx->cell_cap = 0;
-        cudaError_t e = cudaMalloc(&ctx->cell_masks, cells * 128);
-        if (e == cudaSuccess) e = cudaMalloc(&ctx->cell_touched, (cells / 4 + 1) * 4);   // one byte per cell
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            cudaFree(ctx->cell_masks); ctx->cell_masks = nullptr;
-            return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(%llu MB of scan scratch) failed: %s", (unsigned long long)(cells * 128 >> 20), cudaGetErrorString(e));
-        }
-        ctx->cell_cap = cells;
-        ctx->cells_dirty = true;
-    }
-    if (ctx->cells_dirty) {   // fresh memory, or a scan that was abandoned half-way
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->cell_masks, 0, ctx->cell_cap * 128, ctx->stream));
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(ctx->cell_touched, 0, (ctx->cell_cap / 4 + 1) * 4, ctx->stream));
-        ctx->cells_dirty = false;
-    }
-    return R3D_OK;
-}
-
-static int tree_reserve_delta(r3d_tree* t, uint64_t want) {
+int tree_reserve_delta(r3d_tree* t, uint64_t want) {
     r3d_ctx* ctx = t->ctx;
     if (want <= t->delta_cap) return R3D_OK;
     R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -969,266 +666,18 @@ static int tree_reserve_delta(r3d_tree* t, uint64_t want) {
     return R3D_OK;
 }
 
-static unsigned raycast_blocks(r3d_tree* t, unsigned long long n_rays) {
-    r3d_ctx* ctx = t->ctx;
-    if (t->raycast_blocks_per_sm == 0) {
-        int a = 0, b = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_scan_raycast_dense, K3_THREADS, 0);
+static unsigned raycast_blocks(r3d_tree* t) {
+    if (t->raycast_blocks_per_sm_hash == 0) {
+        int b = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_scan_raycast_hash, K3_THREADS, 0);
-        t->raycast_blocks_per_sm = a < 1 ? 1 : a;
         t->raycast_blocks_per_sm_hash = b < 1 ? 1 : b;
     }
-    (void)ctx;
-    return 0;
+    return (unsigned)t->raycast_blocks_per_sm_hash;
 }
 
-// dense mode: rays -> direct-mapped masks -> records.  Returns R3D_OK with *fallback = true when the hash path must
-// take over (a ray left the grid: cannot happen by construction, kept as a safety net).
-static int scan_delta_dense(r3d_tree* t, const ScanArgs& a0, bool* fallback) {
-    r3d_ctx* ctx = t->ctx;
-    ScanArgs a = a0;
-    *fallback = false;
-    R3D_TRY(ctx_reserve_cells(ctx, a.gcells));
-    a.cmasks = ctx->cell_masks;
-    a.ctouched = ctx->cell_touched;
-    if (t->delta_cap < (1u << 16)) R3D_TRY(tree_reserve_delta(t, 1u << 16));
-    ctx->cells_dirty = true;     // until the read-back below has cleaned up
-    if (a.n) {
-        unsigned long long* ray_counter = reinterpret_cast<unsigned long long*>(&t->counters[CNT_RAY_LO]);   // zeroed by the caller
-        raycast_blocks(t, a.n);
-        unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
-        const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
-        if (blocks > need) blocks = need;
-        cudaEventRecord(ctx->ev_a, ctx->stream);
-        k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter, t->counters + CNT_ABORT);
-        cudaEventRecord(ctx->ev_b, ctx->stream);
-        ctx->launches++;
-    }
-    const uint32_t n_words = a.gcells / 4 + 1;
-    for (int attempt = 0; attempt < 8; ++attempt) {
-        R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)t->delta_cap * 4 + 256));
-        if (attempt) R3D_TRY(tree_set_counter(t, CNT_DELTA, 0));
-        k_cells_list<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(a.ctouched, n_words, (uint32_t*)ctx->scratch[SCR_TILE],
-                                                                              (uint32_t)t->delta_cap, t->counters, t->counters + CNT_ABORT);
-        k_cells_emit<<<grid_for(ctx, (uint64_t)t->delta_cap * 32, 256, 8), 256, 0, ctx->stream>>>(
-            a.cmasks, reinterpret_cast<uint8_t*>(a.ctouched), (const uint32_t*)ctx->scratch[SCR_TILE], (uint32_t)t->delta_cap, t->counters, t->delta, a.gx0, a.gy0, a.gz0, a.gdim,
-            t->counters + CNT_ABORT, 0);
-        ctx->launches += 2;
-        R3D_CUDA_OK(ctx, cudaGetLastError());
-        R3D_TRY(tree_sync_counters(t));
-        if (t->h_counters[CNT_DELTA] <= t->delta_cap) {
-            ctx->cells_dirty = false;
-            if (a.n && attempt == 0) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);   // the read-back above fenced both
-            if (t->h_counters[CNT_GRID_MISS]) { *fallback = true; return R3D_OK; }   // records discarded, scratch clean
-            t->delta_n = t->h_counters[CNT_DELTA];
-            return R3D_OK;
-        }
-        R3D_TRY(tree_reserve_delta(t, (uint64_t)t->h_counters[CNT_DELTA] * 2));   // list overflow: masks untouched, list again
-    }
-    return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the record buffer");
-}
-
-static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1);
-
-// ---- two-deep scan pipeline (dense mode, device-resident scans): scan s+1 is queued -- ray cast, cell list, records,
-// counter read-back -- before the host waits for scan s's counters and queues its apply, so the GPU never idles on the
-// host's turnaround.  Each slot has its own counters, cell list and record buffer; the cell scratch is shared (scan
-// s's emit clears it before scan s+1's ray cast starts, in stream order).  If a scan's records do not fit, its emit
-// sets the sticky abort flag instead of touching anything and every later queued kernel skips; the host then grows the
-// buffers, clears the flag, lists / emits again and re-queues what was skipped.
-static int pipe_reserve(r3d_tree* t, uint64_t cap) {
-    r3d_ctx* ctx = t->ctx;
-    if (!t->pipe_counters) {
-        R3D_CUDA_OK(ctx, cudaMalloc(&t->pipe_counters, 2 * CNT_COUNT * sizeof(uint32_t)));
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->pipe_counters, 0, 2 * CNT_COUNT * sizeof(uint32_t), ctx->stream));
-        for (int i = 0; i < 2; ++i) {
-            R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_done[i], cudaEventDisableTiming));
-            R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->rc_done[i], cudaEventDisableTiming));
-        }
-        R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->pipe_start, cudaEventDisableTiming));
-        if (const char* v = getenv("R3D_PIPE_OVERLAP")) t->pipe_overlap = atoi(v) != 0;
-    }
-    // the ray-cast streams belong to the context (creating a stream costs milliseconds; trees come and go)
-    for (int i = 0; i < 2; ++i)
-        if (!ctx->rc_stream[i]) R3D_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->rc_stream[i], cudaStreamNonBlocking));
-    if (t->delta_cap < cap) R3D_TRY(tree_reserve_delta(t, cap));
-    if (t->delta_b_cap < t->delta_cap) {
-        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(t->delta_b);
-        t->delta_b = nullptr; t->delta_b_cap = 0;
-        R3D_CUDA_OK(ctx, cudaMalloc(&t->delta_b, t->delta_cap * sizeof(DeltaRecord)));
-        t->delta_b_cap = t->delta_cap;
-    }
-    if (t->pipe_list_cap < t->delta_cap) {
-        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(t->pipe_list);
-        t->pipe_list = nullptr; t->pipe_list_cap = 0;
-        R3D_CUDA_OK(ctx, cudaMalloc(&t->pipe_list, 2 * t->delta_cap * sizeof(uint32_t)));
-        t->pipe_list_cap = t->delta_cap;
-    }
-    return R3D_OK;
-}
-
-struct PipeScan {
-    ScanArgs a;
-    bool timed;
-    bool overlap;    // ray cast on the slot's own stream (the scan has its own cell cube)
-};
-
-static int pipe_enqueue(r3d_tree* t, const PipeScan& ps, int slot, bool cast) {
-    r3d_ctx* ctx = t->ctx;
-    uint32_t* cnt = t->pipe_counters + slot * CNT_COUNT;
-    ScanArgs a = ps.a;
-    a.counters = cnt;
-    uint32_t* abort_flag = t->counters + CNT_ABORT;
-    if (cast) {
-        cudaStream_t rs = ctx->stream;
-        if (ps.overlap) {
-            // the slot's stream starts after the batch's set-up and after the slot's previous scan has been emitted and its
-            // counters read back (that scan used the same cube, counters and mailbox)
-            rs = ctx->rc_stream[slot];
-            R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, t->pipe_start, 0));
-            if (t->pipe_done_valid[slot]) R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, t->pipe_done[slot], 0));
-        }
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt, 0, CNT_COUNT * sizeof(uint32_t), rs));
-        if (a.n) {
-            raycast_blocks(t, a.n);
-            unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm;
-            const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
-            if (blocks > need) blocks = need;
-            if (ps.timed) cudaEventRecord(ctx->ev_a, rs);
-            k_scan_raycast_dense<<<(unsigned)blocks, K3_THREADS, 0, rs>>>(a, reinterpret_cast<unsigned long long*>(cnt + CNT_RAY_LO), abort_flag);
-            if (ps.timed) cudaEventRecord(ctx->ev_b, rs);
-            ctx->launches++;
-        }
-        if (ps.overlap) {
-            R3D_CUDA_OK(ctx, cudaEventRecord(t->rc_done[slot], rs));
-            R3D_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, t->rc_done[slot], 0));
-        }
-    } else {
-        R3D_CUDA_OK(ctx, cudaMemsetAsync(cnt + CNT_DELTA, 0, sizeof(uint32_t), ctx->stream));
-    }
-    const uint32_t n_words = a.gcells / 4 + 1;
-    uint32_t* list = t->pipe_list + (size_t)slot * t->pipe_list_cap;
-    DeltaRecord* out = slot ? t->delta_b : t->delta;
-    k_cells_list<<<grid_for(ctx, n_words, 256, 8), 256, 0, ctx->stream>>>(a.ctouched, n_words, list, (uint32_t)t->delta_cap, cnt, abort_flag);
-    k_cells_emit<<<grid_for(ctx, (uint64_t)t->delta_cap * 32, 256, 8), 256, 0, ctx->stream>>>(
-        a.cmasks, reinterpret_cast<uint8_t*>(a.ctouched), list, (uint32_t)t->delta_cap, cnt, out, a.gx0, a.gy0, a.gz0, a.gdim, abort_flag, 1);
-    ctx->launches += 2;
-    R3D_CUDA_OK(ctx, cudaGetLastError());
-    R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)ctx->pinned + 1024 + 256 * slot, cnt, CNT_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    // the pool cursor as of this point of the stream (= after every apply queued before this scan): keeps the host's
-    // upper bound of it tight without a synchronising read-back
-    R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)ctx->pinned + 1024 + 256 * slot + 128, t->counters + CNT_POOL_USED, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_done[slot], ctx->stream));
-    t->pipe_done_valid[slot] = true;
-    return R3D_OK;
-}
-
-// Returns the number of scans fully inserted; fewer than n_scans means "continue with the serial path from there".
-static int insert_scans_pipelined(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans,
-                                  double maxrange, uint32_t* done_out, uint64_t* rays_out, uint64_t* steps_out) {
-    r3d_ctx* ctx = t->ctx;
-    *done_out = 0;
-    std::vector<PipeScan> scans(n_scans);
-    uint64_t off = 0;
-    uint32_t gcells_max = 0;
-    for (uint32_t s = 0; s < n_scans; ++s) {
-        ScanArgs& a = scans[s].a;
-        memset(&a, 0, sizeof a);
-        int gx0, gy0, gz0;
-        uint32_t gdim;
-        if (n_points[s] > 0xfffffff0ull || dense_grid_geometry(t, origins + 3 * (size_t)s, maxrange, &gx0, &gy0, &gz0, &gdim) != 0) return R3D_OK;   // serial path decides
-        a.xyz = d_xyz + off * 3; a.n = n_points[s];
-        a.ox = origins[3 * s]; a.oy = origins[3 * s + 1]; a.oz = origins[3 * s + 2];
-        a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
-        a.gx0 = gx0; a.gy0 = gy0; a.gz0 = gz0; a.gdim = gdim; a.gcells = gdim * gdim * gdim;
-        if (a.gcells > gcells_max) gcells_max = a.gcells;
-        scans[s].timed = s + 1 == n_scans;
-        off += n_points[s];
-    }
-    R3D_TRY(pipe_reserve(t, t->delta_cap < (1u << 16) ? (1u << 16) : t->delta_cap));
-    // two cell cubes (one per pipeline slot) when the scratch budget allows: the next scan's ray cast then overlaps this
-    // scan's tail, list, emit and apply
-    const uint64_t cube_cells = ((uint64_t)gcells_max / 4 + 1) * 4;
-    const bool overlap = t->pipe_overlap && n_scans > 1 && 2 * cube_cells * 128ull <= ctx->cell_budget_bytes;
-    R3D_TRY(ctx_reserve_cells(ctx, overlap ? 2 * cube_cells : gcells_max));
-    R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
-    for (uint32_t s = 0; s < n_scans; ++s) {
-        const uint64_t cube = overlap ? (uint64_t)(s & 1u) * cube_cells : 0;
-        scans[s].a.cmasks = ctx->cell_masks + cube * 32;
-        scans[s].a.ctouched = ctx->cell_touched + cube / 4;
-        scans[s].overlap = overlap;
-    }
-    ctx->cells_dirty = true;
-    if (overlap) {
-        R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_start, ctx->stream));   // cubes cleared, abort flag reset, scans resident
-        t->pipe_done_valid[0] = t->pipe_done_valid[1] = false;
-    }
-    auto now_ns = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; };
-    t->pipe_wait_ns = t->pipe_work_ns = t->pipe_max_turn_ns = t->pipe_scans = 0;
-    uint64_t t_mark = now_ns();
-    R3D_TRY(pipe_enqueue(t, scans[0], 0, true));
-    uint64_t prev_records = 0;      // records of the apply queued last (not yet reflected in the cursor read back below)
-    for (uint32_t s = 0; s < n_scans; ++s) {
-        const int slot = (int)(s & 1u);
-        if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
-        uint32_t hc[CNT_COUNT];
-        for (int attempt = 0;; ++attempt) {
-            const uint64_t t_wait = now_ns();
-            R3D_CUDA_OK(ctx, cudaEventSynchronize(t->pipe_done[slot]));
-            const uint64_t t_got = now_ns();
-            t->pipe_work_ns += t_wait - t_mark;
-            if (t_wait - t_mark > t->pipe_max_turn_ns) t->pipe_max_turn_ns = t_wait - t_mark;
-            t->pipe_wait_ns += t_got - t_wait;
-            t_mark = t_got;
-            memcpy(hc, (char*)ctx->pinned + 1024 + 256 * slot, sizeof hc);
-            if (hc[CNT_DELTA] <= t->delta_cap) break;
-            if (attempt >= 8) return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the record buffer");
-            // records of scan s did not fit: nothing after its list kernel has run (abort flag).  Grow, clear, list again,
-            // and queue scan s+1 again.
-            R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-            if (overlap) {   // a ray cast that started before the flag was raised may still be running
-                R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->rc_stream[0]));
-                R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->rc_stream[1]));
-            }
-            R3D_TRY(pipe_reserve(t, (uint64_t)hc[CNT_DELTA] * 2));   // the other slot's records were applied already
-            R3D_CUDA_OK(ctx, cudaMemsetAsync(t->counters + CNT_ABORT, 0, sizeof(uint32_t), ctx->stream));
-            if (overlap) R3D_CUDA_OK(ctx, cudaEventRecord(t->pipe_start, ctx->stream));   // ray casts queued from here on see the cleared flag
-            R3D_TRY(pipe_enqueue(t, scans[s], slot, false));
-            if (s + 1 < n_scans) R3D_TRY(pipe_enqueue(t, scans[s + 1], slot ^ 1, true));
-        }
-        if (hc[CNT_GRID_MISS]) {
-            // cannot happen by construction; hand the rest (from this scan on) to the serial path, which falls back to the hash table
-            R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->cells_dirty = false;   // both queued scans have been emitted: the scratch is clean
-            return R3D_OK;
-        }
-        {   // scan s's read-back was queued after apply(s-2) and before apply(s-1)
-            uint32_t cursor;
-            memcpy(&cursor, (char*)ctx->pinned + 1024 + 256 * slot + 128, sizeof cursor);
-            const uint64_t tight = (uint64_t)cursor + prev_records;
-            if (tight < t->pool_bound) t->pool_bound = tight;
-        }
-        R3D_TRY(apply_delta_impl(t, slot ? t->delta_b : t->delta, hc[CNT_DELTA]));
-        prev_records = hc[CNT_DELTA];
-        *rays_out += scans[s].a.n;
-        *steps_out += (uint64_t)hc[CNT_STEPS_LO] | ((uint64_t)hc[CNT_STEPS_HI] << 32);
-        t->delta_n = hc[CNT_DELTA];
-        *done_out = s + 1;
-        t->pipe_scans = s + 1;
-        if (scans[s].timed && scans[s].a.n) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b);
-    }
-    if ((n_scans & 1u) == 0u) {   // the last scan used slot 1: keep t->delta = "records of the last scan"
-        DeltaRecord* tmp = t->delta; t->delta = t->delta_b; t->delta_b = tmp;
-        const uint64_t c = t->delta_cap; t->delta_cap = t->delta_b_cap; t->delta_b_cap = c;
-    }
-    ctx->cells_dirty = false;
-    return R3D_OK;
-}
-
-// ray-cast one scan into the scratch table and compact it into t->delta (t->delta_n records)
-static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const float origin[3], double maxrange, int discretize) {
+// ray-cast one scan into t->delta (t->delta_n records).  Bounded range: the direct-mapped pipeline (a batch of one);
+// unbounded range, or a cube that cannot be direct-mapped: the per-scan hash table.
+static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const float origin[3], double maxrange, int discretize, bool allow_dense = true) {
     r3d_ctx* ctx = t->ctx;
     if ((!xyz && n) || !origin) return set_error(ctx, R3D_ERR_ARG, "null scan buffer");
     if (n > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "scan too large");
@@ -1240,9 +689,7 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
     a.ox = origin[0]; a.oy = origin[1]; a.oz = origin[2];
     a.maxrange = maxrange; a.res = t->res; a.res_factor = t->res_factor;
     a.counters = t->counters;
-    int gx0 = 0, gy0 = 0, gz0 = 0;
-    uint32_t gdim = 0;
-    bool dense = dense_grid_geometry(t, origin, maxrange, &gx0, &gy0, &gz0, &gdim) == 0;
+    bool dense = allow_dense && maxrange >= 0.0;
     if (!dense || discretize) R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
     for (int attempt = 0; attempt < 14; ++attempt) {
         a.xyz = d; a.n = n;
@@ -1261,29 +708,32 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
             a.n = t->h_counters[CNT_DISCRETE];
         }
         if (!overflow && dense) {
-            a.gx0 = gx0; a.gy0 = gy0; a.gz0 = gz0; a.gdim = gdim; a.gcells = gdim * gdim * gdim;
-            bool fallback = false;
-            R3D_TRY(scan_delta_dense(t, a, &fallback));
-            if (!fallback) {
+            ScanSink sink;
+            sink.mode = ScanSink::EXPORT_TREE;
+            uint32_t done = 0;
+            uint64_t rays = 0, steps = 0, n1 = a.n;
+            R3D_TRY(dense_scans_run(t, a.xyz, &n1, origin, 1, maxrange, &sink, &done, &rays, &steps));
+            if (done == 1) {
+                R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // the staging buffers of a host scan are reused by the next call
                 t->last_scan_rays = a.n;
-                t->last_scan_steps = (uint64_t)t->h_counters[CNT_STEPS_LO] | ((uint64_t)t->h_counters[CNT_STEPS_HI] << 32);
+                t->last_scan_steps = steps;
                 return R3D_OK;
             }
-            dense = false;
+            dense = false;   // cannot be direct-mapped (key-space border, scratch budget): the hash table serves it
             R3D_TRY(tree_reserve_scratch(t, t->scap ? t->scap : (1ull << 18)));
             continue;
         }
         if (!overflow && a.n) {
             // persistent warps pulling rays from a counter (slot CNT_RAY_LO/HI of the tree's counter block, zeroed above)
             unsigned long long* ray_counter = reinterpret_cast<unsigned long long*>(&t->counters[CNT_RAY_LO]);
-            raycast_blocks(t, a.n);
-            unsigned long long blocks = (unsigned long long)ctx->sm_count * t->raycast_blocks_per_sm_hash;
+            unsigned long long blocks = (unsigned long long)ctx->sm_count * raycast_blocks(t);
             const unsigned long long need = (a.n + K3_THREADS - 1) / K3_THREADS;
             if (blocks > need) blocks = need;
             k_scan_raycast_hash<<<(unsigned)blocks, K3_THREADS, 0, ctx->stream>>>(a, ray_counter);
             ctx->launches++;
         }
         if (!overflow) {
+            if (t->delta_cap < t->scap / 2 + 1) R3D_TRY(tree_reserve_delta(t, t->scap / 2 + 1));
             k_scan_compact<<<grid_for(ctx, t->scap * 32, 256, 8), 256, 0, ctx->stream>>>(t->skeys, t->smasks, t->scap, t->delta, t->counters,
                                                                                       (uint32_t)t->delta_cap);
             ctx->launches++;
@@ -1304,13 +754,19 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
     return set_error(ctx, R3D_ERR_OOM, "scan delta does not fit the scratch table");
 }
 
-static int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part, uint32_t nparts) {
+int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part, uint32_t nparts) {
     r3d_ctx* ctx = t->ctx;
     if (n == 0) return R3D_OK;
     // sized from the host-side upper bound of the pool cursor: no read-back between a scan's apply and the next scan.
     // When the BOUND (not necessarily the pool) would outgrow the capacity, read the exact cursor back first: several
     // applies in a row (multi-GPU rounds) inflate the bound by every record, most of which hit existing bricks.
-    if (t->pool_dirty && t->pool_bound + n > t->pool_cap) R3D_TRY(tree_settle(t));
+    if (t->pool_dirty && t->pool_bound + n > t->pool_cap) {
+        R3D_TRY(tree_settle(t));
+        // the exact cursor is known now; leave room for several deltas of this size, so that the next applies neither wait
+        // for a read-back nor regrow (a regrowth copies the pool)
+        R3D_TRY(tree_reserve_table(t, t->pool_bound + 8 * n));
+        R3D_TRY(tree_reserve_pool(t, t->pool_bound + 8 * n));
+    }
     R3D_TRY(tree_reserve_table(t, t->pool_bound + n));
     R3D_TRY(tree_reserve_pool(t, t->pool_bound + n));
     k_apply_delta<<<grid_for(ctx, n * 32, 256, 8), 256, 0, ctx->stream>>>(d_recs, (uint32_t)n, t->tkeys, t->tvals, t->tcap, t->values, t->known,
@@ -1357,13 +813,6 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
-    cudaFree(t->delta_b); cudaFree(t->pipe_counters); cudaFree(t->pipe_list);
-    for (int i = 0; i < 2; ++i) {
-        if (t->ctx->rc_stream[i]) cudaStreamSynchronize(t->ctx->rc_stream[i]);
-        if (t->pipe_done[i]) cudaEventDestroy(t->pipe_done[i]);
-        if (t->rc_done[i]) cudaEventDestroy(t->rc_done[i]);
-    }
-    if (t->pipe_start) cudaEventDestroy(t->pipe_start);
     delete t;
 }
 
@@ -1520,6 +969,48 @@ extern "C" int r3d_tree_insert_scan(r3d_tree* t, const float* xyz, uint64_t n, c
     return finish(t->ctx);
 }
 
+// Serial remainder of a batch call: scans the pipeline cannot take (unbounded range, host buffers, discretize, a cube that
+// cannot be direct-mapped), interleaved with pipelined runs of the scans it can.
+static int scans_run(r3d_tree* t, const float* xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans, double maxrange,
+                     int discretize, ScanSink* sink, uint64_t* rays_out, uint64_t* steps_out) {
+    r3d_ctx* ctx = t->ctx;
+    const bool pipelined = !discretize && maxrange >= 0.0 && xyz && is_device_ptr(xyz);
+    uint64_t off = 0;
+    uint32_t s = 0;
+    while (s < n_scans) {
+        if (pipelined) {
+            uint32_t done = 0;
+            ScanSink sub = *sink;
+            if (sub.counts) sub.counts += s;
+            R3D_TRY(dense_scans_run(t, xyz + off * 3, n_points + s, origins + 3 * (size_t)s, n_scans - s, maxrange, &sub, &done, rays_out, steps_out));
+            sink->used = sub.used;
+            for (uint32_t k = 0; k < done; ++k) off += n_points[s + k];
+            s += done;
+            if (s >= n_scans) break;
+        }
+        // one scan through the serial path (hash table when it must be)
+        R3D_TRY(scan_delta_impl(t, xyz ? xyz + off * 3 : nullptr, n_points[s], origins + 3 * (size_t)s, maxrange, discretize, !pipelined));   // (the pipeline has just declined this scan: hash table)
+        if (sink->mode == ScanSink::APPLY) {
+            R3D_TRY(apply_delta_impl(t, t->delta, t->delta_n));
+        } else if (sink->mode == ScanSink::EXPORT_USER) {
+            sink->counts[s] = t->delta_n;
+            if (sink->used + t->delta_n > sink->capacity) {
+                for (uint32_t r = s + 1; r < n_scans; ++r) sink->counts[r] = 0;
+                return set_error(ctx, R3D_ERR_OOM, "record buffer holds %llu records, scan %u needs %llu in total so far",
+                                 (unsigned long long)sink->capacity, s, (unsigned long long)(sink->used + t->delta_n));
+            }
+            if (t->delta_n)
+                R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)sink->records + sink->used * sizeof(DeltaRecord), t->delta, t->delta_n * sizeof(DeltaRecord), cudaMemcpyDefault, ctx->stream));
+            sink->used += t->delta_n;
+        }
+        *rays_out += t->last_scan_rays;
+        *steps_out += t->last_scan_steps;
+        off += n_points[s];
+        ++s;
+    }
+    return R3D_OK;
+}
+
 extern "C" int r3d_tree_insert_scans(r3d_tree* t, const float* xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans,
                                      double maxrange, int discretize) {
     if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
@@ -1527,19 +1018,10 @@ extern "C" int r3d_tree_insert_scans(r3d_tree* t, const float* xyz, const uint64
     if (n_scans && (!n_points || !origins)) return set_error(ctx, R3D_ERR_ARG, "null scan table");
     if (is_device_ptr(n_points) || is_device_ptr(origins)) return set_error(ctx, R3D_ERR_ARG, "n_points / origins must be host arrays");
     DeviceSetter ds(ctx->device);
-    uint64_t off = 0, rays = 0, steps = 0;
-    uint32_t first = 0;
-    if (n_scans > 1 && !discretize && maxrange >= 0.0 && xyz && is_device_ptr(xyz)) {
-        R3D_TRY(insert_scans_pipelined(t, xyz, n_points, origins, n_scans, maxrange, &first, &rays, &steps));
-        for (uint32_t s = 0; s < first; ++s) off += n_points[s];
-    }
-    for (uint32_t s = first; s < n_scans; ++s) {
-        R3D_TRY(scan_delta_impl(t, xyz ? xyz + off * 3 : nullptr, n_points[s], origins + 3 * (size_t)s, maxrange, discretize));
-        R3D_TRY(apply_delta_impl(t, t->delta, t->delta_n));
-        off += n_points[s];
-        rays += t->last_scan_rays;
-        steps += t->last_scan_steps;
-    }
+    uint64_t rays = 0, steps = 0;
+    ScanSink sink;
+    sink.mode = ScanSink::APPLY;
+    R3D_TRY(scans_run(t, xyz, n_points, origins, n_scans, maxrange, discretize, &sink, &rays, &steps));
     t->last_scan_rays = rays;       // totals of the batch
     t->last_scan_steps = steps;
     return finish(ctx);
@@ -1551,21 +1033,13 @@ extern "C" int r3d_scan_deltas_compute(r3d_tree* t, const float* xyz, const uint
     r3d_ctx* ctx = t->ctx;
     if (n_scans && (!n_points || !origins || !counts)) return set_error(ctx, R3D_ERR_ARG, "null scan table");
     DeviceSetter ds(ctx->device);
-    uint64_t off = 0, used = 0;
-    for (uint32_t s = 0; s < n_scans; ++s) {
-        R3D_TRY(scan_delta_impl(t, xyz ? xyz + off * 3 : nullptr, n_points[s], origins + 3 * (size_t)s, maxrange, discretize));
-        off += n_points[s];
-        counts[s] = t->delta_n;
-        if (used + t->delta_n > capacity_records) {
-            // report what is needed so far; the caller grows the buffer and calls again from scan s
-            for (uint32_t r = s + 1; r < n_scans; ++r) counts[r] = 0;
-            return set_error(ctx, R3D_ERR_OOM, "record buffer holds %llu records, scan %u needs %llu in total so far",
-                             (unsigned long long)capacity_records, s, (unsigned long long)(used + t->delta_n));
-        }
-        if (t->delta_n)
-            R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)records + used * sizeof(DeltaRecord), t->delta, t->delta_n * sizeof(DeltaRecord), cudaMemcpyDefault, ctx->stream));
-        used += t->delta_n;
-    }
+    uint64_t rays = 0, steps = 0;
+    ScanSink sink;
+    sink.mode = ScanSink::EXPORT_USER;
+    sink.records = records; sink.capacity = capacity_records; sink.counts = counts;
+    R3D_TRY(scans_run(t, xyz, n_points, origins, n_scans, maxrange, discretize, &sink, &rays, &steps));
+    t->last_scan_rays = rays;
+    t->last_scan_steps = steps;
     R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return R3D_OK;
 }

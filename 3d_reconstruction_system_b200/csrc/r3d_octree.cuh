@@ -25,7 +25,9 @@ static_assert(sizeof(BrickRecord) == R3D_BRICK_RECORD_BYTES, "record layout is p
 
 // device counters of a tree
 enum { CNT_POOL_USED = 0, CNT_OVERFLOW, CNT_DROPPED, CNT_SCRATCH_USED, CNT_DELTA, CNT_DISCRETE, CNT_STEPS_LO, CNT_STEPS_HI, CNT_RAY_LO, CNT_RAY_HI, CNT_GRID_MISS,
-       CNT_ABORT = 14 /* sticky: a pipelined scan could not be read back; every queued scan kernel skips until the host clears it */,
+       CNT_GRID_NEED = 11 /* cells the scan's cube would need (0xffffffff: cannot be direct-mapped at all) */,
+       CNT_NRAYS = 12 /* rays with at least one free cell, appended by k_scan_prepare */,
+       CNT_ORIGIN_OCC = 13 /* an in-range endpoint lies in the sensor's own voxel */,
        CNT_APPLY_OVERFLOW = 15 /* sticky */, CNT_COUNT = 16 };
 
 }  // namespace r3d
@@ -53,26 +55,28 @@ struct r3d_tree {
     uint64_t scap = 0;
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
-    // second slot of the two-deep scan pipeline (r3d_tree_insert_scans): record buffer, per-slot counters, cell lists, events
-    r3d::DeltaRecord* delta_b = nullptr;
-    uint64_t delta_b_cap = 0;
-    uint32_t* pipe_counters = nullptr;   // [2][CNT_COUNT]
-    uint32_t* pipe_list = nullptr;       // [2][pipe_list_cap]
-    uint64_t pipe_list_cap = 0;
-    cudaEvent_t pipe_done[2] = {nullptr, nullptr};
-    // overlapped ray casting (two cell cubes): scan s+1's ray cast runs on its own stream beside scan s's tail, list,
-    // emit and apply.  R3D_PIPE_OVERLAP=0 keeps everything on the context stream with one cube.
-    cudaEvent_t rc_done[2] = {nullptr, nullptr};
-    cudaEvent_t pipe_start = nullptr;
-    bool pipe_done_valid[2] = {false, false};
-    int pipe_overlap = 1;
-    uint64_t pipe_wait_ns = 0, pipe_work_ns = 0, pipe_max_turn_ns = 0, pipe_scans = 0;   // host clock of the last batch
+    uint64_t pipe_wait_ns = 0, pipe_work_ns = 0, pipe_max_turn_ns = 0, pipe_scans = 0;   // host clock of the last pipelined batch
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};
 };
 
 namespace r3d {
+// r3d_raycast.cu: bounded-range insertPointCloud batches (K3 dense pipeline).  Where the records of each scan go:
+struct ScanSink {
+    enum Mode { APPLY, EXPORT_USER, EXPORT_TREE } mode = APPLY;
+    void* records = nullptr;        // EXPORT_USER: caller's buffer (host or device), records back to back
+    uint64_t capacity = 0, used = 0;
+    uint64_t* counts = nullptr;     // EXPORT_USER: per-scan record counts
+};
+// Runs scans [0, n_scans) of a device-resident batch through the dense pipeline.  *done < n_scans: scan *done cannot be
+// direct-mapped (the caller takes it through the hash path and calls again for the rest).
+int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, const float* origins, uint32_t n_scans, double maxrange,
+                    ScanSink* sink, uint32_t* done, uint64_t* rays, uint64_t* steps);
+void scan_pipe_destroy(r3d_ctx* ctx);
+int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part = 0, uint32_t nparts = 1);
+int tree_reserve_delta(r3d_tree* t, uint64_t want);
+unsigned grid_for(r3d_ctx* ctx, unsigned long long items, int block = 256, int per_sm = 8);
 int tree_sync_counters(r3d_tree* t);
 int tree_settle(r3d_tree* t);   // pool_used exact again (reads the counters back if applies are pending)
 int tree_refresh_pool_keys(r3d_tree* t);

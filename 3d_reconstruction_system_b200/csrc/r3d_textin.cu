@@ -77,34 +77,52 @@ bool parse_field(const char* p, const char* e, double* v) {
     return end == b + tmp.size();
 }
 
-// parses up to three numbers from [p, e) (one line, no newline); comma_mode: fields separated by ',' (surrounding blanks
-// allowed, like float(" 1.5 ")), else by runs of blanks.  Returns the number of leading numeric fields (0..3).
+// One line (no newline) as the reference's readers see it: `str_tofloat(line.split(','))` (comma_mode, surrounding blanks
+// allowed like float(" 1.5 ")) or `str_tofloat(line.split())`: EVERY field goes through float(), the first three are the
+// point.  Returns 3 for a point, 0 for an empty / blank line (skipped: the one documented deviation, the reference's own
+// PLY writer ends its files with such a line), -1 where the reference raises: a field float() rejects, or fewer than three
+// fields (the binding then indexes past the array).
 inline int parse_row(const char* p, const char* e, bool comma_mode, double v[3]) {
+    {
+        const char* q = p;
+        while (q < e && (*q == ' ' || *q == '\t' || *q == '\r')) ++q;
+        if (q == e) return 0;
+    }
     int got = 0;
-    while (got < 3 && p < e) {
+    while (p <= e) {
         while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+        if (!comma_mode && p == e) break;                        // split(): trailing blanks make no field
         const char* q = p;
         if (comma_mode) { while (q < e && *q != ',') ++q; }
         else { while (q < e && *q != ' ' && *q != '\t' && *q != '\r') ++q; }
         const char* te = q;
         while (te > p && (te[-1] == ' ' || te[-1] == '\t' || te[-1] == '\r')) --te;
-        if (te == p || !parse_field(p, te, &v[got])) break;     // empty or not a number (float() would raise)
+        double tmp;
+        if (te == p || !parse_field(p, te, got < 3 ? &v[got] : &tmp)) return -1;   // empty or not a number: float() raises
         ++got;
-        p = (comma_mode && q < e) ? q + 1 : q;
+        if (comma_mode) {
+            if (q >= e) break;
+            p = q + 1;                                           // a trailing ',' leaves an empty last field: float('') raises
+        } else {
+            p = q;
+        }
     }
-    return got;
+    return got >= 3 ? 3 : -1;
 }
 
 struct Piece {
     size_t begin = 0, end = 0;   // byte range, whole lines
     uint64_t rows = 0, first = 0;
+    size_t bad_at = (size_t)-1;  // byte offset of the first line the reference would raise on
+    uint64_t bad_row = 0;        // points of this piece before that line
 };
 
 }  // namespace
 
 // Points of an `x,y,z` text (comma_mode != 0) or of an ASCII PLY body (comma_mode == 0, whitespace separated, only the
-// first three columns used) after skipping skip_lines lines; rows with fewer than three numeric fields (blank lines, the
-// reference writer's trailing indentation) are skipped; at most max_points points (0 = no limit).
+// first three columns used, every column must be a number) after skipping skip_lines lines; empty / blank lines (the
+// reference writer's trailing indentation) are skipped, any other line the reference would raise on is R3D_ERR_ARG with
+// its line number; at most max_points points (0 = no limit: lines after the cap are not looked at, as in the reference).
 // out == NULL or capacity too small: only *n_points is set (size query).  Needs no GPU.
 extern "C" int r3d_read_xyz_text(const char* path, int skip_lines, int comma_mode, uint64_t max_points, double* out, uint64_t capacity,
                                  uint64_t* n_points, int n_threads) {
@@ -162,9 +180,14 @@ extern "C" int r3d_read_xyz_text(const char* path, int skip_lines, int comma_mod
             const void* nl = memchr(base + p, '\n', pc.end - p);
             const size_t le = nl ? (size_t)((const char*)nl - base) : pc.end;
             double v[3];
-            if (parse_row(base + p, base + le, comma, v) == 3) {
+            const int kind = parse_row(base + p, base + le, comma, v);
+            if (kind == 3) {
                 if (keep) mine.insert(mine.end(), v, v + 3);
                 ++rows;
+            } else if (kind < 0) {
+                pc.bad_at = p;
+                pc.bad_row = rows;
+                break;
             }
             p = le + 1;
         }
@@ -177,7 +200,20 @@ extern "C" int r3d_read_xyz_text(const char* path, int skip_lines, int comma_mod
         for (auto& th : pool) th.join();
     }
     uint64_t total = 0;
-    for (auto& pc : pieces) { pc.first = total; total += pc.rows; }
+    for (auto& pc : pieces) {
+        pc.first = total;
+        total += pc.rows;
+        // a malformed line is an error exactly when the reference's loop would have reached it (it stops at max_points)
+        if (pc.bad_at != (size_t)-1 && (!max_points || pc.first + pc.bad_row < max_points)) {
+            uint64_t line = 1;
+            for (size_t i = 0; i < pc.bad_at; ++i) line += base[i] == '\n';
+            const void* nl = memchr(base + pc.bad_at, '\n', size - pc.bad_at);
+            size_t len = nl ? (size_t)((const char*)nl - (base + pc.bad_at)) : size - pc.bad_at;
+            if (len > 80) len = 80;
+            return set_error(nullptr, R3D_ERR_ARG, "%s, line %llu: could not convert string to float (or fewer than three fields): '%.*s'", path,
+                             (unsigned long long)line, (int)len, base + pc.bad_at);
+        }
+    }
     if (max_points && total > max_points) total = max_points;
     *n_points = total;
     if (!out || capacity < total) return R3D_OK;

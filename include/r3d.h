@@ -94,8 +94,10 @@ int r3d_png_decode_batch(const char *const *paths, int n, int mode, int channel,
  * txt_read of the OctoMap scripts on a host thread pool: the points of an `x,y,z` text file (comma_mode != 0:
  * octomap/txt_transfer_octomap.py:16-28, also what get_pointdata re-reads, transfer/camera_to_world.py:92-98) or of an
  * ASCII PLY body (comma_mode == 0: octomap/ply_transfer_octomap.py:16-40 -- skip_lines = 8, whitespace separated, first
- * three columns, max_points = 5 400 001).  Numbers are converted with strtod (correctly rounded like float()).  Rows with
- * fewer than three numeric fields are skipped (the reference raises on them; documented deviation).  out: capacity x 3
+ * three columns, max_points = 5 400 001).  Numbers are converted like float() (correctly rounded, same grammar).  Empty and
+ * blank lines are skipped (documented deviation: the reference's own PLY writer ends files with one and its reader raises on
+ * it); any other line the reference raises on -- a field float() rejects in ANY column, fewer than three fields -- returns
+ * R3D_ERR_ARG with the line number, like the reference's ValueError.  Lines after max_points are not looked at.  out: capacity x 3
  * doubles, or NULL for a size query; *n_points is always set.  Needs no GPU.
  */
 int r3d_read_xyz_text(const char *path, int skip_lines, int comma_mode, uint64_t max_points, double *out, uint64_t capacity,

@@ -86,15 +86,17 @@ def test_large_file_threads_keep_order(tmp_path):
 
 
 def _check_tokens(tmp_path, tokens, name):
-    """Every token three times on a line; rows whose token float() rejects must be skipped, the others bit-identical."""
-    want = []
+    """Every token float() accepts three times on a line: bit-identical values.  Every token float() rejects: the reader
+    raises ValueError naming the line, as the reference's str_tofloat does (no row is ever dropped silently)."""
+    want, good, bad = [], [], []
     for tok in tokens:
         try:
             want.append(float(tok))
+            good.append(tok)
         except ValueError:
-            pass
+            bad.append(tok)
     p = tmp_path / name
-    p.write_text("".join("%s,%s,%s\n" % (t, t, t) for t in tokens))
+    p.write_text("".join("%s,%s,%s\n" % (t, t, t) for t in good))
     got = formats.read_xyz_txt(str(p))
     want = np.array(want, dtype=np.float64)
     assert got.shape == (want.size, 3)
@@ -103,6 +105,45 @@ def _check_tokens(tmp_path, tokens, name):
         nan = np.isnan(want)
         assert np.array_equal(np.isnan(col), nan)
         assert np.array_equal(col[~nan].view(np.uint64), want[~nan].view(np.uint64)), name
+    for k, tok in enumerate(bad):
+        q = tmp_path / ("bad_%d_%s" % (k, name))
+        q.write_text("1,2,3\n4,5,6\n7,%s,9\n10,11,12\n" % tok)
+        with pytest.raises(ValueError, match="line 3"):
+            formats.read_xyz_txt(str(q))
+
+
+def test_malformed_rows_raise_like_the_reference(tmp_path):
+    """a corrupted or truncated cloud must not lose points silently.  The reference's loops raise ValueError on
+    any field float() rejects (str_tofloat converts EVERY field of the line) and fail on rows with fewer than three
+    fields; only empty / blank lines are skipped here (the documented deviation)."""
+    def txt(name, text):
+        p = tmp_path / name
+        p.write_text(text)
+        return str(p)
+    for k, (text, line) in enumerate([("1,2,3\n1,2,x\n4,5,6\n", 2), ("1,2,3\n1,2\n", 2), ("foo\n1,2,3\n", 1), ("1,2,3\n4,5,6\n1,2,0x10\n", 3),
+                                      ("1,2,3,\n", 1), ("1,,3\n", 1), ("1,2,3,abc\n", 1), ("1,2,3\n4,5,6", 0), ("1,2,3\n   \n\t\n4,5,6\n\n", 0)]):
+        if line:
+            with pytest.raises(ValueError, match="line %d" % line):
+                formats.read_xyz_txt(txt("t%d.txt" % k, text))
+        else:
+            assert np.array_equal(formats.read_xyz_txt(txt("t%d.txt" % k, text)), np.array([[1, 2, 3], [4, 5, 6.0]]))
+    hdr = "h\n" * 8
+    assert np.array_equal(formats.read_ply_points(txt("a.ply", hdr + "1 2 3\n4 5 6 255 0 0 0\n\n    ")), np.array([[1, 2, 3], [4, 5, 6.0]]))
+    for k, (body, line) in enumerate([("1 2 3\n4 5\n", 10), ("1 2 3\n4 5 six\n", 10), ("1 2 3 r g b\n", 9), ("1,2,3\n", 9)]):
+        with pytest.raises(ValueError, match="line %d" % line):
+            formats.read_ply_points(txt("b%d.ply" % k, hdr + body))
+    # the reference stops reading at its point cap: a malformed line after the cap is never looked at
+    capped = txt("c.ply", hdr + "1 2 3\n4 5 6\n7 8 9\nbroken\n")
+    assert formats.read_ply_points(capped, max_points=3).shape == (3, 3)
+    with pytest.raises(ValueError, match="line 12"):
+        formats.read_ply_points(capped, max_points=4)
+    # many threads: the error names the FIRST malformed line of the file
+    big = "".join("%d,%d,%d\n" % (i, i + 1, i + 2) for i in range(200000))
+    lines = big.splitlines(True)
+    lines[150000] = "1,2,oops\n"
+    lines[60000] = "1,2\n"
+    with pytest.raises(ValueError, match="line 60001"):
+        formats.read_xyz_txt(txt("big.txt", "".join(lines)))
 
 
 def test_decimal_to_double_is_correctly_rounded(tmp_path):
@@ -138,7 +179,7 @@ def test_decimal_to_double_is_correctly_rounded(tmp_path):
              "123456789012345678901234567890", "0.000000000000000000000000000000000012345678901234567890123",
              "1" + "0" * 40, "0." + "0" * 40 + "1", "3.14159265358979323846264338327950288", "000001.5", ".5", "5.", "+.5e1", "-0.0", "0", "00", "1e5",
              "1E-5", "1.e2", "inf", "-inf", "nan", "infinity", "Infinity", "NaN",
-             # what float() rejects (the row is skipped)
+             # what float() rejects (the reader raises, like the reference)
              ".", "e5", "1e", "1e+", "--1", "1.5x", "1..5", "+-1", "0x10", "0x1p3", "nan(1)", "1__0", "_1", "1_", "1_.5", "1e_5", "in", "infinit",
              # PEP 515 underscores, which float() accepts between digits
              "1_000", "1_0.2_5e1_0", "1" * 70, "-" + "9" * 400 + ".5"]
