@@ -142,11 +142,11 @@ struct ScanArgs {
 // computeUpdate (OccupancyOcTreeBase) for an UNBOUNDED range (maxrange < 0), or a scan whose cube cannot be direct-mapped:
 // the masks of a brick sit in a per-scan hash table.  Bounded ranges -- every BASELINE configuration -- take the batched
 // direct-mapped pipeline of r3d_raycast.cu.  Persistent warps; every lane walks one ray at a time and idle lanes are
-// re-filled from a global ray counter as soon as K3_REFILL_MIN of them are idle.  The walk is the branch-free form of
+// re-filled from a global ray counter as soon as K3H_REFILL_MIN of them are idle.  The walk is the branch-free form of
 // computeRayKeys (r3d_math.cuh); free cells are collected in a 64-bit register mask per 4x4x4 sub-block (64 consecutive
 // Morton voxels = one aligned 64-bit word of the brick's free mask) and written with ONE red.or when the ray leaves it.
 constexpr int K3_THREADS = 256;
-constexpr int K3_REFILL_MIN = 8;
+constexpr int K3H_REFILL_MIN = 8;
 
 __device__ __forceinline__ uint64_t ldcg_u64_if(const uint64_t* p, uint64_t otherwise, bool pred) {
     uint64_t v = otherwise;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_scan_raycast_hash(const ScanArgs
     for (;;) {
         const unsigned act = __ballot_sync(0xffffffffu, active);
         const unsigned idle = ~act;
-        if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
+        if (!exhausted && __popc(idle) >= K3H_REFILL_MIN) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)__popc(idle));
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(K3_THREADS) k_scan_raycast_hash(const ScanArgs
             continue;
         }
         if (act == 0) break;
-        const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
+        const int keep_going = exhausted ? 0 : 32 - K3H_REFILL_MIN;
         do {
             if (active) {
                 const int px = r.kx, py = r.ky, pz = r.kz;
