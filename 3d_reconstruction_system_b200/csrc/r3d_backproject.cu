@@ -998,31 +998,70 @@ extern "C" int r3d_backproject_rt(r3d_ctx* ctx, const void* depth, int dtype, in
                        out_dtype, out_xyz, d_counts);
         cudaEventRecord(ctx->ev_b, ctx->stream);
     } else if (compact) {
-        // compaction needs the whole batch resident (output offsets depend on every earlier tile)
-        void *d_in = nullptr, *d_out = nullptr;
-        if (!depth_dev) {
-            ce = cudaMalloc(&d_in, frame_in * n_frames);
-            if (ce != cudaSuccess) return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(depth staging) failed: %s", cudaGetErrorString(ce));
-            cudaMemcpyAsync(d_in, depth, frame_in * n_frames, cudaMemcpyHostToDevice, ctx->stream);
+        // Compaction with a host buffer on either side, through the same ring of device slots as the plain mode: a chunk of
+        // frames is uploaded, packed into the slot's record buffer (or straight into the caller's device buffer) and its
+        // per-frame counts are read back; the records of chunk c leave for the host (at the running offset the counts of
+        // the chunks before give) while chunk c + 1 is uploaded and packed.  Device memory is bounded by the ring, never
+        // by the batch.
+        const size_t per_frame = (depth_dev ? 0 : frame_in) + (out_dev ? 0 : frame_out);
+        int chunk = (int)(ctx->stage_chunk_bytes / (per_frame ? per_frame : 1));
+        if (chunk < 1) chunk = 1;
+        if (chunk > n_frames) chunk = n_frames;
+        int slots = ctx->stage_slots < 2 ? 2 : ctx->stage_slots;
+        const size_t slot_in = (frame_in * chunk + 255) / 256 * 256, slot_out = (frame_out * chunk + 255) / 256 * 256;
+        if (!depth_dev) rc = scratch_reserve(ctx, SCR_IN0, slot_in * slots);
+        if (rc == R3D_OK && !out_dev) rc = scratch_reserve(ctx, SCR_OUT0, slot_out * slots);
+        unsigned long long* h_counts = nullptr;     // pinned mirror of the per-frame counts
+        if (rc == R3D_OK && cudaHostAlloc((void**)&h_counts, (size_t)n_frames * 8, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            rc = set_error(ctx, R3D_ERR_OOM, "cudaHostAlloc(per-frame counts) failed");
         }
-        if (!out_dev) {
-            ce = cudaMalloc(&d_out, frame_out * n_frames);
-            if (ce != cudaSuccess) { cudaFree(d_in); return set_error(ctx, R3D_ERR_OOM, "cudaMalloc(xyz staging) failed: %s", cudaGetErrorString(ce)); }
-        }
-        rc = launch_k1(ctx, ctx->stream, depth_dev ? depth : d_in, dtype, W, H, pitch, n_frames, intr, d_rt, mode, depth_scale,
-                       fB, compact, out_dtype, out_dev ? out_xyz : d_out, d_counts);
-        if (rc == R3D_OK && !out_dev) {
-            // copy back only what was written
-            unsigned long long* h = (unsigned long long*)malloc((size_t)n_frames * 8);
-            cudaMemcpyAsync(h, d_counts, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, ctx->stream);
-            cudaStreamSynchronize(ctx->stream);
+        cudaStream_t s_in = ctx->copy_stream[0], s_out = ctx->copy_stream[1], s_k = ctx->stream;
+        unsigned long long run_off = 0;             // records written before the chunk being finished
+        const int n_chunks = (n_frames + chunk - 1) / chunk;
+        // finish chunk c: wait for its counts, then (host output) send its records on their way
+        auto finish_chunk = [&](int c) -> int {
+            const int s = c % slots, f0 = c * chunk;
+            const int nf = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+            R3D_CUDA_OK(ctx, cudaEventSynchronize(ctx->ev_k[s]));
             unsigned long long tot = 0;
-            for (int i = 0; i < n_frames; ++i) tot += h[i];
-            free(h);
-            cudaMemcpyAsync(out_xyz, d_out, (size_t)tot * 3 * osz, cudaMemcpyDeviceToHost, ctx->stream);
+            for (int i = 0; i < nf; ++i) tot += h_counts[f0 + i];
+            if (!out_dev && tot) {
+                R3D_CUDA_OK(ctx, cudaMemcpyAsync((char*)out_xyz + (size_t)run_off * 3 * osz, (char*)ctx->scratch[SCR_OUT0] + (size_t)s * slot_out,
+                                                 (size_t)tot * 3 * osz, cudaMemcpyDeviceToHost, s_out));
+            }
+            R3D_CUDA_OK(ctx, cudaEventRecord(ctx->ev_out[s], s_out));
+            run_off += tot;
+            return R3D_OK;
+        };
+        for (int c = 0; c < n_chunks && rc == R3D_OK; ++c) {
+            const int s = c % slots, f0 = c * chunk;
+            const int nf = (n_frames - f0 < chunk) ? n_frames - f0 : chunk;
+            const void* din = depth_dev ? (const void*)((const char*)depth + (size_t)f0 * frame_in)
+                                        : (const void*)((const char*)ctx->scratch[SCR_IN0] + (size_t)s * slot_in);
+            if (!depth_dev) {
+                if (c >= slots) cudaStreamWaitEvent(s_in, ctx->ev_k[s], 0);      // the kernel that read this slot is done
+                cudaMemcpyAsync((void*)din, (const char*)depth + (size_t)f0 * frame_in, frame_in * nf, cudaMemcpyHostToDevice, s_in);
+                cudaEventRecord(ctx->ev_in[s], s_in);
+                cudaStreamWaitEvent(s_k, ctx->ev_in[s], 0);
+            }
+            // a device output is packed in place: the chunk starts where the chunks before it ended, so their counts must be in
+            if (out_dev && c > 0) rc = finish_chunk(c - 1);
+            if (rc != R3D_OK) break;
+            void* dout = out_dev ? (void*)((char*)out_xyz + (size_t)run_off * 3 * osz) : (void*)((char*)ctx->scratch[SCR_OUT0] + (size_t)s * slot_out);
+            if (!out_dev && c >= slots) cudaStreamWaitEvent(s_k, ctx->ev_out[s], 0);   // the slot's records have been read back
+            // (launch_k1 takes the generic kernel for a chunk whose first record is not 16-byte aligned)
+            rc = launch_k1(ctx, s_k, din, dtype, W, H, pitch, nf, intr, d_rt ? d_rt + (size_t)f0 * 12 : nullptr, mode, depth_scale, fB, 1, out_dtype,
+                           dout, d_counts + f0);
+            cudaMemcpyAsync(h_counts + f0, d_counts + f0, (size_t)nf * 8, cudaMemcpyDeviceToHost, s_k);
+            cudaEventRecord(ctx->ev_k[s], s_k);
+            if (!out_dev && c > 0 && rc == R3D_OK) rc = finish_chunk(c - 1);
         }
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_in); cudaFree(d_out);
+        if (rc == R3D_OK && n_chunks > 0) rc = finish_chunk(n_chunks - 1);
+        cudaStreamSynchronize(s_in);
+        cudaStreamSynchronize(s_k);
+        cudaStreamSynchronize(s_out);
+        if (h_counts) cudaFreeHost(h_counts);
     } else {
         // host-side buffers: a ring of device slots; uploads, kernels and read-backs run on three streams chained by
         // events, so the read-back engine (the bound: 12 of the 14 bytes per pixel) never waits for an upload

@@ -35,7 +35,13 @@ namespace r3d {
 constexpr int K3_THREADS = 256;
 constexpr int K3_MAX_BATCH = 8;
 #ifndef K3_REFILL_MIN
-#define K3_REFILL_MIN 4
+#define K3_REFILL_MIN 8
+#endif
+#ifndef K3_STAGES
+#define K3_STAGES 3      // staging registers of the sub-block word fetch = iterations between request and use, plus one
+#endif
+#ifndef K3_CHUNK
+#define K3_CHUNK 64      // rays a warp claims from the batch's counter at a time
 #endif
 
 // One ray with at least one free cell, as computeRayKeys sets it up (r3d_math.cuh::ray_setup).
@@ -197,11 +203,13 @@ __device__ __forceinline__ uint32_t lane_widx(uint32_t cell, uint32_t P) { retur
 // chain (x if tMax.x < tMax.y and tMax.x < tMax.z; else y if tMax.y < tMax.z; else z), stop at the end key or when
 // min(tMax) > length -- evaluated as "every tMax > length", the minimum itself is never needed.  The three mutually
 // exclusive updates are predicated instructions (as C++ conditionals they compile to divergent branches).
-// `stage` is the register the word fetched on entering a sub-block lands in; the caller alternates between two, and a
-// fetched word is moved into `seen` two iterations after it was requested, so the warp never waits on the load it has
-// just issued; a ray that leaves a sub-block earlier publishes without knowing the word (a redundant red.or).
+// `stage` is the register the word fetched on entering a sub-block lands in; the caller rotates through K3_STAGES of them,
+// and a fetched word is moved into `seen` K3_STAGES iterations after it was requested (a scoreboard wait is warp-wide and
+// some lane enters a sub-block on almost every iteration: ncu showed 35 % of all stall samples on this wait with two
+// registers, i.e. one iteration ~ one L2 round trip between request and use); a ray that leaves a sub-block earlier
+// publishes without knowing the word (a redundant red.or, never a wrong bit).
 __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, uint32_t total_cells, uint32_t* miss, WalkLane& L, uint64_t& stage) {
-    if (L.age == 1) L.seen = stage;
+    if (L.age == K3_STAGES - 1) L.seen = stage;
     const uint32_t Pold = L.P;
     int cs;
     asm("{\n\t.reg .pred p0, p1, p2;\n\t"
@@ -243,7 +251,7 @@ __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, u
         L.seen = 0;
     }
     stage = ld_ca_u64_if(masks64 + L.widx, stage, enter);
-    L.age = enter ? 0u : (L.age < 3u ? L.age + 1u : 3u);
+    L.age = enter ? 0u : (L.age < (unsigned)K3_STAGES + 1u ? L.age + 1u : (unsigned)K3_STAGES + 1u);
     L.mask |= lane_bit(L.P);
     return !done;
 }
@@ -291,21 +299,31 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
     bool active = false, exhausted = false;
     WalkLane L;
     memset(&L, 0, sizeof L);
-    L.age = 3;
-    uint64_t stage_a = 0, stage_b = 0;
+    L.age = K3_STAGES + 1;
+    uint64_t stage[K3_STAGES];
+#pragma unroll
+    for (int k = 0; k < K3_STAGES; ++k) stage[k] = 0;
+    // rays are claimed from the batch's counter K3_CHUNK at a time per warp (one atomic round trip per chunk, not per re-fill)
+    uint32_t my_next = 0, my_end = 0;
     for (;;) {
         const unsigned act = __ballot_sync(0xffffffffu, active);
         const unsigned idle = ~act;
         if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + __popc(idle) >= total) exhausted = true;
-            const unsigned long long i = base + __popc(idle & ((1u << lane) - 1u));
-            if (!active && i < total) {
+            if (my_next == my_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)K3_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                my_next = base < total ? (uint32_t)base : total;
+                my_end = base + K3_CHUNK < total ? (uint32_t)base + K3_CHUNK : total;
+                if (my_next == my_end) { exhausted = true; continue; }
+            }
+            const uint32_t i = my_next + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+            const bool take = !active && i < my_end;
+            my_next = my_next + (uint32_t)__popc(idle) < my_end ? my_next + (uint32_t)__popc(idle) : my_end;
+            if (take) {
                 int s = 0;
-                while ((uint32_t)i >= s_prefix[s + 1]) ++s;
-                const uint4* rp = reinterpret_cast<const uint4*>(a.rays + (size_t)s * a.ray_stride + ((uint32_t)i - s_prefix[s]));
+                while (i >= s_prefix[s + 1]) ++s;
+                const uint4* rp = reinterpret_cast<const uint4*>(a.rays + (size_t)s * a.ray_stride + (i - s_prefix[s]));
                 const uint4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3), q4 = __ldg(rp + 4);
                 L.tmx = __hiloint2double((int)q0.y, (int)q0.x); L.tmy = __hiloint2double((int)q0.w, (int)q0.z);
                 L.tmz = __hiloint2double((int)q1.y, (int)q1.x); L.tdx = __hiloint2double((int)q1.w, (int)q1.z);
@@ -322,35 +340,34 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
                 L.eP = ((uint32_t)(ex & 7) | ((uint32_t)(ey & 7) << 8) | ((uint32_t)(ez & 7) << 16)) | 0x00080808u;
                 L.dPx = sx; L.dPy = sy * 256; L.dPz = sz * 65536;
                 L.csx = sx; L.csy = sy * (int)g.dx; L.csz = sz * (int)g.dxy;
-                if (ezf & 0x10000u) {   // the endpoint is an occupied cell (Morton order, like the record format)
+                if (ezf & 0x10000u) {   // the endpoint is an occupied cell (Morton order, like the record format); fire and forget
                     const unsigned vox = brick_voxel_index((uint32_t)ex, (uint32_t)ey, (uint32_t)ez);
-                    uint32_t* w = a.cmasks + (size_t)L.ecell * 32 + (vox >> 5);
-                    const uint32_t bit = 1u << (vox & 31u);
-                    if (!(__ldcg(w) & bit)) {
-                        atomicOr(w, bit);
-                        touched[L.ecell] = 1;
-                    }
+                    atomicOr(a.cmasks + (size_t)L.ecell * 32 + (vox >> 5), 1u << (vox & 31u));
+                    touched[L.ecell] = 1;
                 }
                 active = true;
-                // the origin cell is the first free cell; its word is read here
+                // the origin cell is the first free cell; its word is requested like any other sub-block's (the last staging
+                // register is free here: words still on their way were dropped when the step loop was left)
                 L.widx = lane_widx(L.cell, L.P);
-                L.seen = __ldcg(reinterpret_cast<const unsigned long long*>(masks64 + L.widx));
-                L.age = 3;
+                L.seen = 0;
+                L.age = 0;
                 L.mask = lane_bit(L.P);
                 const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
                 L.axis = (xy & xz) ? 0 : (((!xy) & yz) ? 1 : 2);
             }
+            stage[K3_STAGES - 1] = ld_ca_u64_if(masks64 + L.widx, stage[K3_STAGES - 1], take);
             continue;
         }
         if (act == 0) break;   // no ray left anywhere in this warp
         const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
         do {
-            if (active) active = walk_step(masks64, touched, total_cells, miss, L, stage_a);
-            if (active) active = walk_step(masks64, touched, total_cells, miss, L, stage_b);
+#pragma unroll
+            for (int k = 0; k < K3_STAGES; ++k)
+                if (active) active = walk_step(masks64, touched, total_cells, miss, L, stage[k]);
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
         // fetched words still on their way are dropped (their rays publish without them): the next round may start
-        // with either staging register
-        if (L.age < 2) L.age = 3;
+        // with any staging register
+        if (L.age < (unsigned)K3_STAGES) L.age = K3_STAGES + 1;
     }
     // statistics only: free-cell visits of this batch
     unsigned long long steps = L.steps;
@@ -648,9 +665,9 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     if (n_ok == 0) return R3D_OK;
     ScanPipe* p = nullptr;
     R3D_TRY(pipe_get(ctx, &p));
-    int want_B = 4;
-    if (const char* v = getenv("R3D_SCAN_BATCH")) { const int b = atoi(v); if (b >= 1 && b <= K3_MAX_BATCH) want_B = b; }
-    if ((uint32_t)want_B > n_ok) want_B = (int)n_ok;
+    int cfg_B = 4;
+    if (const char* v = getenv("R3D_SCAN_BATCH")) { const int b = atoi(v); if (b >= 1 && b <= K3_MAX_BATCH) cfg_B = b; }
+    int want_B = (uint32_t)cfg_B > n_ok ? (int)n_ok : cfg_B;
     // first guess of the cube: 2^20 cells (128 MB) or the whole (2 reach + 1)^3 cube when that is smaller; a scan that
     // needs more reports it and the pipeline is re-shaped
     uint64_t cube = p->cube_cells ? p->cube_cells : (1ull << 20);
@@ -661,17 +678,24 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     }
     // `lay` cubes per slot are laid out (kept from call to call: a single-scan call after a batch call re-shapes nothing),
     // `B` of them are used per batch
-    int lay = pipe_fit_batch(ctx, p->B > want_B ? p->B : want_B, cube);
+    int lay = pipe_fit_batch(ctx, p->B > cfg_B ? p->B : cfg_B, cube);
     if (lay == 0) return R3D_OK;   // scratch budget too small for direct mapping: hash path
     int B = want_B < lay ? want_B : lay;
     uint64_t rec_cap = p->rec_cap ? p->rec_cap : (1ull << 16);
     uint64_t ray_cap = (n_max + 255) / 256 * 256;
     auto now_ns = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; };
+    static const bool trace = getenv("R3D_PIPE_TRACE") != nullptr;   // host-side turnarounds above 1 ms, to stderr
     t->pipe_wait_ns = t->pipe_work_ns = t->pipe_max_turn_ns = t->pipe_scans = 0;
     uint32_t next = 0;          // first scan not yet consumed
     float kernel_ms = 0.f;
     for (int attempt = 0; attempt < 24 && next < n_ok; ++attempt) {
-        R3D_TRY(pipe_reserve(ctx, p, lay, cube, rec_cap, ray_cap));
+        {
+            const uint64_t t_r = trace ? now_ns() : 0;
+            R3D_TRY(pipe_reserve(ctx, p, lay, cube, rec_cap, ray_cap));
+            if (trace && now_ns() - t_r > 1000000ull)
+                fprintf(stderr, "[r3d pipe] shaping the pipeline took %.2f ms (%d cubes per slot of %llu cells, %llu records, %llu rays per scan)\n", (now_ns() - t_r) * 1e-6,
+                        lay, (unsigned long long)cube, (unsigned long long)rec_cap, (unsigned long long)ray_cap);
+        }
         if (p->overlap) {
             R3D_CUDA_OK(ctx, cudaEventRecord(p->start, ctx->stream));   // buffers shaped, cubes clear, scans resident
             // nothing of an earlier call is pending on the slots
@@ -720,7 +744,7 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
                     // the scan's cube does not fit: re-shape the pipeline for it, or hand the scan to the hash path
                     R3D_TRY(pipe_sync_all(ctx, p));
                     const uint64_t need = c[CNT_GRID_NEED] == 0xffffffffu ? 0 : (uint64_t)c[CNT_GRID_NEED] + c[CNT_GRID_NEED] / 8;
-                    const int nb = need ? pipe_fit_batch(ctx, want_B, need) : 0;
+                    const int nb = need ? pipe_fit_batch(ctx, cfg_B, need) : 0;
                     if (nb == 0) { *done_out = s; ctx->last_kernel_ms = kernel_ms; return R3D_OK; }
                     cube = need; lay = nb; B = want_B < lay ? want_B : lay;
                     reshape = true;
@@ -735,7 +759,13 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
                 const DeltaRecord* recs = p->recs + ((size_t)slot * p->B + j) * p->rec_cap;
                 const uint64_t n_rec = c[CNT_DELTA];
                 if (sink->mode == ScanSink::APPLY) {
+                    const uint64_t t_a = trace ? now_ns() : 0;
+                    const uint64_t cap0 = t->pool_cap, tcap0 = t->tcap;
                     R3D_TRY(apply_delta_impl(t, recs, n_rec));
+                    if (trace && now_ns() - t_a > 1000000ull)
+                        fprintf(stderr, "[r3d pipe] apply of scan %u took %.2f ms on the host (pool %llu -> %llu bricks, table %llu -> %llu, bound %llu)\n", s,
+                                (now_ns() - t_a) * 1e-6, (unsigned long long)cap0, (unsigned long long)t->pool_cap, (unsigned long long)tcap0,
+                                (unsigned long long)t->tcap, (unsigned long long)t->pool_bound);
                     p->snap_after[0] += n_rec; p->snap_after[1] += n_rec;
                     if (s + 1 == n_scans) {   // r3d_scan_delta_export after a batch call refers to its last scan
                         if (n_rec > t->delta_cap) R3D_TRY(tree_reserve_delta(t, n_rec + n_rec / 4 + 1024));

@@ -60,30 +60,48 @@ def camera_centre(rt_row):
     return out[0]
 
 
+def camera_centres(rt):
+    """Sensor origins of n frames at once: R^-1 (0 - t) per pose-table row, in the kernel's operation order (every product and
+    sum rounded separately, left to right, + 0.0 last: r3d_math.cuh::pose_apply / pose_canon), so the values equal what
+    camera_centre() gets from the GPU.  Per-frame host arithmetic, like r3d_pose_to_rt."""
+    rt = np.ascontiguousarray(rt, dtype=np.float64).reshape(-1, 12)
+    d0, d1, d2 = 0.0 - rt[:, 9], 0.0 - rt[:, 10], 0.0 - rt[:, 11]
+    out = np.empty((rt.shape[0], 3), dtype=np.float64)
+    for k in range(3):
+        out[:, k] = ((rt[:, 3 * k] * d0 + rt[:, 3 * k + 1] * d1) + rt[:, 3 * k + 2] * d2) + 0.0
+    return out
+
+
 def sequence_to_octree(depths, quats, trans, intr, resolution=0.1, maxrange=80.0, mode=MODE_DEPTH, depth_scale=1.0, fB=0.0,
-                       t_scale=1.0, tree=None, drop_invalid=False, frames_per_batch=64):
+                       t_scale=1.0, tree=None, drop_invalid=True, frames_per_batch=64):
     """North-star mode (BASELINE.json configs 3-5): every frame is one scan.  Frames are back-projected to float32 world
-    points by the fused kernel in batches that stay on the GPU, then inserted in frame order with
-    insertPointCloud(points, origin = camera centre, maxrange).  drop_invalid removes pixels whose decoded depth is not
-    positive before the insertion (the reference has no validity filter: Z = 0 pixels are points at the camera centre)."""
+    points by the fused kernel in batches that stay on the GPU, then inserted in frame order by ONE pipelined library call
+    per batch: insertPointCloud(points, origin = camera centre, maxrange) per frame.
+
+    drop_invalid (default): pixels whose decoded depth / disparity is not positive (sky, holes -- routine in disparity maps)
+    are compacted away on the device (K1's compaction mode, per-frame counts read back once per batch).  The reference has
+    no validity filter; with drop_invalid=False such pixels stay what its back-projection makes of them -- points AT the
+    camera centre, which mark the sensor's own voxel occupied in every frame and leave an occupied trail along the
+    trajectory in the .bt."""
     ctx = default_context(DEVICE)
     depths = np.ascontiguousarray(depths)
     n, H, W = depths.shape
     rt = ctx.pose_to_rt(quats, trans, t_scale=t_scale)
+    origins = camera_centres(rt)
     if tree is None:
         tree = OcTree(resolution, ctx=ctx)
     for a in range(0, n, frames_per_batch):
         b = min(n, a + frames_per_batch)
+        # the batch's world points never leave the GPU between the two kernels
+        xyz = ctx.device_empty(((b - a) * H * W, 3), np.float32)
         if drop_invalid:
-            for k in range(a, b):
-                xyz, cnt = ctx.backproject(depths[k], intr, rt=rt[k:k + 1], mode=mode, depth_scale=depth_scale, fB=fB, compact=True)
-                tree.insertPointCloud(xyz, camera_centre(rt[k]), maxrange=maxrange)
+            _, cnt = ctx.backproject(depths[a:b], intr, rt=rt[a:b], mode=mode, depth_scale=depth_scale, fB=fB, out=xyz, compact=True)
+            total = int(cnt.sum())
+            tree.insertPointClouds(xyz[:total] if total else xyz[:0], origins[a:b], maxrange=maxrange, counts=cnt)
         else:
-            # the batch's world points never leave the GPU between the two kernels
-            xyz = ctx.device_empty(((b - a) * H * W, 3), np.float32)
             ctx.backproject(depths[a:b], intr, rt=rt[a:b], mode=mode, depth_scale=depth_scale, fB=fB, out=xyz)
-            tree.insertPointClouds(xyz, [camera_centre(rt[k]) for k in range(a, b)], maxrange=maxrange)
-            xyz.free()
+            tree.insertPointClouds(xyz, origins[a:b], maxrange=maxrange)
+        xyz.free()
     return tree
 
 

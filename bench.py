@@ -234,7 +234,7 @@ def octomap_section(args, torch, r3d, ctx, dev, depth, rt_host, n_scans, with_cp
         return st["steps"], st["rays"]
 
     warm = octomap.OcTree(res, ctx=ctx)
-    run(warm, min(3, n_scans))
+    run(warm, min(8, n_scans))
     del warm
     # the timed batch, three times on a fresh tree (median): one pass is ~30 ms and the scan pipeline has a host turnaround
     # per scan, so a single pass is at the mercy of one descheduled host thread

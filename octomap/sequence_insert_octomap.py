@@ -23,14 +23,17 @@ def main(argv=None):
     ap.add_argument("--depth-scale", type=float, default=1.0, help="metres (or disparity pixels) per raw unit")
     ap.add_argument("--disparity", action="store_true", help="samples are disparities: Z = fx*B/d")
     ap.add_argument("--baseline", type=float, default=0.25, help="stereo baseline B in metres (disparity mode)")
-    ap.add_argument("--drop-invalid", action="store_true", help="do not cast rays for pixels with non-positive depth")
+    ap.add_argument("--keep-invalid", action="store_true",
+                    help="literal behaviour of the reference's back-projection: pixels with non-positive depth / disparity become points AT the "
+                         "camera centre (the sensor's own voxel is then marked occupied in every frame); default: such pixels are dropped on the device")
+    ap.add_argument("--drop-invalid", action="store_true", help="(default since round 2; kept for old command lines)")
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args(argv)
     _m.DEVICE = a.device
     _m.pose_sequence_to_bt(a.qt_path, a.file_bt, a.intrinsics, depth_dir=a.depth_dir, resolution=a.resolution, maxrange=a.maxrange,
                            pose_format=a.pose_format, raw_depth=a.raw_depth, depth_scale=a.depth_scale,
                            mode=_l.MODE_DISPARITY if a.disparity else _l.MODE_DEPTH, fB=a.intrinsics[0] * a.baseline,
-                           drop_invalid=a.drop_invalid)
+                           drop_invalid=not a.keep_invalid)
 
 
 if __name__ == '__main__':
