@@ -111,23 +111,37 @@ def read_frame_batch(paths, mode="gray", max_frames=256):
     bmode, chan = {"gray": ("gray", 0), "raw": ("raw", 0), "green": ("channel", 1)}[mode]
     if not paths:
         return np.zeros((0, 0, 0), np.uint8), 0
-    if _is_png(paths[0]):
+    if _native_png(paths[0]):
         w, h, _, d = png_info(paths[0])
         n = 1
-        while n < len(paths) and n < max_frames and _is_png(paths[n]):
+        while n < len(paths) and n < max_frames and _native_png(paths[n]):
             wn, hn, _, dn = png_info(paths[n])
             if (wn, hn, dn) != (w, h, d):
                 break
             n += 1
-        return imread_batch(paths[:n], bmode, channel=chan), n
+        try:
+            return imread_batch(paths[:n], bmode, channel=chan), n
+        except ValueError:
+            pass        # a file of the prefix has a defect only the decode finds: frame by frame below (OpenCV has the last word)
     first = one(paths[0])
     batch = [first]
-    while len(batch) < len(paths) and len(batch) < max_frames and not _is_png(paths[len(batch)]):
+    while len(batch) < len(paths) and len(batch) < max_frames and not _native_png(paths[len(batch)]):
         img = one(paths[len(batch)])
         if img.shape != first.shape or img.dtype != first.dtype:
             break
         batch.append(img)
     return np.stack(batch), len(batch)
+
+
+def _native_png(path):
+    """A PNG the native decoder serves (its header says so; interlaced files do not qualify)."""
+    if not _is_png(path):
+        return False
+    try:
+        png_info(path)
+        return True
+    except ValueError:
+        return False
 
 
 def _is_png(path):
@@ -138,40 +152,59 @@ def _is_png(path):
         return False
 
 
-def imread_gray(path):
-    """cv.imread(path, IMREAD_GRAYSCALE) (transfer/camera_to_world.py:160): always uint8 (16-bit -> >>8).  PNG files go
-    through the native decoder; other formats (the reference only uses PNG) through OpenCV."""
+def _native_or_cv2(path, mode, channel, cv2_read):
+    """A PNG goes through the native decoder; a well-formed variant it does not serve (Adam7 interlacing, trailing bytes
+    after the image data that libpng only warns about) is read by OpenCV -- the reference's reader -- instead, so every
+    file cv.imread accepts is accepted here.  Other formats (the reference only uses PNG) always go through OpenCV."""
     if _is_png(path):
-        return imread_batch([path], "gray", n_threads=1)[0]
-    import cv2
-    img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        try:
+            return imread_batch([path], mode, channel=channel, n_threads=1)[0]
+        except (ValueError, IndexError) as exc:
+            try:
+                img = cv2_read(path)
+            except Exception:
+                raise exc
+            if img is None:
+                raise exc
+            return img
+    img = cv2_read(path)
     if img is None:
         raise FileNotFoundError(path)
     return img
 
 
-def imread_unchanged_green(path):
-    """cv.imread(path, IMREAD_UNCHANGED)[:, :, 1] (transfer/pixel_to_camera.py:133-134)."""
-    if _is_png(path):
-        return imread_batch([path], "channel", channel=1, n_threads=1)[0]
+def _cv2_gray(path):
+    import cv2
+    return cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+
+
+def _cv2_green(path):
+    import cv2
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    return None if img is None else np.ascontiguousarray(img[:, :, 1])
+
+
+def _cv2_raw(path):
     import cv2
     img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
     if img is None:
-        raise FileNotFoundError(path)
-    return np.ascontiguousarray(img[:, :, 1])
+        return None
+    return np.ascontiguousarray(img[:, :, 0] if img.ndim == 3 else img)
+
+
+def imread_gray(path):
+    """cv.imread(path, IMREAD_GRAYSCALE) (transfer/camera_to_world.py:160): always uint8 (16-bit -> >>8)."""
+    return _native_or_cv2(path, "gray", 0, _cv2_gray)
+
+
+def imread_unchanged_green(path):
+    """cv.imread(path, IMREAD_UNCHANGED)[:, :, 1] (transfer/pixel_to_camera.py:133-134)."""
+    return _native_or_cv2(path, "channel", 1, _cv2_green)
 
 
 def imread_raw(path):
     """Full-precision single-channel depth / disparity (uint8 or uint16), for the metric pipelines."""
-    if _is_png(path):
-        return imread_batch([path], "raw", n_threads=1)[0]
-    import cv2
-    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
-    if img is None:
-        raise FileNotFoundError(path)
-    if img.ndim == 3:
-        img = img[:, :, 0]
-    return np.ascontiguousarray(img)
+    return _native_or_cv2(path, "raw", 0, _cv2_raw)
 
 
 # ------------------------------------------------------------------------------------------------ txt clouds

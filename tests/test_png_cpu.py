@@ -149,3 +149,60 @@ def test_batch_threads_and_errors(tmp_path):
     with pytest.raises(ValueError):
         formats.imread_batch([str(tmp_path / "junk.png")], "gray")
     assert formats.imread_batch([], "gray").shape[0] == 0
+
+
+def _png_chunks(ihdr, idat):
+    def ch(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    return b"\x89PNG\r\n\x1a\n" + ch(b"IHDR", ihdr) + ch(b"IDAT", idat) + ch(b"IEND", b"")
+
+
+def test_png_variants_only_opencv_reads_fall_back(tmp_path):
+    """every file cv.imread (the reference's reader) accepts must be accepted.  Adam7-interlaced PNGs and streams
+    with bytes after the image data (libpng only warns) are not served by the native decoder: the readers hand exactly those
+    files to OpenCV, per file in imread_*, and by ending the native prefix in read_frame_batch."""
+    rng = np.random.default_rng(9)
+    H, W = 13, 21
+    img = rng.integers(0, 65536, size=(H, W)).astype(np.uint16)
+    # Adam7: seven reduced images, each as un-filtered scanlines
+    raw = bytearray()
+    for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+        sub = img[y0::dy, x0::dx]
+        if sub.size == 0:
+            continue
+        for row in sub:
+            raw.append(0)
+            raw += row.astype(">u2").tobytes()
+    inter = tmp_path / "interlaced.png"
+    inter.write_bytes(_png_chunks(struct.pack(">IIBBBBB", W, H, 16, 0, 0, 0, 1), zlib.compress(bytes(raw))))
+    ref = cv2.imread(str(inter), cv2.IMREAD_UNCHANGED)
+    assert ref is not None and np.array_equal(ref, img)                       # OpenCV de-interlaces
+    assert np.array_equal(formats.imread_raw(str(inter)), img)
+    assert np.array_equal(formats.imread_gray(str(inter)), cv2.imread(str(inter), cv2.IMREAD_GRAYSCALE))
+    # trailing bytes after the zlib stream inside IDAT
+    plain = bytearray()
+    for row in img:
+        plain.append(0)
+        plain += row.astype(">u2").tobytes()
+    trail = tmp_path / "trailing.png"
+    trail.write_bytes(_png_chunks(struct.pack(">IIBBBBB", W, H, 16, 0, 0, 0, 0), zlib.compress(bytes(plain)) + b"\x00" * 7))
+    ref = cv2.imread(str(trail), cv2.IMREAD_UNCHANGED)
+    if ref is not None:                                                       # (whatever OpenCV says goes)
+        assert np.array_equal(formats.imread_raw(str(trail)), ref)
+    # a batch: native prefix, then the interlaced file on its own, then native again
+    good = []
+    for k in range(3):
+        p = tmp_path / ("g%d.png" % k)
+        cv2.imwrite(str(p), np.roll(img, k, axis=1))
+        good.append(str(p))
+    paths = good[:2] + [str(inter)] + good[2:]
+    stack, used = formats.read_frame_batch(paths, "raw")
+    assert used == 2 and np.array_equal(stack[1], np.roll(img, 1, axis=1))
+    stack, used = formats.read_frame_batch(paths[2:], "raw")
+    assert used == 1 and np.array_equal(stack[0], img)
+    stack, used = formats.read_frame_batch(paths[3:], "raw")
+    assert used == 1 and np.array_equal(stack[0], np.roll(img, 2, axis=1))
+    with pytest.raises((ValueError, FileNotFoundError)):
+        bad = tmp_path / "broken.png"
+        bad.write_bytes(_png_chunks(struct.pack(">IIBBBBB", W, H, 16, 0, 0, 0, 0), b"not a zlib stream"))
+        formats.imread_raw(str(bad))
