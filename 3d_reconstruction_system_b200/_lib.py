@@ -72,6 +72,7 @@ SIGNATURES = {
     "r3d_delta_expand_keys": (_i32, [_vp, _u64, _vp, _u64, _u64p, _vp, _u64, _u64p]),
     "r3d_tree_last_scan_stats": (_i32, [_vp, _vp]),
     "r3d_tree_pipeline_stats": (_i32, [_vp, _vp]),
+    "r3d_tree_growth_stats": (_i32, [_vp, _vp]),
     "r3d_tree_update_inner_occupancy": (_i32, [_vp]),
     "r3d_tree_write_bt": (_i32, [_vp, C.c_char_p]),
     "r3d_tree_write_bt_mem": (_i32, [_vp, _vp, _sz, C.POINTER(_sz)]),

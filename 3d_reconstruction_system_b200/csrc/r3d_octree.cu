@@ -539,6 +539,7 @@ static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
         R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(t->tkeys);
         cudaFree(t->tvals);
+        t->n_table_grow++;
     }
     t->tkeys = nk; t->tvals = nv; t->tcap = need;
     return R3D_OK;
@@ -568,6 +569,7 @@ static int tree_reserve_pool(r3d_tree* t, uint64_t want) {
     R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(t->values);
     cudaFree(t->known);
+    if (used) t->n_pool_grow++;
     t->values = nv; t->known = nk; t->pool_cap = ncap;
     return R3D_OK;
 }
@@ -1096,6 +1098,12 @@ extern "C" int r3d_tree_last_scan_stats(r3d_tree* t, uint64_t out[4]) {
 extern "C" int r3d_tree_pipeline_stats(r3d_tree* t, uint64_t out[4]) {
     if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
     out[0] = t->pipe_wait_ns; out[1] = t->pipe_work_ns; out[2] = t->pipe_max_turn_ns; out[3] = t->pipe_scans;
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_growth_stats(r3d_tree* t, uint64_t out[4]) {
+    if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
+    out[0] = t->n_pool_grow; out[1] = t->n_table_grow; out[2] = t->pool_cap; out[3] = t->tcap;
     return R3D_OK;
 }
 

@@ -56,6 +56,7 @@ struct r3d_tree {
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
     uint64_t pipe_wait_ns = 0, pipe_work_ns = 0, pipe_max_turn_ns = 0, pipe_scans = 0;   // host clock of the last pipelined batch
+    uint64_t n_pool_grow = 0, n_table_grow = 0;   // regrowth events since the tree was created (each copies / re-hashes)
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};

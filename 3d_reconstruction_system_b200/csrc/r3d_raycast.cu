@@ -190,9 +190,20 @@ struct WalkLane {
     unsigned steps;        // statistics: free cells recorded by this lane
 };
 
-__device__ __forceinline__ uint64_t ld_ca_u64_if(const uint64_t* p, uint64_t otherwise, bool pred) {
-    uint64_t v = otherwise;
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q ld.global.ca.u64 %0, [%1];\n\t}" : "+l"(v) : "l"(p), "r"((unsigned)pred) : "memory");
+// The word of the sub-block a ray enters is fetched with an ASYNCHRONOUS copy into a per-lane shared-memory slot
+// (cp.async / LDGSTS): no destination register, so no scoreboard for the warp to wait on -- with a register destination
+// ptxas waits for every fetch in flight at the head of the step loop (ncu: 35 % of all stall samples on that one wait,
+// whatever the number of staging registers).  One commit group per step; a step first waits for the group committed
+// K3_STAGES steps earlier (normally long complete), then reads its slot.
+__device__ __forceinline__ void fetch_word_async(uint32_t smem_slot, const uint64_t* gptr, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q cp.async.ca.shared.global [%0], [%1], 8;\n\t}" :: "r"(smem_slot), "l"(gptr), "r"((unsigned)pred) : "memory");
+}
+__device__ __forceinline__ void fetch_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void fetch_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(kPending) : "memory"); }
+__device__ __forceinline__ uint64_t lds_u64(uint32_t smem_slot) {
+    uint64_t v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_slot) : "memory");
     return v;
 }
 // bit of the current cell in its sub-block's word, and the word's index
@@ -203,13 +214,12 @@ __device__ __forceinline__ uint32_t lane_widx(uint32_t cell, uint32_t P) { retur
 // chain (x if tMax.x < tMax.y and tMax.x < tMax.z; else y if tMax.y < tMax.z; else z), stop at the end key or when
 // min(tMax) > length -- evaluated as "every tMax > length", the minimum itself is never needed.  The three mutually
 // exclusive updates are predicated instructions (as C++ conditionals they compile to divergent branches).
-// `stage` is the register the word fetched on entering a sub-block lands in; the caller rotates through K3_STAGES of them,
-// and a fetched word is moved into `seen` K3_STAGES iterations after it was requested (a scoreboard wait is warp-wide and
-// some lane enters a sub-block on almost every iteration: ncu showed 35 % of all stall samples on this wait with two
-// registers, i.e. one iteration ~ one L2 round trip between request and use); a ray that leaves a sub-block earlier
-// publishes without knowing the word (a redundant red.or, never a wrong bit).
-__device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, uint32_t total_cells, uint32_t* miss, WalkLane& L, uint64_t& stage) {
-    if (L.age == K3_STAGES - 1) L.seen = stage;
+// `slot` is the shared-memory slot (of this lane, for this position of the unrolled step sequence) the word fetched on
+// entering a sub-block lands in; the word is moved into `seen` K3_STAGES steps after it was requested; a ray that leaves
+// a sub-block earlier publishes without knowing the word (a redundant red.or, never a wrong bit).
+__device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, uint32_t total_cells, uint32_t* miss, WalkLane& L, uint32_t slot) {
+    fetch_wait<K3_STAGES - 1>();
+    if (L.age == K3_STAGES - 1) L.seen = lds_u64(slot);
     const uint32_t Pold = L.P;
     int cs;
     asm("{\n\t.reg .pred p0, p1, p2;\n\t"
@@ -250,7 +260,8 @@ __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, u
         L.mask = 0;
         L.seen = 0;
     }
-    stage = ld_ca_u64_if(masks64 + L.widx, stage, enter);
+    fetch_word_async(slot, masks64 + L.widx, enter);
+    fetch_commit();
     L.age = enter ? 0u : (L.age < (unsigned)K3_STAGES + 1u ? L.age + 1u : (unsigned)K3_STAGES + 1u);
     L.mask |= lane_bit(L.P);
     return !done;
@@ -264,6 +275,7 @@ struct WalkGrid {
 __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) {
     __shared__ WalkGrid sg[K3_MAX_BATCH];
     __shared__ uint32_t s_prefix[K3_MAX_BATCH + 1];
+    __shared__ __align__(8) uint64_t s_words[K3_STAGES][K3_THREADS];
     if (threadIdx.x < (unsigned)a.n_scans) {
         const int s = threadIdx.x;
         const Grid g = grid_of(a.geom + s * 8, a.cube_cells);
@@ -300,9 +312,7 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
     WalkLane L;
     memset(&L, 0, sizeof L);
     L.age = K3_STAGES + 1;
-    uint64_t stage[K3_STAGES];
-#pragma unroll
-    for (int k = 0; k < K3_STAGES; ++k) stage[k] = 0;
+    const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(&s_words[0][threadIdx.x]);
     // rays are claimed from the batch's counter K3_CHUNK at a time per warp (one atomic round trip per chunk, not per re-fill)
     uint32_t my_next = 0, my_end = 0;
     for (;;) {
@@ -346,8 +356,8 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
                     touched[L.ecell] = 1;
                 }
                 active = true;
-                // the origin cell is the first free cell; its word is requested like any other sub-block's (the last staging
-                // register is free here: words still on their way were dropped when the step loop was left)
+                // the origin cell is the first free cell; its word is requested like any other sub-block's (into the last slot:
+                // words still on their way were dropped when the step loop was left)
                 L.widx = lane_widx(L.cell, L.P);
                 L.seen = 0;
                 L.age = 0;
@@ -355,7 +365,10 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
                 const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
                 L.axis = (xy & xz) ? 0 : (((!xy) & yz) ? 1 : 2);
             }
-            stage[K3_STAGES - 1] = ld_ca_u64_if(masks64 + L.widx, stage[K3_STAGES - 1], take);
+            // (a dropped fetch of this lane may still be on its way into the same slot: let it land first, once per re-fill)
+            fetch_wait<0>();
+            fetch_word_async(slot0 + (K3_STAGES - 1) * K3_THREADS * 8u, masks64 + L.widx, take);
+            fetch_commit();
             continue;
         }
         if (act == 0) break;   // no ray left anywhere in this warp
@@ -363,10 +376,9 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
         do {
 #pragma unroll
             for (int k = 0; k < K3_STAGES; ++k)
-                if (active) active = walk_step(masks64, touched, total_cells, miss, L, stage[k]);
+                if (active) active = walk_step(masks64, touched, total_cells, miss, L, slot0 + (uint32_t)k * K3_THREADS * 8u);
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
-        // fetched words still on their way are dropped (their rays publish without them): the next round may start
-        // with any staging register
+        // fetched words still on their way are dropped (their rays publish without them): the re-fill reuses the last slot
         if (L.age < (unsigned)K3_STAGES) L.age = K3_STAGES + 1;
     }
     // statistics only: free-cell visits of this batch

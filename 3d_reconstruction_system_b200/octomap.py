@@ -127,6 +127,12 @@ class OcTree:
         check(self._lib.r3d_tree_pipeline_stats(self._h, a), self._ctx.handle)
         return {"wait_ms": a[0] / 1e6, "work_ms": a[1] / 1e6, "max_turnaround_ms": a[2] / 1e6, "scans": int(a[3])}
 
+    def growthStats(self):
+        """dict(pool_regrowths, table_regrowths, pool_capacity_bricks, table_capacity) since the tree was created."""
+        a = (C.c_uint64 * 4)()
+        check(self._lib.r3d_tree_growth_stats(self._h, a), self._ctx.handle)
+        return {"pool_regrowths": int(a[0]), "table_regrowths": int(a[1]), "pool_capacity_bricks": int(a[2]), "table_capacity": int(a[3])}
+
     def updateInnerOccupancy(self):
         self._flush()
         check(self._lib.r3d_tree_update_inner_occupancy(self._h), self._ctx.handle)

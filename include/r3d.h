@@ -266,6 +266,9 @@ int r3d_tree_last_scan_stats(r3d_tree *tree, uint64_t out[4]);
  * on scan counters (the GPU was the slower side), out[1] time it spent queueing work, out[2] the longest single
  * turnaround between a scan's counters arriving and the next wait, out[3] scans that went through the pipeline. */
 int r3d_tree_pipeline_stats(r3d_tree *tree, uint64_t out[4]);
+/* Regrowth of the map while it was filled: out = { brick-pool regrowths (each copies the pool), hash-table regrowths (each
+ * re-hashes), brick-pool capacity, hash-table capacity }.  r3d_tree_reserve() up front avoids them. */
+int r3d_tree_growth_stats(r3d_tree *tree, uint64_t out[4]);
 
 /* tree.updateInnerOccupancy() (octomap/txt_transfer_octomap.py:35): inner values are derived on demand. */
 int r3d_tree_update_inner_occupancy(r3d_tree *tree);

@@ -17,7 +17,7 @@ run st3_b4 "" 4
 run st2_b4 _st2 4
 run st4_b4 _st4 4
 run st3rf4_b4 _st3rf4 4
+run st3ch32_b4 _st3ch32 4
 run st3_b8 "" 8
-run st3_b2 "" 2
 CMD="python bench.py --frames 64 --steps 2 --warmup 3 --no-cpu-baseline --octomap-scans 16"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_scan_walk -s 3 -c 1 -o gpurun_out/k3_walk_prof2 -f $CMD > gpurun_out/ncu_k3walk2.log 2>&1; echo "ncu exit $?"
