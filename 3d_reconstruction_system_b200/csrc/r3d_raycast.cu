@@ -40,6 +40,9 @@ constexpr int K3_MAX_BATCH = 8;
 #ifndef K3_STAGES
 #define K3_STAGES 3      // staging registers of the sub-block word fetch = iterations between request and use, plus one
 #endif
+#ifndef K3_BLIND
+#define K3_BLIND 0       // 1: never fetch the sub-block word, publish every visited sub-block unconditionally (experiment)
+#endif
 #ifndef K3_CHUNK
 #define K3_CHUNK 64      // rays a warp claims from the batch's counter at a time
 #endif
@@ -218,8 +221,10 @@ __device__ __forceinline__ uint32_t lane_widx(uint32_t cell, uint32_t P) { retur
 // entering a sub-block lands in; the word is moved into `seen` K3_STAGES steps after it was requested; a ray that leaves
 // a sub-block earlier publishes without knowing the word (a redundant red.or, never a wrong bit).
 __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, uint32_t total_cells, uint32_t* miss, WalkLane& L, uint32_t slot) {
+#if !K3_BLIND
     fetch_wait<K3_STAGES - 1>();
     if (L.age == K3_STAGES - 1) L.seen = lds_u64(slot);
+#endif
     const uint32_t Pold = L.P;
     int cs;
     asm("{\n\t.reg .pred p0, p1, p2;\n\t"
@@ -260,9 +265,11 @@ __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, u
         L.mask = 0;
         L.seen = 0;
     }
+#if !K3_BLIND
     fetch_word_async(slot, masks64 + L.widx, enter);
     fetch_commit();
     L.age = enter ? 0u : (L.age < (unsigned)K3_STAGES + 1u ? L.age + 1u : (unsigned)K3_STAGES + 1u);
+#endif
     L.mask |= lane_bit(L.P);
     return !done;
 }
@@ -366,9 +373,11 @@ __global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) 
                 L.axis = (xy & xz) ? 0 : (((!xy) & yz) ? 1 : 2);
             }
             // (a dropped fetch of this lane may still be on its way into the same slot: let it land first, once per re-fill)
+#if !K3_BLIND
             fetch_wait<0>();
             fetch_word_async(slot0 + (K3_STAGES - 1) * K3_THREADS * 8u, masks64 + L.widx, take);
             fetch_commit();
+#endif
             continue;
         }
         if (act == 0) break;   // no ray left anywhere in this warp

@@ -178,12 +178,15 @@ def merged_insert(n_scans, rank, world, compute_delta, apply_delta, make_buffer,
 class OctreeSharder:
     """Glue between merged_insert and the GPU OcTree of this package (device buffers are torch CUDA uint8 tensors)."""
 
-    def __init__(self, tree, get_scan, maxrange=-1.0, owner_partition=False, rank=0, world=1, get_scan_batch=None):
+    def __init__(self, tree, get_scan, maxrange=-1.0, owner_partition=False, rank=0, world=1, get_scan_batch=None, state=None):
         """get_scan(s) -> (points, origin).  get_scan_batch(first, n) -> (points buffer with the n scans back to back,
-        per-scan point counts, origins (n, 3)): optional, lets a round's scans go through one library call."""
+        per-scan point counts, origins (n, 3)): optional, lets a round's scans go through one library call.
+        state: a dict the caller keeps between runs (record / exchange buffers are allocated once and reused)."""
         self.tree, self.get_scan, self.maxrange = tree, get_scan, float(maxrange)
         self.owner_partition, self.rank, self.world = owner_partition, rank, world
         self.get_scan_batch = get_scan_batch
+        self.state = state if state is not None else {}
+        self._buf = self.state.get("buf")
 
     def make_buffer(self, nbytes):
         """Record buffer of this rank, kept across rounds and runs (a too small buffer costs a re-cast of the round)."""
@@ -191,6 +194,7 @@ class OctreeSharder:
         want = max(int(nbytes), 32 << 20)
         if getattr(self, "_buf", None) is None or self._buf.numel() < want:
             self._buf = torch.empty(want, dtype=torch.uint8, device=torch.device("cuda", self.tree._ctx.device))
+            self.state["buf"] = self._buf
         return self._buf
 
     def compute_delta(self, scan_idx, out, offset):
