@@ -103,9 +103,10 @@ def imread_batch(paths, mode="gray", channel=1, out=None, n_threads=0):
     return out
 
 
-def read_frame_batch(paths, mode="gray", max_frames=256):
+def read_frame_batch(paths, mode="gray", max_frames=256, alloc=None):
     """Longest prefix of `paths` (at most max_frames) that decodes to equally shaped frames of one dtype, as one (n, H, W)
     stack: PNG prefixes go through the thread-pool decoder in one call, anything else frame by frame.
+    alloc(shape, dtype) -> array to decode into (e.g. a view of pinned memory); default: a fresh numpy array.
     Returns (stack, n_consumed)."""
     one = {"gray": imread_gray, "raw": imread_raw, "green": imread_unchanged_green}[mode]
     bmode, chan = {"gray": ("gray", 0), "raw": ("raw", 0), "green": ("channel", 1)}[mode]
@@ -120,7 +121,10 @@ def read_frame_batch(paths, mode="gray", max_frames=256):
                 break
             n += 1
         try:
-            return imread_batch(paths[:n], bmode, channel=chan), n
+            dst = None
+            if alloc is not None:
+                dst = alloc((n, h, w), np.uint8 if (bmode == "gray" or d == 8) else np.uint16)
+            return imread_batch(paths[:n], bmode, channel=chan, out=dst), n
         except ValueError:
             pass        # a file of the prefix has a defect only the decode finds: frame by frame below (OpenCV has the last word)
     first = one(paths[0])
@@ -130,7 +134,21 @@ def read_frame_batch(paths, mode="gray", max_frames=256):
         if img.shape != first.shape or img.dtype != first.dtype:
             break
         batch.append(img)
+    if alloc is not None:
+        dst = alloc((len(batch),) + first.shape, first.dtype)
+        for i, img in enumerate(batch):
+            dst[i] = img
+        return dst, len(batch)
     return np.stack(batch), len(batch)
+
+
+def frame_pixels(path):
+    """W * H of a depth image without decoding it when it is a PNG the native decoder serves (header only)."""
+    if _native_png(path):
+        w, h, _, _ = png_info(path)
+        return w * h
+    img = imread_gray(path)
+    return int(img.shape[0]) * int(img.shape[1])
 
 
 def _native_png(path):

@@ -107,17 +107,20 @@ def sequence_to_octree(depths, quats, trans, intr, resolution=0.1, maxrange=80.0
 
 def pose_sequence_to_bt(qt_path, file_bt, intr, depth_dir='./depth/', resolution=0.1, maxrange=80.0, pose_format="comma",
                         raw_depth=False, **kw):
-    """Pose file + depth PNGs -> .bt, the file-level form of sequence_to_octree."""
+    """Pose file + depth PNGs -> .bt, the file-level form of sequence_to_octree, streamed (decode overlaps the GPU work)."""
+    from . import streaming
     poses = formats.read_pose_file(qt_path) if pose_format == "comma" else formats.read_colmap_images_txt(qt_path)
     tree = None
-    k, n = 0, len(poses["names"])
-    while k < n:
-        stack, used = formats.read_frame_batch([os.path.join(depth_dir, nm) for nm in poses["names"][k:k + 64]],
-                                               "raw" if raw_depth else "gray", max_frames=64)
-        j = k + used
-        tree = sequence_to_octree(stack, poses["q"][k:j], poses["t"][k:j], intr, resolution=resolution, maxrange=maxrange,
-                                  tree=tree, **kw)
-        k = j
+    # batch k + 1 is decoded into pinned memory on a worker thread while batch k is back-projected and ray-cast
+    dec = streaming.BatchDecoder([os.path.join(depth_dir, nm) for nm in poses["names"]], "raw" if raw_depth else "gray", 64)
+    try:
+        k = 0
+        for stack, used in dec:
+            tree = sequence_to_octree(stack, poses["q"][k:k + used], poses["t"][k:k + used], intr, resolution=resolution, maxrange=maxrange,
+                                      tree=tree, **kw)
+            k += used
+    finally:
+        dec.close()
     if tree is None:
         tree = OcTree(resolution, device=DEVICE)
     tree.updateInnerOccupancy()

@@ -281,6 +281,20 @@ class Context:
         del keep
         return buf[: need.value].tobytes()
 
+    def format_rows_into(self, xyz_dev, n, out, kind="ply", z_is_integer=False):
+        """K6 from a DEVICE (n, 3) float64 buffer into a caller-provided host byte array (pinned memory from
+        streaming.PinnedBuffer is the fast case): kind "ply" = genply's "%.4f %.4f %.4f \\n" rows, "txt" = the txt files'
+        str(float64) rows.  Returns the number of bytes the rows take; when that exceeds out.size nothing was written
+        (call again with a larger array)."""
+        p = _ptr(xyz_dev)
+        need = C.c_size_t(0)
+        if kind == "ply":
+            rc = self.lib.r3d_format_ply_rows(self._h, p, p + 8, p + 16, 3, int(n), None, out.ctypes.data, out.size, C.byref(need))
+        else:
+            rc = self.lib.r3d_format_txt_rows(self._h, p, p + 8, p + 16, 3, int(n), 1 if z_is_integer else 0, out.ctypes.data, out.size, C.byref(need))
+        check(rc, self._h)
+        return int(need.value)
+
     def transform_points(self, xyz, T):
         """T . [x y z 1]^T for an (n,3) float64 cloud (other_tools/transfer_T_icp.py:10-12)."""
         p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)

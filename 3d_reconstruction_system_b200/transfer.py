@@ -151,39 +151,84 @@ def sequence_to_world(depths, quats, trans, intr=None, mode=MODE_DEPTH, depth_sc
                            out_dtype=out_dtype, compact=compact)
 
 
-def get_file_name(qt_path, intr=None, write_intermediate=True, ply_path=None, pose_format="comma"):
-    """Sequence driver (camera_to_world.py:138-174): pose file -> per frame depth PNG -> world points -> one merged PLY.
-    Frames are read with IMREAD_GRAYSCALE like the reference and pushed through ONE fused kernel launch per image
-    shape; write_intermediate keeps the reference's side files (./point/<name>.txt per frame and the world txt)."""
+def _rows_to_file(ctx, xyz_dev, n, path, kind, z_is_integer=False):
+    """One small text file from device points (the per-frame side files of the reference)."""
+    cap = n * (48 if kind == "ply" else 64) + 64
+    buf = np.empty(cap, dtype=np.uint8)
+    need = ctx.format_rows_into(xyz_dev, n, buf, kind, z_is_integer)
+    if need > cap:
+        buf = np.empty(need, dtype=np.uint8)
+        need = ctx.format_rows_into(xyz_dev, n, buf, kind, z_is_integer)
+    with open(path, "wb") as f:
+        f.write(memoryview(buf)[:need])
+
+
+def get_file_name(qt_path, intr=None, write_intermediate=True, ply_path=None, pose_format="comma", keep_points=False, max_frames=None,
+                  quiet=False, frames_per_batch=64):
+    """Sequence driver (camera_to_world.py:138-174): pose file -> per frame depth PNG -> world points -> one merged PLY,
+    STREAMED: frame batches are decoded (IMREAD_GRAYSCALE semantics) into pinned memory on a worker thread while the batch
+    before is on the GPU; a batch goes through ONE fused kernel launch per ring chunk, its float64 world points stay on the
+    device and are formatted there (K6); only text comes back, and it is appended to the PLY by a writer thread while the
+    next batch is formatted.  The PLY's vertex count is known up front (every pixel of every frame is a vertex), so the
+    file is written front to back and host memory is bounded by two batches for any sequence length.
+    write_intermediate keeps the reference's side files (./point/<name>.txt per frame, and the world txt, which the
+    reference re-opens with 'w' for every frame so that only the last frame's survives).  Returns None like the reference,
+    or (x, y, z) of every world point with keep_points=True."""
+    from . import streaming
     poses = formats.read_pose_file(qt_path) if pose_format == "comma" else formats.read_colmap_images_txt(qt_path)
-    print('data start transfer')
-    n = len(poses["names"])
-    xs, ys, zs = [], [], []
-    k = 0
-    while k < n:
-        t1 = time.time()
-        stack, used = formats.read_frame_batch([os.path.join(DEPTH_DIR, nm) for nm in poses["names"][k:k + 256]], "gray")
-        j = k + used
-        batch = stack
-        world, _ = sequence_to_world(stack, poses["q"][k:j], poses["t"][k:j], intr, out_dtype=np.float64)
-        world = world.reshape(j - k, -1, 3)
-        if write_intermediate:
-            cam, _ = default_context(DEVICE).backproject(stack, _intr(intr), rt=None, out_dtype=np.float64)
-            cam = cam.reshape(j - k, -1, 3)
-            for i in range(j - k):
-                name = poses["names"][k + i]
-                _write_xyz_txt(os.path.join(POINT_DIR, name[0:-4] + '.txt'), cam[i, :, 0], cam[i, :, 1], cam[i, :, 2], z_raw=batch[i])
-            _write_xyz_txt(POINT_WORLD_PATH, world[-1, :, 0], world[-1, :, 1], world[-1, :, 2])
-        xs.append(world[:, :, 0].ravel())
-        ys.append(world[:, :, 1].ravel())
-        zs.append(world[:, :, 2].ravel())
-        t2 = time.time()
-        print('##################')
-        print("two epoch cost .", t2 - t1)
-        print('the picture generation is: ', j)
-        k = j
-    x = np.concatenate(xs) if xs else np.zeros(0)
-    y = np.concatenate(ys) if ys else np.zeros(0)
-    z = np.concatenate(zs) if zs else np.zeros(0)
-    genply([x, y, z], ply_path or PLY_PATH, x.size)
-    return x, y, z
+    say = (lambda *a: None) if quiet else print
+    say('data start transfer')
+    names = poses["names"] if max_frames is None else poses["names"][:max_frames]
+    n = len(names)
+    paths = [os.path.join(DEPTH_DIR, nm) for nm in names]
+    ctx = default_context(DEVICE)
+    total = sum(formats.frame_pixels(p) for p in paths)
+    kept = []
+    dec = streaming.BatchDecoder(paths, "gray", frames_per_batch)
+    slots = streaming.TextSlots()
+    with open(ply_path or PLY_PATH, "wb") as f:
+        f.write((formats.PLY_HEADER_XYZ % total).encode("ascii"))
+        writer = streaming.AsyncFileWriter(f)
+        try:
+            k = 0
+            for stack, used in dec:
+                t1 = time.time()
+                j = k + used
+                H, W = int(stack.shape[1]), int(stack.shape[2])
+                npts = used * H * W
+                rt = ctx.pose_to_rt(poses["q"][k:j], poses["t"][k:j])
+                world = ctx.device_empty((npts, 3), np.float64)
+                ctx.backproject(stack, _intr(intr), rt=rt, out=world)          # pinned stack -> staging ring -> device records
+                slot, buf = slots.acquire(npts * 40 + 64)
+                need = ctx.format_rows_into(world, npts, buf, "ply")
+                if need > buf.size:
+                    buf = slots.regrow(slot, need)
+                    need = ctx.format_rows_into(world, npts, buf, "ply")
+                writer.write(memoryview(buf)[:need], slots.releaser(slot))
+                if keep_points:
+                    kept.append(world.numpy())
+                if write_intermediate:
+                    cam = ctx.device_empty((npts, 3), np.float64)
+                    ctx.backproject(stack, _intr(intr), rt=None, out=cam)
+                    for i in range(used):
+                        # Z is printed as the integer pixel value, as the reference does (it is still np.uint8 there)
+                        _rows_to_file(ctx, cam[i * H * W:(i + 1) * H * W], H * W, os.path.join(POINT_DIR, names[k + i][0:-4] + '.txt'), "txt", True)
+                    cam.free()
+                    if j == n:
+                        _rows_to_file(ctx, world[(used - 1) * H * W:], H * W, POINT_WORLD_PATH, "txt")
+                world.free()
+                t2 = time.time()
+                say('##################')
+                say("two epoch cost .", t2 - t1)
+                say('the picture generation is: ', j)
+                k = j
+        finally:
+            writer.close()
+            slots.close()
+            dec.close()
+        f.write(formats.PLY_TRAILER.encode("ascii"))
+    say("Write into .ply file Done.")
+    if keep_points:
+        w = np.concatenate(kept) if kept else np.zeros((0, 3))
+        return w[:, 0].copy(), w[:, 1].copy(), w[:, 2].copy()
+    return None
