@@ -50,7 +50,7 @@ def brick_owner(keys_u64, world):
 
 
 def allgather_varlen(payload, counts, group=None):
-    """All-gather of one variable-length uint8 payload per rank.
+    """All-gather of one variable-length uint8 payload per rank (utility; the merge below uses fixed slots instead).
 
     payload: 1-D uint8 tensor (CPU for gloo, CUDA for nccl) holding this rank's records back to back.
     counts:  1-D int64 tensor (same device) with this rank's per-scan record counts (fixed length on every rank).
@@ -76,63 +76,124 @@ def allgather_varlen(payload, counts, group=None):
     return [recv[r * maxb:r * maxb + int(nbytes[r].item())] for r in range(world)], counts_all
 
 
-def _start_gather(payload, counts, group, sync_stream):
-    """Counts all-gather (small, blocking) then the payload all-gather, asynchronous: returns (work, recv, counts_host, maxb).
-    The payload is first copied into a private send buffer (the caller reuses its own for the next round)."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    counts_all = torch.empty((world, counts.numel()), dtype=torch.int64, device=counts.device)
-    dist.all_gather_into_tensor(counts_all.view(-1), counts.contiguous(), group=group)
-    counts_host = counts_all.cpu().numpy()
-    maxb = int(counts_host.sum(axis=1).max()) * RECORD_BYTES
-    if maxb == 0:
-        return None, None, counts_host, 0
-    send = torch.zeros(maxb, dtype=torch.uint8, device=payload.device)
-    send[:payload.numel()] = payload
-    if sync_stream is not None:
-        sync_stream()              # the copy above must have read `payload` before the caller overwrites it
-    recv = torch.empty(world * maxb, dtype=torch.uint8, device=payload.device)
-    work = dist.all_gather_into_tensor(recv, send, group=group, async_op=True)
-    return (work, send), recv, counts_host, maxb
+class _Exchange:
+    """The one exchange step of the merge: per round every rank contributes ONE fixed-size slot -- a header (payload bytes,
+    bytes it would have needed, per-scan record counts) followed by its records -- and one all-gather moves all slots.
+    No separate counts collective, no per-round allocation, no zero-fill: send / receive buffers are double-buffered
+    (round r + 1 is packed and sent while round r is applied) and kept in `state` between runs.  A rank whose records do
+    not fit its slot says so in its header; every rank sees that in the same round and the slots are regrown."""
+
+    def __init__(self, world, scans_per_rank, device, state, group):
+        self.world, self.C, self.device, self.group, self.state = world, scans_per_rank, device, group, state
+        self.hdr_words = 2 + scans_per_rank
+        self.hdr_bytes = ((self.hdr_words * 8 + 255) // 256) * 256        # payload starts 256-byte aligned (device records want 8)
+        self.slot = 0
+        key = ("xchg", str(device), world, scans_per_rank)
+        if key in state:
+            self.slot, self.send, self.recv = state[key]
+        else:
+            self._alloc(max(int(state.get("slot_hint", 0)), int(state.get("slot_min", 1 << 20))))
+        self.key = key
+
+    def _alloc(self, payload_bytes):
+        import torch
+        self.slot = self.hdr_bytes + ((int(payload_bytes) + 255) // 256) * 256
+        self.send = [torch.empty(self.slot, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.recv = [torch.empty(self.world * self.slot, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.state[("xchg", str(self.device), self.world, self.C)] = (self.slot, self.send, self.recv)
+
+    def capacity(self):
+        return self.slot - self.hdr_bytes
+
+    def start(self, parity, payload, counts):
+        """Pack this rank's slot and start the all-gather; returns the work handle."""
+        import torch
+        import torch.distributed as dist
+        nbytes = int(payload.numel())
+        fits = nbytes <= self.capacity()
+        hdr = torch.zeros(self.hdr_words, dtype=torch.int64)
+        hdr[0] = nbytes if fits else 0
+        hdr[1] = nbytes
+        for i, c in enumerate(counts):
+            hdr[2 + i] = int(c)
+        send = self.send[parity]
+        send[:self.hdr_words * 8].copy_(hdr.view(torch.uint8), non_blocking=True)
+        if fits and nbytes:
+            send[self.hdr_bytes:self.hdr_bytes + nbytes].copy_(payload, non_blocking=True)
+        return dist.all_gather_into_tensor(self.recv[parity], send, group=self.group, async_op=True)
+
+    def headers(self, parity):
+        """(world, 2 + C) int64 on the host (one small read-back)."""
+        import torch
+        recv = self.recv[parity].view(self.world, self.slot)
+        return recv[:, :self.hdr_words * 8].contiguous().view(torch.int64).view(self.world, self.hdr_words).cpu().numpy()
+
+    def payload(self, parity, rank, nbytes):
+        off = rank * self.slot + self.hdr_bytes
+        return self.recv[parity][off:off + nbytes]
 
 
 def merged_insert(n_scans, rank, world, compute_delta, apply_delta, make_buffer, group=None, scans_per_rank=4, fence=None,
-                  compute_round=None, apply_round=None, overlap=False):
-    """Scan-ordered multi-GPU insertPointCloud.  overlap=True software-pipelines the rounds: while round r's records
-    travel (asynchronous all-gather), round r-1 is applied and round r+1 is ray-cast.  Measured on 2 x B200 it is SLOWER
-    than the plain sequence (1 340 vs 1 620 scans/s): the persistent ray-casting kernel fills every SM, the NCCL kernel
-    waits for CTA slots and then spins on its peer while holding them, so the default applies a round as soon as it has
-    been gathered.
+                  compute_round=None, apply_round=None, overlap=True, state=None):
+    """Scan-ordered multi-GPU insertPointCloud.  Rounds of world * scans_per_rank consecutive scans; rank r ray-casts scans
+    [base + r*C, base + (r+1)*C) of a round, the rounds' records are exchanged (one all-gather of fixed slots, _Exchange)
+    and every rank applies them in global scan order.  overlap=True software-pipelines the rounds: round r's records travel
+    and are applied while round r + 1 is ray-cast (the exchange is started BEFORE the next round's ray casting is queued,
+    its records are applied right after that ray casting has been queued).
 
     compute_delta(scan_idx, out, offset_bytes) -> n_records | (n_records, new_out): ray-casts one scan and writes its
         records into the uint8 tensor `out` at `offset_bytes` (it may grow the tensor and return the new one).
     apply_delta(records_tensor, n_records, scan_idx): applies one scan's records (a 1-D uint8 view) to the local map.
     compute_round(first_scan, n, out) -> (counts list, out) and apply_round(payload_tensor, counts list, first_scan):
         optional batched forms of the two (one library call per round and rank instead of one per scan).
-    make_buffer(nbytes) -> 1-D uint8 tensor on the exchange device.
+    make_buffer(nbytes) -> 1-D uint8 tensor on the exchange device (this rank's record buffer).
     fence(): called after a collective completed and before its data is applied (stream hand-over between torch and the
-        library); also used to make sure a send buffer has been read.
+        library).
+    state: dict kept by the caller between runs (exchange buffers are allocated once).
     Returns the number of records applied locally."""
     import torch
     applied = 0
-    buf = make_buffer(1 << 20)
+    state = state if state is not None else {}
+    bufs = [make_buffer(1 << 20), None]          # this rank's records of the round in flight / the round being cast
+    xchg = None
+
+    def cast(first, n_mine, buf):
+        counts = [0] * scans_per_rank
+        off = 0
+        if compute_round is not None and n_mine:
+            cnts, buf = compute_round(first, n_mine, buf)
+            for i, c in enumerate(cnts):
+                counts[i] = int(c)
+            off = sum(counts) * RECORD_BYTES
+        else:
+            for i in range(n_mine):
+                res = compute_delta(first + i, buf, off)
+                if isinstance(res, tuple):
+                    n_rec, buf = res
+                else:
+                    n_rec = res
+                counts[i] = int(n_rec)
+                off += int(n_rec) * RECORD_BYTES
+        return counts, off, buf
 
     def finish(pending):
+        """Wait for a round's exchange and apply it; returns False when some rank's records did not fit (nothing applied)."""
         nonlocal applied
-        handle, recv, counts_host, maxb, parts = pending
-        if handle is not None:
-            handle[0].wait()
-            if fence is not None:
-                fence()
+        work, parity, parts = pending
+        work.wait()
+        if fence is not None:
+            fence()
+        hdr = xchg.headers(parity)
+        if int(hdr[:, 1].max()) > xchg.capacity():
+            return False, int(hdr[:, 1].max())
         for r, a, n in parts:
-            if n == 0 or maxb == 0:
+            if n == 0:
                 continue
-            cnts = [int(c) for c in counts_host[r, :n]]
+            cnts = [int(c) for c in hdr[r, 2:2 + n]]
             total = sum(cnts)
             if total == 0:
                 continue
-            seg = recv[r * maxb:r * maxb + total * RECORD_BYTES]
+            seg = xchg.payload(parity, r, total * RECORD_BYTES)
             if apply_round is not None:
                 apply_round(seg, cnts, a)
             else:
@@ -142,36 +203,54 @@ def merged_insert(n_scans, rank, world, compute_delta, apply_delta, make_buffer,
                         apply_delta(seg[o:o + c * RECORD_BYTES], c, a + i)
                     o += c * RECORD_BYTES
             applied += total
+        return True, 0
 
-    pending = None
-    for base, parts in scan_rounds(n_scans, world, scans_per_rank):
+    rounds = list(scan_rounds(n_scans, world, scans_per_rank))
+    pending = None                                # (work, parity, parts) of the round whose records are travelling
+    kept = {}                                     # parity -> (counts, nbytes) of the rounds not yet applied (for a regrow)
+    for k, (base, parts) in enumerate(rounds):
+        parity = k & 1
         _, first, n_mine = parts[rank]
-        counts = torch.zeros(scans_per_rank, dtype=torch.int64)
-        off = 0
-        if compute_round is not None and n_mine:
-            cnts, buf = compute_round(first, n_mine, buf)
-            for i, c in enumerate(cnts):
-                counts[i] = int(c)
-            off = int(sum(int(c) for c in cnts)) * RECORD_BYTES
-        else:
-            for i in range(n_mine):
-                res = compute_delta(first + i, buf, off)
-                if isinstance(res, tuple):
-                    n_rec, buf = res
-                else:
-                    n_rec = res
-                counts[i] = n_rec
-                off += int(n_rec) * RECORD_BYTES
-        counts = counts.to(buf.device)
-        handle, recv, counts_host, maxb = _start_gather(buf[:off], counts, group, fence)
-        if pending is not None:
-            finish(pending)
-        pending = (handle, recv, counts_host, maxb, parts)
-        if not overlap:
-            finish(pending)
+        if bufs[parity] is None:
+            bufs[parity] = make_buffer(1 << 20) if parity == 0 else torch.empty_like(bufs[0])
+        counts, nbytes, bufs[parity] = cast(first, n_mine, bufs[parity])
+        if xchg is None:
+            xchg = _Exchange(world, scans_per_rank, bufs[parity].device, state, group)
+        kept[parity] = (counts, nbytes)
+        work = xchg.start(parity, bufs[parity][:nbytes], counts)
+        cur = (work, parity, parts)
+        last = k + 1 == len(rounds)
+        # pipelined: apply the round before this one now (its records arrived while this round was ray-cast) and leave
+        # this round's exchange in flight; otherwise (and for the last round) apply this round too
+        todo = [it for it in ([pending] + ([cur] if (not overlap or last) else [])) if it is not None]
+        pending = cur if (overlap and not last) else None
+        for n_done, item in enumerate(todo):
+            ok, need = finish(item)
+            if ok:
+                continue
+            # Some rank's records did not fit its slot; every rank sees that in this same round.  Let everything in flight
+            # land, regrow the slots, and exchange the rounds not yet applied again, in order (their records are kept).
+            redo = todo[n_done:] + ([pending] if pending is not None else [])
+            for it in redo:
+                it[0].wait()
+            if fence is not None:
+                fence()
+            state["slot_hint"] = need + need // 2
+            xchg._alloc(state["slot_hint"])
+            for it in redo:
+                c2, nb2 = kept[it[1]]
+                ok2, need2 = finish((xchg.start(it[1], bufs[it[1]][:nb2], c2), it[1], it[2]))
+                if not ok2:       # a later round needs even more
+                    state["slot_hint"] = need2 + need2 // 2
+                    xchg._alloc(state["slot_hint"])
+                    ok2, _ = finish((xchg.start(it[1], bufs[it[1]][:nb2], c2), it[1], it[2]))
+                    assert ok2, "exchange slot still too small after regrowing"
             pending = None
-    if pending is not None:
-        finish(pending)
+            break
+    if xchg is not None:
+        state["exchange"] = ("one all-gather of fixed %d-byte slots per round (header with the per-scan record counts + 136-byte "
+                             "brick-delta records), double-buffered, software-pipelined with the next round's ray casting: %s"
+                             % (xchg.slot, "on" if overlap else "off"))
     return applied
 
 
@@ -194,7 +273,7 @@ class OctreeSharder:
         want = max(int(nbytes), 32 << 20)
         if getattr(self, "_buf", None) is None or self._buf.numel() < want:
             self._buf = torch.empty(want, dtype=torch.uint8, device=torch.device("cuda", self.tree._ctx.device))
-            self.state["buf"] = self._buf
+        self.state["buf"] = self._buf
         return self._buf
 
     def compute_delta(self, scan_idx, out, offset):
@@ -206,7 +285,9 @@ class OctreeSharder:
             grown = torch.empty(max(need, out.numel() * 2), dtype=torch.uint8, device=out.device)
             grown[:offset] = out[:offset]
             torch.cuda.current_stream(out.device).synchronize()
-            out = self._buf = grown
+            if out is self._buf:
+                self._buf = self.state["buf"] = grown
+            out = grown
         if n:
             self.tree.scanDeltaInto(out.data_ptr() + offset, n)
         return n, out
@@ -234,7 +315,10 @@ class OctreeSharder:
                 rec = self.tree.computeScanDeltasInto(points, counts, origins, self.maxrange, out.data_ptr(), out.numel() // RECORD_BYTES)
                 return [int(c) for c in rec], out
             except MemoryError:
-                out = self._buf = torch.empty(out.numel() * 2, dtype=torch.uint8, device=out.device)
+                grown = torch.empty(out.numel() * 2, dtype=torch.uint8, device=out.device)
+                if out is self._buf:
+                    self._buf = self.state["buf"] = grown
+                out = grown
 
     def apply_round(self, payload, counts, first_scan):
         self.tree.applyDeltasOwned(payload.data_ptr(), counts, self.rank if self.owner_partition else 0, self.world if self.owner_partition else 1)
@@ -243,10 +327,16 @@ class OctreeSharder:
         import torch
         torch.cuda.current_stream().synchronize()
 
-    def run(self, n_scans, group=None, scans_per_rank=4, overlap=False):
+    def run(self, n_scans, group=None, scans_per_rank=8, overlap=None):
+        """overlap (default on; R3D_MERGE_OVERLAP=0 turns it off): a round's exchange and apply run beside the next round's
+        ray casting."""
+        import os
+        if overlap is None:
+            overlap = os.environ.get("R3D_MERGE_OVERLAP", "1") != "0"
+        self._second = None
         return merged_insert(n_scans, self.rank, self.world, self.compute_delta, self.apply_delta, self.make_buffer, group=group,
                              scans_per_rank=scans_per_rank, fence=self.fence, compute_round=self.compute_round, apply_round=self.apply_round,
-                             overlap=overlap)
+                             overlap=overlap, state=self.state)
 
 
 def gather_bricks(tree, group=None):
@@ -268,8 +358,9 @@ def gather_bricks(tree, group=None):
     maxn = int(ch.max())
     if maxn == 0:
         return 0
-    send = torch.zeros(maxn * rec, dtype=torch.uint8, device=dev)
-    send[:n * rec] = mine[:n * rec]
+    send = mine if mine.numel() == maxn * rec else torch.empty(maxn * rec, dtype=torch.uint8, device=dev)
+    if send is not mine:
+        send[:n * rec] = mine[:n * rec]       # (the padding is never read)
     recv = torch.empty(world * maxn * rec, dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(recv, send, group=group)
     torch.cuda.current_stream().synchronize()

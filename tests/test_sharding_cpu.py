@@ -47,7 +47,7 @@ def test_brick_owner_matches_kernel_hash(r3d):
     assert np.bincount(own, minlength=8).min() > 11000      # balanced
 
 
-@pytest.mark.parametrize("world,n_scans,per_rank,mode", [(2, 23, 3, "plain"), (3, 10, 2, "plain"), (2, 4, 4, "plain"), (2, 17, 2, "overlap")])
+@pytest.mark.parametrize("world,n_scans,per_rank,mode", [(2, 23, 3, "plain"), (3, 10, 2, "plain"), (2, 4, 4, "plain"), (2, 17, 2, "overlap"), (3, 19, 2, "regrow"), (2, 9, 3, "regrow")])
 def test_scan_ordered_merge_gloo(world, n_scans, per_rank, mode):
     port = free_port()
     procs = []

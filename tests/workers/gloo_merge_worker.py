@@ -64,7 +64,9 @@ def apply_keys(tree, free, occ):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     n_scans, per_rank = int(sys.argv[1]), int(sys.argv[2])
-    overlap = len(sys.argv) > 3 and sys.argv[3] == "overlap"
+    overlap = len(sys.argv) > 3 and sys.argv[3] in ("overlap", "regrow")
+    # "regrow": exchange slots that start far too small, so that the header's "did not fit" path runs (several times)
+    state = {"slot_min": 136} if (len(sys.argv) > 3 and sys.argv[3] == "regrow") else {}
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"], rank=rank, world_size=world)
     res, maxrange = 0.1, 2.5
     caster = oo.OcTree(res)          # never updated: only computeUpdate
@@ -93,7 +95,9 @@ def main():
         apply_keys(tree, free, occ)
 
     applied = sharding.merged_insert(n_scans, rank, world, compute_delta, apply_delta, lambda nb: torch.zeros(64, dtype=torch.uint8),
-                                     scans_per_rank=per_rank, overlap=overlap)
+                                     scans_per_rank=per_rank, overlap=overlap, state=state)
+    if "slot_min" in state:
+        assert state.get("slot_hint", 0) > 136, "the regrow path did not run"
     # serial reference on every rank
     ref = oo.OcTree(res)
     ref_log = []
