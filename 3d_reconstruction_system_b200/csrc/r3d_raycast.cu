@@ -279,7 +279,10 @@ struct WalkGrid {
     uint32_t dx, dxy, cube_off;
 };
 
-__global__ void __launch_bounds__(K3_THREADS, 3) k_scan_walk(const BatchArgs a) {
+#ifndef K3_MIN_CTAS
+#define K3_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const BatchArgs a) {
     __shared__ WalkGrid sg[K3_MAX_BATCH];
     __shared__ uint32_t s_prefix[K3_MAX_BATCH + 1];
     __shared__ __align__(8) uint64_t s_words[K3_STAGES][K3_THREADS];
