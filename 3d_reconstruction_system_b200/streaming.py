@@ -27,15 +27,22 @@ class PinnedBuffer:
             want = max(need + need // 8, 1 << 20)
             self.ptr = self.lib.r3d_host_alloc(want)
             if not self.ptr:
-                raise MemoryError("r3d_host_alloc(%d) failed" % want)
-            self.nbytes = want
+                # page-locking failed (no CUDA device in this process: the decode-only tools, or the limit on locked memory):
+                # plain memory works everywhere a pinned buffer does, the copies are just slower
+                self._plain = np.empty(want, dtype=np.uint8)
+                self.nbytes = want
+            else:
+                self._plain = None
+                self.nbytes = want
+        if getattr(self, "_plain", None) is not None:
+            return self._plain[:need].view(dt).reshape(shape)
         ct = (C.c_uint8 * max(need, 1)).from_address(self.ptr)
         return np.frombuffer(ct, dtype=dt, count=need // dt.itemsize).reshape(shape)
 
     def free(self):
         if self.ptr:
             self.lib.r3d_host_free(self.ptr)
-        self.ptr, self.nbytes = None, 0
+        self.ptr, self.nbytes, self._plain = None, 0, None
 
     def __del__(self):
         try:
@@ -47,7 +54,7 @@ class PinnedBuffer:
 class BatchDecoder:
     """Iterates over (stack, n_frames) prefixes of `paths` like formats.read_frame_batch, decoding batch k + 1 on a worker
     thread (the native decoder releases the GIL) into one of two pinned stacks while the caller works on batch k.  The
-    stack yielded for batch k stays valid until the caller asks for batch k + 2."""
+    stack yielded for batch k is valid until the caller asks for the next batch (its buffer then goes back to the decoder)."""
 
     def __init__(self, paths, mode="gray", frames_per_batch=64):
         self.paths, self.mode, self.fpb = list(paths), mode, int(frames_per_batch)
