@@ -40,9 +40,6 @@ constexpr int K3_MAX_BATCH = 8;
 #ifndef K3_STAGES
 #define K3_STAGES 3      // staging registers of the sub-block word fetch = iterations between request and use, plus one
 #endif
-#ifndef K3_BLIND
-#define K3_BLIND 0       // 1: never fetch the sub-block word, publish every visited sub-block unconditionally (experiment)
-#endif
 #ifndef K3_CHUNK
 #define K3_CHUNK 64      // rays a warp claims from the batch's counter at a time
 #endif
@@ -185,11 +182,10 @@ struct WalkLane {
     uint32_t cell, ecell;  // brick cell (index into the slot's cubes) / end cell
     int dPx, dPy, dPz;     // P increment of one step along each axis
     int csx, csy, csz;     // cell increment of one brick step along each axis
-    int axis;              // axis of the next step
     uint32_t widx;         // index of the current sub-block's free word in the 64-bit view of the masks
     uint64_t mask;         // cells of that sub-block visited by this ray (bit = x + 4y + 16z)
     uint64_t seen;         // what the word held when the ray entered the sub-block; 0 = not known (yet)
-    unsigned age;          // iterations since the ray entered the sub-block (saturates at 3)
+    int epos;              // position (of the unrolled step sequence) at which the word of the current sub-block was requested; -1: none pending
     unsigned steps;        // statistics: free cells recorded by this lane
 };
 
@@ -220,25 +216,27 @@ __device__ __forceinline__ uint32_t lane_widx(uint32_t cell, uint32_t P) { retur
 // `slot` is the shared-memory slot (of this lane, for this position of the unrolled step sequence) the word fetched on
 // entering a sub-block lands in; the word is moved into `seen` K3_STAGES steps after it was requested; a ray that leaves
 // a sub-block earlier publishes without knowing the word (a redundant red.or, never a wrong bit).
+template <int kPos>
 __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, uint32_t total_cells, uint32_t* miss, WalkLane& L, uint32_t slot) {
-#if !K3_BLIND
+    // the word requested K3_STAGES steps ago (same position of the sequence) has landed: it is what the sub-block held
     fetch_wait<K3_STAGES - 1>();
-    if (L.age == K3_STAGES - 1) L.seen = lds_u64(slot);
-#endif
+    if (L.epos == kPos) { L.seen = lds_u64(slot); L.epos = -1; }
     const uint32_t Pold = L.P;
     int cs;
-    asm("{\n\t.reg .pred p0, p1, p2;\n\t"
-        "setp.eq.s32 p0, %5, 0;\n\tsetp.eq.s32 p1, %5, 1;\n\tsetp.eq.s32 p2, %5, 2;\n\t"
-        "@p0 add.s32 %0, %0, %6;\n\t@p1 add.s32 %0, %0, %7;\n\t@p2 add.s32 %0, %0, %8;\n\t"
-        "@p0 add.rn.f64 %2, %2, %9;\n\t@p1 add.rn.f64 %3, %3, %10;\n\t@p2 add.rn.f64 %4, %4, %11;\n\t"
-        "mov.s32 %1, %14;\n\t@p0 mov.s32 %1, %12;\n\t@p1 mov.s32 %1, %13;\n\t}"
+    // axis of this step (upstream's comparison chain), then tMax += tDelta and position += step on that axis only.  The
+    // three mutually exclusive updates are written without selects on the (busy) integer pipe: tMax through an FMA with a
+    // 1.0 / 0.0 multiplier on the (idle) fp64 pipe -- fma(1, d, t) = rn(t + d) and fma(0, d, t) = t are exact -- and the
+    // position through predicated adds.
+    asm("{\n\t.reg .pred pxy, psx, psy, psz;\n\t.reg .b32 hx, hy, hz, zero;\n\t.reg .f64 mx, my, mz;\n\t"
+        "setp.lt.f64 pxy, %2, %3;\n\tsetp.lt.and.f64 psx, %2, %4, pxy;\n\tsetp.lt.and.f64 psy, %3, %4, !pxy;\n\t"
+        "or.pred psz, psx, psy;\n\tnot.pred psz, psz;\n\t"
+        "selp.b32 hx, 0x3FF00000, 0, psx;\n\tselp.b32 hy, 0x3FF00000, 0, psy;\n\tselp.b32 hz, 0x3FF00000, 0, psz;\n\t"
+        "mov.b32 zero, 0;\n\tmov.b64 mx, {zero, hx};\n\tmov.b64 my, {zero, hy};\n\tmov.b64 mz, {zero, hz};\n\t"
+        "fma.rn.f64 %2, mx, %8, %2;\n\tfma.rn.f64 %3, my, %9, %3;\n\tfma.rn.f64 %4, mz, %10, %4;\n\t"
+        "@psx add.s32 %0, %0, %5;\n\t@psy add.s32 %0, %0, %6;\n\t@psz add.s32 %0, %0, %7;\n\t"
+        "mov.s32 %1, %13;\n\t@psx mov.s32 %1, %11;\n\t@psy mov.s32 %1, %12;\n\t}"
         : "+r"(L.P), "=&r"(cs), "+d"(L.tmx), "+d"(L.tmy), "+d"(L.tmz)
-        : "r"(L.axis), "r"(L.dPx), "r"(L.dPy), "r"(L.dPz), "d"(L.tdx), "d"(L.tdy), "d"(L.tdz), "r"(L.csx), "r"(L.csy), "r"(L.csz));
-    // next axis
-    asm("{\n\t.reg .pred pxy, psx, psy;\n\t"
-        "setp.lt.f64 pxy, %1, %2;\n\tsetp.lt.and.f64 psx, %1, %3, pxy;\n\tsetp.lt.and.f64 psy, %2, %3, !pxy;\n\t"
-        "selp.s32 %0, 1, 2, psy;\n\tselp.s32 %0, 0, %0, psx;\n\t}"
-        : "=&r"(L.axis) : "d"(L.tmx), "d"(L.tmy), "d"(L.tmz));
+        : "r"(L.dPx), "r"(L.dPy), "r"(L.dPz), "d"(L.tdx), "d"(L.tdy), "d"(L.tdz), "r"(L.csx), "r"(L.csy), "r"(L.csz));
     const bool past = (L.tmx > L.len) & (L.tmy > L.len) & (L.tmz > L.len);
     // brick / sub-block bookkeeping on the packed position
     const bool new_brick = (~L.P & 0x00080808u) != 0u;
@@ -264,14 +262,18 @@ __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, u
         L.widx = lane_widx(L.cell, L.P);
         L.mask = 0;
         L.seen = 0;
+        L.epos = kPos;
     }
-#if !K3_BLIND
     fetch_word_async(slot, masks64 + L.widx, enter);
     fetch_commit();
-    L.age = enter ? 0u : (L.age < (unsigned)K3_STAGES + 1u ? L.age + 1u : (unsigned)K3_STAGES + 1u);
-#endif
     L.mask |= lane_bit(L.P);
     return !done;
+}
+
+template <int kPos>
+__device__ __forceinline__ void walk_sequence(uint64_t* masks64, uint8_t* touched, uint32_t total_cells, uint32_t* miss, WalkLane& L, uint32_t slot0, bool& active) {
+    if (active) active = walk_step<kPos>(masks64, touched, total_cells, miss, L, slot0 + (uint32_t)kPos * K3_THREADS * 8u);
+    if constexpr (kPos + 1 < K3_STAGES) walk_sequence<kPos + 1>(masks64, touched, total_cells, miss, L, slot0, active);
 }
 
 struct WalkGrid {
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const Bat
     bool active = false, exhausted = false;
     WalkLane L;
     memset(&L, 0, sizeof L);
-    L.age = K3_STAGES + 1;
+    L.epos = -1;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(&s_words[0][threadIdx.x]);
     // rays are claimed from the batch's counter K3_CHUNK at a time per warp (one atomic round trip per chunk, not per re-fill)
     uint32_t my_next = 0, my_end = 0;
@@ -366,32 +368,24 @@ __global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const Bat
                     touched[L.ecell] = 1;
                 }
                 active = true;
-                // the origin cell is the first free cell; its word is requested like any other sub-block's (into the last slot:
-                // words still on their way were dropped when the step loop was left)
+                // the origin cell is the first free cell; its word is requested like any other sub-block's, into the last slot
+                // (a fetch of the lane's previous ray may still be on its way there: fetch_wait<0> below)
                 L.widx = lane_widx(L.cell, L.P);
                 L.seen = 0;
-                L.age = 0;
+                L.epos = K3_STAGES - 1;
                 L.mask = lane_bit(L.P);
-                const bool xy = L.tmx < L.tmy, xz = L.tmx < L.tmz, yz = L.tmy < L.tmz;
-                L.axis = (xy & xz) ? 0 : (((!xy) & yz) ? 1 : 2);
             }
             // (a dropped fetch of this lane may still be on its way into the same slot: let it land first, once per re-fill)
-#if !K3_BLIND
             fetch_wait<0>();
             fetch_word_async(slot0 + (K3_STAGES - 1) * K3_THREADS * 8u, masks64 + L.widx, take);
             fetch_commit();
-#endif
             continue;
         }
         if (act == 0) break;   // no ray left anywhere in this warp
         const int keep_going = exhausted ? 0 : 32 - K3_REFILL_MIN;
         do {
-#pragma unroll
-            for (int k = 0; k < K3_STAGES; ++k)
-                if (active) active = walk_step(masks64, touched, total_cells, miss, L, slot0 + (uint32_t)k * K3_THREADS * 8u);
+            walk_sequence<0>(masks64, touched, total_cells, miss, L, slot0, active);
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keep_going);
-        // fetched words still on their way are dropped (their rays publish without them): the re-fill reuses the last slot
-        if (L.age < (unsigned)K3_STAGES) L.age = K3_STAGES + 1;
     }
     // statistics only: free-cell visits of this batch
     unsigned long long steps = L.steps;
