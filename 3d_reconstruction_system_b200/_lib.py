@@ -62,6 +62,8 @@ SIGNATURES = {
     "r3d_tree_insert_scans": (_i32, [_vp, _vp, _vp, _vp, C.c_uint32, _dbl, _i32]),
     "r3d_scan_deltas_compute": (_i32, [_vp, _vp, _vp, _vp, C.c_uint32, _dbl, _i32, _vp, _u64, _vp]),
     "r3d_tree_apply_deltas_owned": (_i32, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "r3d_tree_defer_deltas_owned": (_i32, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "r3d_tree_flush_deferred": (_i32, [_vp]),
     "r3d_scan_delta_compute": (_i32, [_vp, _vp, _u64, _vp, _dbl, _i32, _u64p]),
     "r3d_scan_delta_export": (_i32, [_vp, _vp, _u64, _u64p]),
     "r3d_tree_apply_delta": (_i32, [_vp, _vp, _u64]),

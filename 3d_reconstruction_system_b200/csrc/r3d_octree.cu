@@ -500,7 +500,22 @@ int tree_sync_counters(r3d_tree* t) {
     return R3D_OK;
 }
 
+int tree_flush_deferred(r3d_tree* t) {
+    if (t->deferred.empty()) return R3D_OK;
+    std::vector<r3d_tree::Deferred> jobs;
+    jobs.swap(t->deferred);          // (apply_delta_impl may come back here through tree_settle)
+    for (const auto& j : jobs) {
+        const DeltaRecord* d = j.recs;
+        for (uint64_t c : j.counts) {
+            R3D_TRY(apply_delta_impl(t, d, c, j.part, j.nparts));
+            d += c;
+        }
+    }
+    return R3D_OK;
+}
+
 int tree_settle(r3d_tree* t) {
+    R3D_TRY(tree_flush_deferred(t));
     if (!t->pool_dirty) return R3D_OK;
     return tree_sync_counters(t);
 }
@@ -758,6 +773,7 @@ static int scan_delta_impl(r3d_tree* t, const float* xyz, uint64_t n, const floa
 
 int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_t part, uint32_t nparts) {
     r3d_ctx* ctx = t->ctx;
+    R3D_TRY(tree_flush_deferred(t));     // order: whatever was deferred comes first
     if (n == 0) return R3D_OK;
     // sized from the host-side upper bound of the pool cursor: no read-back between a scan's apply and the next scan.
     // When the BOUND (not necessarily the pool) would outgrow the capacity, read the exact cursor back first: several
@@ -821,6 +837,7 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
 extern "C" int r3d_tree_clear(r3d_tree* t) {
     if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
     r3d_ctx* ctx = t->ctx;
+    t->deferred.clear();
     DeviceSetter ds(ctx->device);
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->tkeys, 0xff, t->tcap * sizeof(uint64_t), ctx->stream));
     R3D_CUDA_OK(ctx, cudaMemsetAsync(t->values, 0, t->pool_cap * kBrickVoxels * sizeof(float), ctx->stream));
@@ -1062,6 +1079,30 @@ extern "C" int r3d_tree_apply_deltas_owned(r3d_tree* t, const void* records, con
     return finish(ctx);
 }
 
+extern "C" int r3d_tree_defer_deltas_owned(r3d_tree* t, const void* records, const uint64_t* counts, uint32_t n_scans, uint32_t part, uint32_t nparts) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    r3d_ctx* ctx = t->ctx;
+    if (n_scans && (!records || !counts)) return set_error(ctx, R3D_ERR_ARG, "null argument");
+    if (nparts == 0 || part >= nparts) return set_error(ctx, R3D_ERR_ARG, "bad partition %u of %u", part, nparts);
+    if (n_scans && !is_device_ptr(records)) return set_error(ctx, R3D_ERR_ARG, "r3d_tree_defer_deltas_owned expects device records");
+    r3d_tree::Deferred job;
+    job.recs = reinterpret_cast<const DeltaRecord*>(records);
+    job.part = part; job.nparts = nparts;
+    for (uint32_t s = 0; s < n_scans; ++s) {
+        if (counts[s] > 0xfffffff0ull) return set_error(ctx, R3D_ERR_ARG, "too many records");
+        job.counts.push_back(counts[s]);
+    }
+    if (n_scans) t->deferred.push_back(std::move(job));
+    return R3D_OK;
+}
+
+extern "C" int r3d_tree_flush_deferred(r3d_tree* t) {
+    if (!t) return set_error(nullptr, R3D_ERR_ARG, "null tree");
+    DeviceSetter ds(t->ctx->device);
+    R3D_TRY(tree_flush_deferred(t));
+    return finish(t->ctx);
+}
+
 extern "C" int r3d_delta_expand_keys(const void* records_host, uint64_t n_records, uint16_t* free_keys, uint64_t free_cap,
                                      uint64_t* n_free, uint16_t* occ_keys, uint64_t occ_cap, uint64_t* n_occ) {
     if (!records_host && n_records) return set_error(nullptr, R3D_ERR_ARG, "null records");
@@ -1151,6 +1192,7 @@ extern "C" int r3d_tree_search(r3d_tree* t, const uint16_t* keys, uint64_t n, fl
     if (!keys && n) return set_error(ctx, R3D_ERR_ARG, "null keys");
     if (n == 0) return R3D_OK;
     DeviceSetter ds(ctx->device);
+    R3D_TRY(tree_flush_deferred(t));
     const uint16_t* dk = keys;
     R3D_TRY(stage_in(ctx, SCR_IN0, keys, (size_t)n * 3, &dk));
     const bool vdev = values && is_device_ptr(values), fdev = found && is_device_ptr(found);

@@ -1,5 +1,7 @@
 // r3d_octree.cuh -- the voxel store shared by the update kernels (r3d_octree.cu) and the .bt serialiser (r3d_bt.cu).
 #pragma once
+#include <vector>
+
 #include "r3d_common.cuh"
 
 namespace r3d {
@@ -56,6 +58,10 @@ struct r3d_tree {
     r3d::DeltaRecord* delta = nullptr;
     uint64_t delta_cap = 0, delta_n = 0;
     uint64_t pipe_wait_ns = 0, pipe_work_ns = 0, pipe_max_turn_ns = 0, pipe_scans = 0;   // host clock of the last pipelined batch
+    // applies handed in with r3d_tree_defer_deltas_owned: queued by the next scan batch once its first ray casts are in flight
+    // (so that they run BESIDE the ray casting instead of ahead of it), or by whatever touches the map first
+    struct Deferred { const r3d::DeltaRecord* recs; std::vector<uint64_t> counts; uint32_t part, nparts; };
+    std::vector<Deferred> deferred;
     uint64_t n_pool_grow = 0, n_table_grow = 0;   // regrowth events since the tree was created (each copies / re-hashes)
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
     uint32_t* counters = nullptr;
@@ -79,6 +85,7 @@ int apply_delta_impl(r3d_tree* t, const DeltaRecord* d_recs, uint64_t n, uint32_
 int tree_reserve_delta(r3d_tree* t, uint64_t want);
 unsigned grid_for(r3d_ctx* ctx, unsigned long long items, int block = 256, int per_sm = 8);
 int tree_sync_counters(r3d_tree* t);
-int tree_settle(r3d_tree* t);   // pool_used exact again (reads the counters back if applies are pending)
+int tree_settle(r3d_tree* t);   // deferred applies queued, pool_used exact again (reads the counters back if applies are pending)
+int tree_flush_deferred(r3d_tree* t);
 int tree_refresh_pool_keys(r3d_tree* t);
 }  // namespace r3d

@@ -266,6 +266,7 @@ class OctreeSharder:
         self.get_scan_batch = get_scan_batch
         self.state = state if state is not None else {}
         self._buf = self.state.get("buf")
+        self._defer = False
 
     def make_buffer(self, nbytes):
         """Record buffer of this rank, kept across rounds and runs (a too small buffer costs a re-cast of the round)."""
@@ -321,7 +322,10 @@ class OctreeSharder:
                 out = grown
 
     def apply_round(self, payload, counts, first_scan):
-        self.tree.applyDeltasOwned(payload.data_ptr(), counts, self.rank if self.owner_partition else 0, self.world if self.owner_partition else 1)
+        # deferred: queued by the next round's ray-casting call once its ray casts are in flight (the applies of round r then
+        # run beside the ray casting of round r + 1), or by the end of run()
+        fn = self.tree.deferDeltasOwned if self._defer else self.tree.applyDeltasOwned
+        fn(payload.data_ptr(), counts, self.rank if self.owner_partition else 0, self.world if self.owner_partition else 1)
 
     def fence(self):
         import torch
@@ -333,7 +337,14 @@ class OctreeSharder:
         import os
         if overlap is None:
             overlap = os.environ.get("R3D_MERGE_OVERLAP", "1") != "0"
-        self._second = None
+        self._defer = bool(overlap) and self.get_scan_batch is not None
+        try:
+            return self._run(n_scans, group, scans_per_rank, overlap)
+        finally:
+            if self._defer:
+                self.tree.flushDeferred()
+
+    def _run(self, n_scans, group, scans_per_rank, overlap):
         return merged_insert(n_scans, self.rank, self.world, self.compute_delta, self.apply_delta, self.make_buffer, group=group,
                              scans_per_rank=scans_per_rank, fence=self.fence, compute_round=self.compute_round, apply_round=self.apply_round,
                              overlap=overlap, state=self.state)

@@ -7,7 +7,7 @@
   c2  KITTI-odometry shape: 4 500 x 1242x375 uint16 depth + poses -> world float32 records.  One "step" = one pass of the fused
       back-projection + pose transform over the whole sequence, inputs and outputs resident in HBM (`value`, CUDA events);
       `e2e` = the same call through the C ABI with HOST (pinned) buffers, copies inside the timed region.  The line also
-      carries the OctoMap half of the metric on a FIXED workload of 256 consecutive scans of the same sequence (0.1 m, 80 m):
+      carries the OctoMap half of the metric on a FIXED workload of 1 024 consecutive scans of the same sequence (0.1 m, 80 m):
       scans/s and the .bt SHA-256, the same workload at every N, so the SHA is the same at 1 / 2 / 4 / 8 GPUs.
   c3  the same sequence -> insertPointCloud for all 4 500 scans at 0.1 m / 80 m -> .bt (value = scans/s).
   c4  AirSim drone shape: 1 000 x 640x480 uint16 disparity (PSMNet style, d = raw/256), Z = f B / d, octree at 0.05 m.
@@ -935,10 +935,10 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: c2, the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the secondary sections (compaction, text rows, PNG decode, script e2e)")
-    ap.add_argument("--octomap-scans", type=int, default=256, help="scans of the fixed OctoMap workload of c2 / c4 (0 = skip)")
+    ap.add_argument("--octomap-scans", type=int, default=1024, help="scans of the fixed OctoMap workload of c2 / c4 (0 = skip)")
     ap.add_argument("--octomap-scans-full", type=int, default=0, help="c3 / c5: scans to insert (default: every frame)")
     ap.add_argument("--no-octomap", action="store_true", help="c3 / c5: skip the octree")
-    ap.add_argument("--octomap-scans-per-round", type=int, default=8, help="multi-GPU: scans each rank ray-casts between two exchanges")
+    ap.add_argument("--octomap-scans-per-round", type=int, default=16, help="multi-GPU: scans each rank ray-casts between two exchanges")
     ap.add_argument("--reserve-bricks", type=int, default=0, help="capacity hint for the map (c3 / c5 default: let it grow, growth events are reported)")
     ap.add_argument("--depth-kind", default="street", choices=["street", "uniform"],
                     help="synthetic depth: analytic street scene (headline) or i.i.d. U[1, 80] m (ray-casting worst case, SURVEY.md section 8d)")

@@ -255,6 +255,12 @@ int r3d_scan_deltas_compute(r3d_tree *tree, const float *xyz, const uint64_t *n_
                             double maxrange, int discretize, void *records, uint64_t capacity_records, uint64_t *counts);
 int r3d_tree_apply_deltas_owned(r3d_tree *tree, const void *records, const uint64_t *counts, uint32_t n_scans, uint32_t part,
                                 uint32_t nparts);
+/* Same, but only NOTED: the applies are queued on the context stream by the next r3d_scan_deltas_compute call once its
+ * first ray casts are in flight (they then run beside the ray casting instead of ahead of it: the software pipeline of the
+ * multi-GPU merge), or by the first call that reads or updates the map, or by r3d_tree_flush_deferred.  `records` must stay
+ * valid until then; `counts` is copied.  Order among deferred jobs and against later applies is the call order. */
+int r3d_tree_defer_deltas_owned(r3d_tree *tree, const void *records, const uint64_t *counts, uint32_t n_scans, uint32_t part, uint32_t nparts);
+int r3d_tree_flush_deferred(r3d_tree *tree);
 /* Expand delta records to explicit OcTreeKeys (n x 3 uint16) for inspection / parity tests (host buffers). */
 int r3d_delta_expand_keys(const void *records_host, uint64_t n_records, uint16_t *free_keys, uint64_t free_cap,
                           uint64_t *n_free, uint16_t *occ_keys, uint64_t occ_cap, uint64_t *n_occ);
