@@ -16,6 +16,7 @@
 //     to the store by the clamped log-odds kernel (K4).  Records are what multi-GPU runs exchange.
 #include <vector>
 
+#include <stdlib.h>
 #include <time.h>
 
 #include "r3d_octree.cuh"
@@ -500,10 +501,22 @@ int tree_sync_counters(r3d_tree* t) {
     return R3D_OK;
 }
 
+static int tree_reserve_table(r3d_tree* t, uint64_t want_entries);
+static int tree_reserve_pool(r3d_tree* t, uint64_t want);
+
+int tree_reserve(r3d_tree* t, uint64_t n_bricks) {
+    R3D_TRY(tree_reserve_table(t, n_bricks));
+    return tree_reserve_pool(t, n_bricks);
+}
+
 int tree_flush_deferred(r3d_tree* t) {
     if (t->deferred.empty()) return R3D_OK;
     std::vector<r3d_tree::Deferred> jobs;
     jobs.swap(t->deferred);          // (apply_delta_impl may come back here through tree_settle)
+    size_t n_scans = 0;
+    for (const auto& j : jobs) n_scans += j.counts.size();
+    static const bool sorted = !getenv("R3D_ROUND_SORTED") || atoi(getenv("R3D_ROUND_SORTED")) != 0;
+    if (sorted && n_scans >= 4) return apply_round_sorted(t, jobs);   // one sorted, scan-ordered pass (r3d_round.cu)
     for (const auto& j : jobs) {
         const DeltaRecord* d = j.recs;
         for (uint64_t c : j.counts) {
@@ -1052,6 +1065,9 @@ extern "C" int r3d_scan_deltas_compute(r3d_tree* t, const float* xyz, const uint
     r3d_ctx* ctx = t->ctx;
     if (n_scans && (!n_points || !origins || !counts)) return set_error(ctx, R3D_ERR_ARG, "null scan table");
     DeviceSetter ds(ctx->device);
+    // the deltas noted by r3d_tree_defer_deltas_owned (the round before this one, every rank's share): ONE sorted,
+    // scan-ordered pass, queued now that the stream is empty (its two small read-backs cost nothing here)
+    R3D_TRY(tree_flush_deferred(t));
     uint64_t rays = 0, steps = 0;
     ScanSink sink;
     sink.mode = ScanSink::EXPORT_USER;

@@ -87,5 +87,8 @@ unsigned grid_for(r3d_ctx* ctx, unsigned long long items, int block = 256, int p
 int tree_sync_counters(r3d_tree* t);
 int tree_settle(r3d_tree* t);   // deferred applies queued, pool_used exact again (reads the counters back if applies are pending)
 int tree_flush_deferred(r3d_tree* t);
+int tree_reserve(r3d_tree* t, uint64_t n_bricks);   // table + pool with room for n_bricks
+// r3d_round.cu: many scans' deltas in one sorted, scan-ordered pass
+int apply_round_sorted(r3d_tree* t, const std::vector<r3d_tree::Deferred>& jobs);
 int tree_refresh_pool_keys(r3d_tree* t);
 }  // namespace r3d

@@ -734,8 +734,6 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
             nxt.count = nxt.first < n_ok ? ((uint32_t)B < n_ok - nxt.first ? (uint32_t)B : n_ok - nxt.first) : 0u;
             nxt.timed = nxt.count && nxt.first + nxt.count == n_ok;
             if (nxt.count) R3D_TRY(pipe_enqueue(t, p, d_xyz, offsets.data(), n_points, origins, maxrange, nxt, slot ^ 1));
-            // applies deferred by the caller (multi-GPU rounds): both slots' ray casts are queued and do not wait for them
-            if (sink->mode != ScanSink::APPLY) R3D_TRY(tree_flush_deferred(t));
             const uint64_t t_wait = now_ns();
             R3D_CUDA_OK(ctx, cudaEventSynchronize(p->done[slot]));
             const uint64_t t_got = now_ns();

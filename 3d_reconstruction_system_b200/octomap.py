@@ -336,8 +336,8 @@ class OcTree:
         check(self._lib.r3d_tree_apply_deltas_owned(self._h, _ptr(records_ptr), cnt.ctypes.data, cnt.size, int(part), int(nparts)), self._ctx.handle)
 
     def deferDeltasOwned(self, records_ptr, counts, part=0, nparts=1):
-        """applyDeltasOwned, but only noted: queued by the next computeScanDeltasInto once its ray casts are in flight (or by
-        whatever touches the map first).  The records must stay valid until then."""
+        """applyDeltasOwned, but only noted: everything noted is applied in ONE sorted, scan-ordered pass by the next
+        computeScanDeltasInto (or whatever touches the map first).  The records must stay valid until then."""
         self._flush()
         cnt = np.ascontiguousarray(counts, dtype=np.uint64)
         check(self._lib.r3d_tree_defer_deltas_owned(self._h, _ptr(records_ptr), cnt.ctypes.data, cnt.size, int(part), int(nparts)), self._ctx.handle)

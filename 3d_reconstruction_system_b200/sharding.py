@@ -322,8 +322,8 @@ class OctreeSharder:
                 out = grown
 
     def apply_round(self, payload, counts, first_scan):
-        # deferred: queued by the next round's ray-casting call once its ray casts are in flight (the applies of round r then
-        # run beside the ray casting of round r + 1), or by the end of run()
+        # noted only: every rank's share of the round is applied in ONE sorted, scan-ordered pass (three launches instead of one
+        # per scan and rank) by the next round's ray-casting call, or by the end of run()
         fn = self.tree.deferDeltasOwned if self._defer else self.tree.applyDeltasOwned
         fn(payload.data_ptr(), counts, self.rank if self.owner_partition else 0, self.world if self.owner_partition else 1)
 
@@ -337,7 +337,7 @@ class OctreeSharder:
         import os
         if overlap is None:
             overlap = os.environ.get("R3D_MERGE_OVERLAP", "1") != "0"
-        self._defer = bool(overlap) and self.get_scan_batch is not None
+        self._defer = self.get_scan_batch is not None
         try:
             return self._run(n_scans, group, scans_per_rank, overlap)
         finally:

@@ -255,10 +255,12 @@ int r3d_scan_deltas_compute(r3d_tree *tree, const float *xyz, const uint64_t *n_
                             double maxrange, int discretize, void *records, uint64_t capacity_records, uint64_t *counts);
 int r3d_tree_apply_deltas_owned(r3d_tree *tree, const void *records, const uint64_t *counts, uint32_t n_scans, uint32_t part,
                                 uint32_t nparts);
-/* Same, but only NOTED: the applies are queued on the context stream by the next r3d_scan_deltas_compute call once its
- * first ray casts are in flight (they then run beside the ray casting instead of ahead of it: the software pipeline of the
- * multi-GPU merge), or by the first call that reads or updates the map, or by r3d_tree_flush_deferred.  `records` must stay
- * valid until then; `counts` is copied.  Order among deferred jobs and against later applies is the call order. */
+/* Same, but only NOTED: everything noted since the last flush -- every rank's share of a round of the multi-GPU merge -- is
+ * applied by the next r3d_scan_deltas_compute call (or the first call that reads or updates the map, or
+ * r3d_tree_flush_deferred) in ONE sorted, scan-ordered pass: owned records are keyed by (brick, position of the scan in
+ * the round), radix-sorted, and every brick is updated by one warp in scan order -- three launches per round instead of one
+ * per scan and rank.  `records` must stay valid until then; `counts` is copied.  Order among noted jobs and against later
+ * applies is the call order.  R3D_ROUND_SORTED=0 applies them scan by scan instead. */
 int r3d_tree_defer_deltas_owned(r3d_tree *tree, const void *records, const uint64_t *counts, uint32_t n_scans, uint32_t part, uint32_t nparts);
 int r3d_tree_flush_deferred(r3d_tree *tree);
 /* Expand delta records to explicit OcTreeKeys (n x 3 uint16) for inspection / parity tests (host buffers). */

@@ -61,6 +61,49 @@ def test_owner_partition_and_brick_merge_equal_serial(octomap, r3d, nparts):
     assert merged.writeBinary() == serial.writeBinary() == ref.write_binary_bytes()
 
 
+@pytest.mark.parametrize("nparts", [1, 3])
+def test_sorted_round_apply_equals_scan_by_scan(octomap, r3d, nparts):
+    """r3d_round.cu: the deltas of a whole round noted with deferDeltasOwned and applied in ONE sorted, scan-ordered pass
+    (index -> radix sort by (brick, scan) -> one warp per brick) equal the scan-by-scan applies and the serial
+    insertPointCloud run, for every voxel's float32 log-odds -- including bricks that saturate inside the round (the clamp
+    makes the order matter), scans without records, a second round into the same trees and the flush by a map read."""
+    ctx = r3d.default_context(0)
+    res, maxrange = 0.1, 10.0
+    n_scans = 23
+    serial, ref = octomap.OcTree(res), oo.OcTree(res)
+    caster = octomap.OcTree(res)
+    recs = []
+    for s in range(n_scans):
+        p, o = _scan(s % 5, n=3000) if s % 7 != 6 else (np.zeros((0, 3), np.float32), np.zeros(3))   # repeats saturate voxels; one empty scan
+        serial.insertPointCloud(p, o, maxrange=maxrange)
+        ref.insertPointCloud_f32(p, o, maxrange)
+        recs.append(caster.computeScanDelta(p, o, maxrange=maxrange))
+    parts = [octomap.OcTree(res) for _ in range(nparts)]
+    for lo, hi in ((0, 9), (9, n_scans)):                                   # two rounds
+        flat = np.concatenate([r.reshape(-1) for r in recs[lo:hi]]) if any(r.size for r in recs[lo:hi]) else np.zeros(0, np.uint8)
+        dev = ctx.to_device(flat if flat.size else np.zeros(136, np.uint8))
+        counts = [r.shape[0] for r in recs[lo:hi]]
+        for r, t in enumerate(parts):
+            # as the merge does: one job per sending rank (here: the round cut in two pieces), all applied in one pass
+            half = (hi - lo) // 2
+            n0 = sum(counts[:half])
+            t.deferDeltasOwned(dev.data_ptr(), counts[:half], r, nparts)
+            t.deferDeltasOwned(dev.data_ptr() + n0 * 136, counts[half:], r, nparts)
+            if lo == 0:
+                t.flushDeferred()
+            else:
+                assert t.numBricks() > 0                                    # a map read flushes what was noted
+        ctx.synchronize()
+        dev.free()
+    merged = parts[0]
+    for t in parts[1:]:
+        merged.importBricks(t.exportBricks())
+    k, v = merged.voxels()
+    wk, wv = serial.voxels()
+    assert np.array_equal(k, wk) and np.array_equal(v.view(np.uint32), wv.view(np.uint32))
+    assert merged.writeBinary() == serial.writeBinary() == ref.write_binary_bytes()
+
+
 def test_brick_export_import_roundtrip_and_overwrite(octomap):
     a = octomap.OcTree(0.05)
     pts = np.random.default_rng(3).normal(scale=2.0, size=(20000, 3))
