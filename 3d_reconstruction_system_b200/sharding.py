@@ -350,18 +350,17 @@ class OctreeSharder:
                              overlap=overlap, state=self.state)
 
 
-def gather_bricks(tree, group=None):
+def gather_bricks(tree, group=None, state=None):
     """Merge owner-partitioned maps: every rank exports its bricks (key, 512 log-odds, 512 known bits), the bricks are
-    all-gathered and imported, so that every rank ends with the whole map (disjoint union; bit-identical to a 1-GPU run)."""
+    all-gathered and imported, so that every rank ends with the whole map (disjoint union; bit-identical to a 1-GPU run).
+    state: a dict the caller keeps between runs (the export / receive buffers are allocated once)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     dev = torch.device("cuda", tree._ctx.device)
+    state = state if state is not None else {}
     n = tree.numBricks()
     rec = tree.BRICK_RECORD_BYTES
-    mine = torch.empty(max(n, 1) * rec, dtype=torch.uint8, device=dev)
-    if n:
-        tree.exportBricks(mine.data_ptr(), n)
     counts = torch.tensor([n], dtype=torch.int64, device=dev)
     counts_all = torch.empty(world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts_all, counts, group=group)
@@ -369,10 +368,15 @@ def gather_bricks(tree, group=None):
     maxn = int(ch.max())
     if maxn == 0:
         return 0
-    send = mine if mine.numel() == maxn * rec else torch.empty(maxn * rec, dtype=torch.uint8, device=dev)
-    if send is not mine:
-        send[:n * rec] = mine[:n * rec]       # (the padding is never read)
-    recv = torch.empty(world * maxn * rec, dtype=torch.uint8, device=dev)
+    need = maxn * rec
+    if state.get("gather_send") is None or state["gather_send"].numel() < need:
+        state["gather_send"] = torch.empty(need + need // 4, dtype=torch.uint8, device=dev)
+        state["gather_recv"] = torch.empty(world * (need + need // 4), dtype=torch.uint8, device=dev)
+    send = state["gather_send"][:need]
+    recv = state["gather_recv"][:world * need]
+    if n:
+        tree.exportBricks(send.data_ptr(), n)          # (the padding behind a rank's bricks is never read)
+    tree.reserve(int(ch.sum()))                         # one regrowth at most, before the imports
     dist.all_gather_into_tensor(recv, send, group=group)
     torch.cuda.current_stream().synchronize()
     me = dist.get_rank(group)
@@ -380,6 +384,6 @@ def gather_bricks(tree, group=None):
     for r in range(world):
         if r == me or ch[r] == 0:
             continue
-        tree.importBricks(recv.data_ptr() + r * maxn * rec, int(ch[r]))
+        tree.importBricks(recv.data_ptr() + r * need, int(ch[r]))
         total += int(ch[r])
     return total

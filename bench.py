@@ -325,7 +325,7 @@ def octomap_fixed_workload(args, torch, dist, ctx, dev, cfg, seq, rank, world, w
         ms_runs, host_runs, launches_run, growth = [], [], 0, None
         for _ in range(3):                       # a pass is short and has one host turnaround per batch of scans: median of three
             tree = octomap.OcTree(res, ctx=ctx)
-            tree.reserve(args.reserve_bricks or (1 << 19))   # capacity hint: no pool regrowth inside the timed region
+            tree.reserve(args.reserve_bricks or (1 << 20))   # capacity hint: no pool regrowth inside the timed region
             ctx.set_blocking(False)
             ctx.synchronize()
             launches0 = ctx.launch_count()
@@ -360,7 +360,7 @@ def octomap_fixed_workload(args, torch, dist, ctx, dev, cfg, seq, rank, world, w
 
         def run_once():
             tree = octomap.OcTree(res, ctx=ctx)
-            tree.reserve(args.reserve_bricks or (1 << 19))
+            tree.reserve(args.reserve_bricks or (1 << 20))
             sh = sharding.OctreeSharder(tree, get_scan, maxrange=maxrange, owner_partition=True, rank=rank, world=world,
                                         get_scan_batch=get_scan_batch, state=shared)
             ctx.synchronize()
@@ -371,7 +371,7 @@ def octomap_fixed_workload(args, torch, dist, ctx, dev, cfg, seq, rank, world, w
             ctx.synchronize()
             torch.cuda.synchronize()
             t1 = time.perf_counter()
-            sharding.gather_bricks(tree)
+            sharding.gather_bricks(tree, state=shared)
             ctx.synchronize()
             torch.cuda.synchronize()
             dist.barrier()

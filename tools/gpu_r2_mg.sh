@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29511 tests/workers/nccl_octomap_worker.py 19 3 > gpurun_out/mg${N}_worker.log 2>&1; echo "nccl worker exit $?"; tail -3 gpurun_out/mg${N}_worker.log
 timeout 300 $TR --master-port 29533 tools/pcie_probe.py > gpurun_out/mg${N}_pcie.json 2> gpurun_out/mg${N}_pcie.err; echo "pcie exit $?"; cat gpurun_out/mg${N}_pcie.json
-for ov in 1 0; do
+for ov in 1; do
 R3D_MERGE_OVERLAP=$ov TORCH_NCCL_HIGH_PRIORITY=1 timeout 900 $TR --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 --frames 2048 --quick > gpurun_out/mg${N}_bench_ov$ov.json 2> gpurun_out/mg${N}_bench_ov$ov.err; echo "bench ov=$ov exit $?"
 python - $N $ov <<'PY'
 import json,sys
