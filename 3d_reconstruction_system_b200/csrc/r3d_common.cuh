@@ -31,6 +31,10 @@ struct r3d_ctx {
     void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t cell_budget_bytes = 16ull << 30;   // cap of the ray caster's direct-mapped scratch (R3D_SCAN_SCRATCH_GB overrides)
+    // K1, disparity mode with integer samples: Z = fB / (raw * depth_scale) for every possible sample value (r3d_backproject.cu)
+    double* ztab = nullptr;
+    double ztab_scale = 0.0, ztab_fB = 0.0;
+    int ztab_n = 0;
     void* pinned = nullptr;          // small pinned mailbox for counters read back from the device
     size_t pinned_bytes = 0;
 };

@@ -135,6 +135,7 @@ extern "C" void r3d_destroy(r3d_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < SCR_COUNT; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     scan_pipe_destroy(ctx);
+    if (ctx->ztab) cudaFree(ctx->ztab);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
