@@ -573,10 +573,49 @@ static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
     return R3D_OK;
 }
 
-// brick pool with room for `want` bricks; new bricks are zero (log-odds 0 = a freshly created node, nothing known)
+// brick pool with room for `want` bricks; new bricks are zero (log-odds 0 = a freshly created node, nothing known).
+// With virtual memory management the pool grows IN PLACE: chunks of 32 768 bricks (64 MB of log-odds + 2 MB of masks) are
+// mapped behind a reserved address range, nothing is copied, freed or waited for, and the pointers kernels hold stay valid.
+constexpr uint64_t kPoolChunkBricks = 32768;
+constexpr uint64_t kPoolMaxBricks = 1ull << 26;      // 137 GB of log-odds: more than a B200 holds
+
 static int tree_reserve_pool(r3d_tree* t, uint64_t want) {
     r3d_ctx* ctx = t->ctx;
     if (want <= t->pool_cap) return R3D_OK;
+    if (want > 0xfffffff0ull) return set_error(ctx, R3D_ERR_OOM, "brick pool would exceed 2^32 bricks");
+    if (t->pool_cap == 0 && !t->pool_vmm && !getenv("R3D_POOL_MALLOC") && vmm_supported(ctx->device)) {
+        if (vmm_reserve(&t->vm_values, ctx->device, kPoolMaxBricks * kBrickVoxels * sizeof(float), kPoolChunkBricks * kBrickVoxels * sizeof(float)) &&
+            vmm_reserve(&t->vm_known, ctx->device, kPoolMaxBricks * 16 * sizeof(uint32_t), kPoolChunkBricks * 16 * sizeof(uint32_t)) &&
+            t->vm_values.chunk == kPoolChunkBricks * kBrickVoxels * sizeof(float) && t->vm_known.chunk == kPoolChunkBricks * 16 * sizeof(uint32_t)) {
+            t->pool_vmm = true;
+            t->values = reinterpret_cast<float*>(t->vm_values.base);
+            t->known = reinterpret_cast<uint32_t*>(t->vm_known.base);
+        } else {
+            vmm_release(&t->vm_values);
+            vmm_release(&t->vm_known);
+        }
+    }
+    if (t->pool_vmm) {
+        // geometric steps (at least half of what is there) keep the number of map calls logarithmic
+        uint64_t ncap = t->pool_cap + t->pool_cap / 2;
+        if (ncap < want) ncap = want;
+        ncap = (ncap + kPoolChunkBricks - 1) / kPoolChunkBricks * kPoolChunkBricks;
+        if (ncap > kPoolMaxBricks) ncap = kPoolMaxBricks;
+        if (ncap < want) return set_error(ctx, R3D_ERR_OOM, "brick pool would exceed %llu bricks", (unsigned long long)kPoolMaxBricks);
+        if (!vmm_grow(&t->vm_values, ncap * kBrickVoxels * sizeof(float)) || !vmm_grow(&t->vm_known, ncap * 16 * sizeof(uint32_t))) {
+            // out of device memory at the geometric step: take exactly what is asked for
+            ncap = (want + kPoolChunkBricks - 1) / kPoolChunkBricks * kPoolChunkBricks;
+            if (!vmm_grow(&t->vm_values, ncap * kBrickVoxels * sizeof(float)) || !vmm_grow(&t->vm_known, ncap * 16 * sizeof(uint32_t)))
+                return set_error(ctx, R3D_ERR_OOM, "out of device memory growing the brick pool to %llu bricks", (unsigned long long)ncap);
+        }
+        const uint64_t have = t->vm_values.mapped / (kBrickVoxels * sizeof(float));
+        const uint64_t used = t->pool_cap;
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->values + used * kBrickVoxels, 0, (have - used) * kBrickVoxels * sizeof(float), ctx->stream));
+        R3D_CUDA_OK(ctx, cudaMemsetAsync(t->known + used * 16, 0, (have - used) * 16 * sizeof(uint32_t), ctx->stream));
+        if (used) t->n_pool_grow++;
+        t->pool_cap = have;
+        return R3D_OK;
+    }
     // geometric growth from 4096 bricks (8.6 MB): a growth step costs a device allocation, a copy and a sync
     uint64_t ncap = t->pool_cap ? t->pool_cap : 4096;
     while (ncap < want) ncap *= 2;
@@ -842,7 +881,9 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     if (!t) return;
     DeviceSetter ds(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->values); cudaFree(t->known); cudaFree(t->pool_keys);
+    cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->pool_keys);
+    if (t->pool_vmm) { vmm_release(&t->vm_values); vmm_release(&t->vm_known); }
+    else { cudaFree(t->values); cudaFree(t->known); }
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
     delete t;
 }

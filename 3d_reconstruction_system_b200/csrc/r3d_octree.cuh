@@ -3,6 +3,7 @@
 #include <vector>
 
 #include "r3d_common.cuh"
+#include "r3d_vmm.cuh"
 
 namespace r3d {
 
@@ -45,6 +46,9 @@ struct r3d_tree {
     float* values = nullptr;      // [pool_cap][512] log-odds, Morton order inside the brick
     uint32_t* known = nullptr;    // [pool_cap][16]  voxel was updated at least once (node exists)
     uint64_t pool_cap = 0;
+    // the pool grows in place (r3d_vmm.cuh) where the driver offers virtual memory management; values / known then point into these
+    r3d::VmmRegion vm_values, vm_known;
+    bool pool_vmm = false;
     uint32_t pool_used = 0;       // host mirror of counters[CNT_POOL_USED] as of the last counter read-back
     uint64_t pool_bound = 0;      // upper bound of the device value once every queued apply has run
     bool pool_dirty = false;      // applies were queued since the last read-back: call tree_settle before using pool_used
