@@ -938,7 +938,7 @@ def main():
     ap.add_argument("--octomap-scans", type=int, default=1024, help="scans of the fixed OctoMap workload of c2 / c4 (0 = skip)")
     ap.add_argument("--octomap-scans-full", type=int, default=0, help="c3 / c5: scans to insert (default: every frame)")
     ap.add_argument("--no-octomap", action="store_true", help="c3 / c5: skip the octree")
-    ap.add_argument("--octomap-scans-per-round", type=int, default=16, help="multi-GPU: scans each rank ray-casts between two exchanges")
+    ap.add_argument("--octomap-scans-per-round", type=int, default=32, help="multi-GPU: scans each rank ray-casts between two exchanges")
     ap.add_argument("--reserve-bricks", type=int, default=0, help="capacity hint for the map (c3 / c5 default: let it grow, growth events are reported)")
     ap.add_argument("--depth-kind", default="street", choices=["street", "uniform"],
                     help="synthetic depth: analytic street scene (headline) or i.i.d. U[1, 80] m (ray-casting worst case, SURVEY.md section 8d)")
