@@ -574,8 +574,9 @@ static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
 }
 
 // brick pool with room for `want` bricks; new bricks are zero (log-odds 0 = a freshly created node, nothing known).
-// With virtual memory management the pool grows IN PLACE: chunks of 32 768 bricks (64 MB of log-odds + 2 MB of masks) are
-// mapped behind a reserved address range, nothing is copied, freed or waited for, and the pointers kernels hold stay valid.
+// With virtual memory management the pool grows IN PLACE: one physical allocation per growth step (a multiple of 32 768
+// bricks = 64 MB of log-odds + 2 MB of masks, geometric steps) is mapped behind a reserved address range; nothing is copied or
+// freed and the pointers kernels hold stay valid.
 constexpr uint64_t kPoolChunkBricks = 32768;
 constexpr uint64_t kPoolMaxBricks = 1ull << 26;      // 137 GB of log-odds: more than a B200 holds
 
@@ -584,9 +585,10 @@ static int tree_reserve_pool(r3d_tree* t, uint64_t want) {
     if (want <= t->pool_cap) return R3D_OK;
     if (want > 0xfffffff0ull) return set_error(ctx, R3D_ERR_OOM, "brick pool would exceed 2^32 bricks");
     if (t->pool_cap == 0 && !t->pool_vmm && !getenv("R3D_POOL_MALLOC") && vmm_supported(ctx->device)) {
-        if (vmm_reserve(&t->vm_values, ctx->device, kPoolMaxBricks * kBrickVoxels * sizeof(float), kPoolChunkBricks * kBrickVoxels * sizeof(float)) &&
-            vmm_reserve(&t->vm_known, ctx->device, kPoolMaxBricks * 16 * sizeof(uint32_t), kPoolChunkBricks * 16 * sizeof(uint32_t)) &&
-            t->vm_values.chunk == kPoolChunkBricks * kBrickVoxels * sizeof(float) && t->vm_known.chunk == kPoolChunkBricks * 16 * sizeof(uint32_t)) {
+        // (a step of 32 768 bricks is 64 MB of log-odds and 2 MB of masks: both multiples of the 2 MB mapping granularity)
+        if (vmm_reserve(&t->vm_values, ctx->device, kPoolMaxBricks * kBrickVoxels * sizeof(float)) &&
+            vmm_reserve(&t->vm_known, ctx->device, kPoolMaxBricks * 16 * sizeof(uint32_t)) &&
+            (kPoolChunkBricks * 16 * sizeof(uint32_t)) % t->vm_known.chunk == 0 && (kPoolChunkBricks * kBrickVoxels * sizeof(float)) % t->vm_values.chunk == 0) {
             t->pool_vmm = true;
             t->values = reinterpret_cast<float*>(t->vm_values.base);
             t->known = reinterpret_cast<uint32_t*>(t->vm_known.base);
@@ -596,8 +598,8 @@ static int tree_reserve_pool(r3d_tree* t, uint64_t want) {
         }
     }
     if (t->pool_vmm) {
-        // geometric steps (at least half of what is there) keep the number of map calls logarithmic
-        uint64_t ncap = t->pool_cap + t->pool_cap / 2;
+        // geometric steps (doubling) keep the number of driver calls logarithmic: each may wait for running kernels
+        uint64_t ncap = 2 * t->pool_cap;
         if (ncap < want) ncap = want;
         ncap = (ncap + kPoolChunkBricks - 1) / kPoolChunkBricks * kPoolChunkBricks;
         if (ncap > kPoolMaxBricks) ncap = kPoolMaxBricks;

@@ -51,16 +51,15 @@ bool vmm_supported(int device) {
     return api().memGetAllocationGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && gran > 0;
 }
 
-bool vmm_reserve(VmmRegion* r, int device, size_t max_bytes, size_t chunk_bytes) {
+bool vmm_reserve(VmmRegion* r, int device, size_t max_bytes) {
     if (!api().ok) return false;
     size_t gran = 0;
     const CUmemAllocationProp p = prop_for(device);
     if (api().memGetAllocationGranularity(&gran, &p, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || gran == 0) return false;
-    chunk_bytes = (chunk_bytes + gran - 1) / gran * gran;
-    max_bytes = (max_bytes + chunk_bytes - 1) / chunk_bytes * chunk_bytes;
+    max_bytes = (max_bytes + gran - 1) / gran * gran;
     CUdeviceptr base = 0;
     if (api().memAddressReserve(&base, max_bytes, 0, 0, 0) != CUDA_SUCCESS) return false;
-    r->base = base; r->reserved = max_bytes; r->mapped = 0; r->chunk = chunk_bytes; r->device = device;
+    r->base = base; r->reserved = max_bytes; r->mapped = 0; r->chunk = gran; r->device = device;
     r->handles.clear();
     return true;
 }
@@ -73,18 +72,18 @@ bool vmm_grow(VmmRegion* r, size_t want_bytes) {
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     acc.location.id = r->device;
     acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    while (r->mapped < want_bytes) {
-        CUmemGenericAllocationHandle h;
-        if (api().memCreate(&h, r->chunk, &p, 0) != CUDA_SUCCESS) return false;
-        if (api().memMap(r->base + r->mapped, r->chunk, 0, h, 0) != CUDA_SUCCESS) { api().memRelease(h); return false; }
-        if (api().memSetAccess(r->base + r->mapped, r->chunk, &acc, 1) != CUDA_SUCCESS) {
-            api().memUnmap(r->base + r->mapped, r->chunk);
-            api().memRelease(h);
-            return false;
-        }
-        r->handles.push_back(h);
-        r->mapped += r->chunk;
+    size_t size = (want_bytes - r->mapped + r->chunk - 1) / r->chunk * r->chunk;
+    if (r->mapped + size > r->reserved) size = r->reserved - r->mapped;
+    CUmemGenericAllocationHandle h;
+    if (api().memCreate(&h, size, &p, 0) != CUDA_SUCCESS) return false;
+    if (api().memMap(r->base + r->mapped, size, 0, h, 0) != CUDA_SUCCESS) { api().memRelease(h); return false; }
+    if (api().memSetAccess(r->base + r->mapped, size, &acc, 1) != CUDA_SUCCESS) {
+        api().memUnmap(r->base + r->mapped, size);
+        api().memRelease(h);
+        return false;
     }
+    r->handles.push_back(h);
+    r->mapped += size;
     return true;
 }
 

@@ -16,14 +16,15 @@ struct VmmRegion {
     CUdeviceptr base = 0;
     size_t reserved = 0;     // bytes of address space
     size_t mapped = 0;       // bytes backed by memory, always a prefix
-    size_t chunk = 0;        // bytes mapped per step (multiple of the allocation granularity)
+    size_t chunk = 0;        // allocation granularity: every mapping is a multiple of it
     int device = 0;
-    std::vector<CUmemGenericAllocationHandle> handles;
+    std::vector<CUmemGenericAllocationHandle> handles;   // ONE physical allocation per growth step (a step is three driver calls,
+                                                          // each of which may wait for running kernels: few, large steps)
 };
 
 bool vmm_supported(int device);
-// reserve `max_bytes` of address space (rounded up to whole chunks); nothing is mapped yet
-bool vmm_reserve(VmmRegion* r, int device, size_t max_bytes, size_t chunk_bytes);
+// reserve `max_bytes` of address space; nothing is mapped yet
+bool vmm_reserve(VmmRegion* r, int device, size_t max_bytes);
 // make at least `want_bytes` usable; false when the device (or the reservation) has no more room
 bool vmm_grow(VmmRegion* r, size_t want_bytes);
 void vmm_release(VmmRegion* r);
