@@ -554,6 +554,7 @@ static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
     uint64_t need = 1024;
     while (need < want_entries * 2) need <<= 1;
     if (need <= t->tcap) return R3D_OK;
+    if (t->tcap && need < (1ull << 32)) need <<= 1;   // regrowing: one doubling ahead (12 bytes per slot against 2 112 per brick)
     uint64_t* nk = nullptr;
     uint32_t* nv = nullptr;
     R3D_CUDA_OK(ctx, cudaMalloc(&nk, need * sizeof(uint64_t)));
@@ -564,9 +565,11 @@ static int tree_reserve_table(r3d_tree* t, uint64_t want_entries) {
     if (t->tcap) {
         k_rehash<<<grid_for(ctx, t->tcap), 256, 0, ctx->stream>>>(t->tkeys, t->tvals, t->tcap, nk, nv, need);
         ctx->launches++;
-        R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(t->tkeys);
-        cudaFree(t->tvals);
+        // No wait, no cudaFree (a device-wide synchronisation) here: kernels queued earlier hold the old table, everything
+        // queued from now on is ordered after the re-hash by the stream.  The old arrays are retired and freed with the tree
+        // (together they are smaller than the new table).
+        t->retired.push_back(t->tkeys);
+        t->retired.push_back(t->tvals);
         t->n_table_grow++;
     }
     t->tkeys = nk; t->tvals = nv; t->tcap = need;
@@ -884,6 +887,7 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     DeviceSetter ds(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->tkeys); cudaFree(t->tvals); cudaFree(t->pool_keys);
+    for (void* q : t->retired) cudaFree(q);
     if (t->pool_vmm) { vmm_release(&t->vm_values); vmm_release(&t->vm_known); }
     else { cudaFree(t->values); cudaFree(t->known); }
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);

@@ -43,6 +43,7 @@ struct r3d_tree {
     uint64_t* tkeys = nullptr;
     uint32_t* tvals = nullptr;
     uint64_t tcap = 0;
+    std::vector<void*> retired;   // tables replaced by a re-hash: freed with the tree (no device-wide sync while mapping)
     float* values = nullptr;      // [pool_cap][512] log-odds, Morton order inside the brick
     uint32_t* known = nullptr;    // [pool_cap][16]  voxel was updated at least once (node exists)
     uint64_t pool_cap = 0;
