@@ -2,6 +2,7 @@
 # ncu ledger of round 2: one --set full capture per kernel family at bench-like sizes (run only after the same command has
 # exited 0 without ncu), plus the per-launch time list of a short default run.  Read back with tools/ncu_summary.py.
 mkdir -p gpurun_out
+timeout 900 python bench.py --config c3 --steps 3 > gpurun_out/r2_bench_c3.json 2> gpurun_out/r2_bench_c3.err; python -c "import json; d=json.load(open('gpurun_out/r2_bench_c3.json')); o=d['octomap']; print('c3', round(o['value']), round(o['ms_per_scan'],3), o['growth'], o['host_pipeline'], o['bt_sha256'][:12])"
 CMD="python bench.py --frames 1024 --steps 2 --warmup 3 --no-cpu-baseline --octomap-scans 32"
 timeout 600 $CMD > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain.err; exit 1; }
 cap() { # name regex skip count

@@ -15,7 +15,7 @@ from ncu_summary import summarise  # noqa: E402
 
 KEEP = ("kernel", "duration", "dram_read", "dram_write", "traffic_bytes", "dram_pct_of_peak", "l2_pct_of_peak", "sm_pct_of_peak", "achieved_occupancy_pct",
         "theoretical_occupancy_pct", "registers_per_thread", "grid", "block", "dyn_smem_per_block", "l1_hit_pct", "l2_hit_pct", "l2_atom_sectors",
-        "l2_red_sectors", "warp_instructions", "active_threads_per_warp_inst", "fp64_pipe_pct", "issue_active_pct", "stall_long_scoreboard_per_issue")
+        "l2_red_sectors", "l2_read_sectors_from_sm", "l2_write_sectors_from_sm", "warp_instructions", "active_threads_per_warp_inst", "fp64_pipe_pct", "issue_active_pct", "stall_long_scoreboard_per_issue")
 
 
 def main():

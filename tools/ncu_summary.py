@@ -30,6 +30,11 @@ WANT = {
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "lts__t_sectors_op_atom.sum": "l2_atom_sectors",
     "lts__t_sectors_op_red.sum": "l2_red_sectors",
+    # (this ncu build's full set carries the L1 -> crossbar side of the same traffic: sectors of global atomics / reductions sent to L2)
+    "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum": "l2_atom_sectors",
+    "l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum": "l2_red_sectors",
+    "lts__t_sectors_srcunit_tex_op_read.sum": "l2_read_sectors_from_sm",
+    "lts__t_sectors_srcunit_tex_op_write.sum": "l2_write_sectors_from_sm",
     "smsp__inst_executed.sum": "warp_instructions",
     "smsp__thread_inst_executed_per_inst_executed.ratio": "active_threads_per_warp_inst",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
