@@ -246,7 +246,9 @@ __device__ __forceinline__ bool walk_step(uint64_t* masks64, uint8_t* touched, u
     const bool done = ((L.cell == L.ecell) & (L.P == L.eP)) | past;
     // ---- leaving the sub-block (or the ray): publish its cells unless all of them are known to be set
     if (done | new_sub) {
-        L.steps += (unsigned)__popcll(L.mask);
+#ifndef K3_NO_STATS
+        L.steps += (unsigned)__popcll(L.mask);      // statistics: free cells recorded (DDA steps/s in the bench)
+#endif
         if ((L.mask & ~L.seen) != 0ull) {
             atomicOr(reinterpret_cast<unsigned long long*>(masks64 + L.widx), (unsigned long long)L.mask);
             touched[L.widx >> 4] = 1;

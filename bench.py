@@ -144,8 +144,11 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "frames_per_gpu": cfg["frames"], "frames_per_step": frames_per_core * cores,
-                   "sample": sample, "note": "a step of this arm is a bounded sample of the workload (rate metric)"},
+        "config": {"workload": cfg["workload"], "frames_per_gpu": cfg["frames"], "frame_range_of_rank0": [0, cfg["frames"]],
+                   "pixels_per_step_per_gpu": cfg["frames"] * cfg["W"] * cfg["H"], "frames_per_step": frames_per_core * cores,
+                   "frames_per_launch": None, "l2": None, "parity_sample_ok": None, "merged_cloud": None,
+                   "sample": sample, "note": "same workload and keys as the GPU arm; a step of THIS arm is a bounded sample of it (frames_per_step frames: the "
+                                             "full 4 500-frame pass takes minutes on the host), the value is a rate"},
         "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -909,7 +912,8 @@ def run_gpu_arm(args):
             "scaling": octo["scaling"] if (headline_octo and "scaling" in octo) else scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["workload"] + ("" if total_frames == CONFIGS[cfg["name"]]["frames"] else " [--frames %d]" % total_frames),
-                       "frames_per_gpu": n_frames, "frame_range_of_rank0": [lo, hi], "pixels_per_step_per_gpu": px_rank, "frames_per_launch": min(chunk, n_frames),
+                       "frames_per_gpu": n_frames, "frame_range_of_rank0": [lo, hi], "pixels_per_step_per_gpu": px_rank, "frames_per_step": n_frames,
+                       "frames_per_launch": min(chunk, n_frames),
                        "l2": "inputs+outputs %.1f GB per launch >> 126 MB L2" % (px_launch * 14 / 1e9), "parity_sample_ok": pp["parity_ok"],
                        "merged_cloud": ("rank r writes its records at offset r * %d points of the merged cloud; no data-path collective" % px_rank) if world > 1 else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
