@@ -38,7 +38,7 @@ constexpr int K3_MAX_BATCH = 8;
 #define K3_REFILL_MIN 8
 #endif
 #ifndef K3_STAGES
-#define K3_STAGES 3      // staging registers of the sub-block word fetch = iterations between request and use, plus one
+#define K3_STAGES 2      // shared-memory slots of the sub-block word fetch = steps between request and use
 #endif
 #ifndef K3_CHUNK
 #define K3_CHUNK 64      // rays a warp claims from the batch's counter at a time

@@ -325,7 +325,7 @@ def octomap_fixed_workload(args, torch, dist, ctx, dev, cfg, seq, rank, world, w
         warm = octomap.OcTree(res, ctx=ctx)
         run(warm, min(16, S))
         del warm
-        ms_runs, host_runs, launches_run, growth = [], [], 0, None
+        ms_runs, host_runs, launches_run, growth, wall_runs = [], [], 0, None, []
         for _ in range(3):                       # a pass is short and has one host turnaround per batch of scans: median of three
             tree = octomap.OcTree(res, ctx=ctx)
             tree.reserve(args.reserve_bricks or (1 << 20))   # capacity hint: no pool regrowth inside the timed region
@@ -335,18 +335,22 @@ def octomap_fixed_workload(args, torch, dist, ctx, dev, cfg, seq, rank, world, w
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             del k3_ms[:]
+            tw0 = time.perf_counter()
             steps, rays = run(tree, S)
+            tw1 = time.perf_counter()
             e1.record(stream)
             ctx.synchronize()
+            tw2 = time.perf_counter()
             ctx.set_blocking(True)
             ms_runs.append(e0.elapsed_time(e1))
+            wall_runs.append([1e3 * (tw1 - tw0), 1e3 * (tw2 - tw1)])
             host_runs.append(tree.pipelineStats())
             launches_run = ctx.launch_count() - launches0
             growth = tree.growthStats()
         ms = float(np.median(ms_runs))
         out.update({"value": S / (ms * 1e-3), "ms_per_scan": ms / S, "ms_per_scan_runs": [m / S for m in ms_runs], "rays_per_scan": rays // S,
                     "dda_steps_per_scan": steps // S, "rays_per_s": rays / (ms * 1e-3), "dda_steps_per_s": steps / (ms * 1e-3),
-                    "gpu_launches": launches_run, "host_pipeline_runs": host_runs, "growth": growth,
+                    "gpu_launches": launches_run, "host_pipeline_runs": host_runs, "host_wall_ms_runs_call_and_drain": wall_runs, "growth": growth,
                     "raycast_kernel_ms_per_scan_last_batch": float(k3_ms[-1]),
                     "raycast_steps_per_s_in_kernel": (steps / S) / max(k3_ms[-1], 1e-9) * 1e3,
                     "timing": "CUDA events on the context stream around one r3d_tree_insert_scans call, median of three passes into fresh trees"})

@@ -530,3 +530,40 @@ def test_pipelined_batch_record_overflow_path(octomap, r3d):
     kb, vb = b.voxels()
     assert np.array_equal(ka, kb) and np.array_equal(va.view(np.uint32), vb.view(np.uint32))
     assert a.writeBinary() == b.writeBinary()
+
+
+def test_pool_growth_in_place_and_malloc_fallback_agree(octomap, r3d, tmp_path):
+    """The brick pool grows in place (virtual memory management: chunks mapped behind a reserved address range) while scans are
+    in flight; R3D_POOL_MALLOC=1 keeps the allocate-copy-free pool.  Both must give the oracle's tree, through several growth
+    steps of the pool and re-hashes of the table inside one pipelined call."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    rng = np.random.default_rng(97)
+    S, N = 12, 6000
+    origins = np.array([[3.0 * s, 0.5 * s, 0.0] for s in range(S)])          # the sensor moves: new bricks with every scan
+    scans = np.stack([_scan(rng, N, origins[s], far=25.0) for s in range(S)]).astype(np.float32)
+    ctx = r3d.default_context(0)
+    dev = ctx.to_device(scans.reshape(-1, 3))
+    t, ref = octomap.OcTree(0.05), oo.OcTree(0.05)
+    t.insertPointClouds(dev, origins, maxrange=20.0)
+    for s in range(S):
+        ref.insertPointCloud_f32(scans[s], origins[s], 20.0)
+    g = t.growthStats()
+    assert g["pool_regrowths"] >= 2 and g["table_regrowths"] >= 2, g        # the tree started at its minimum size
+    assert_same_tree(t, ref)
+    want = hashlib.sha256(t.writeBinary()).hexdigest()
+    np.save(tmp_path / "scans.npy", scans)
+    np.save(tmp_path / "origins.npy", origins)
+    code = ("import importlib,sys,hashlib,numpy as np\n"
+            "sys.path.insert(0, %r)\n"
+            "r3d = importlib.import_module('3d_reconstruction_system_b200'); om = importlib.import_module('3d_reconstruction_system_b200.octomap')\n"
+            "ctx = r3d.default_context(0); sc = np.load(%r); org = np.load(%r)\n"
+            "t = om.OcTree(0.05); t.insertPointClouds(ctx.to_device(sc.reshape(-1, 3)), org, maxrange=20.0)\n"
+            "print(hashlib.sha256(t.writeBinary()).hexdigest(), t.growthStats()['pool_regrowths'])\n") % (
+                os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "scans.npy"), str(tmp_path / "origins.npy"))
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, R3D_POOL_MALLOC="1"), capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got, grows = p.stdout.split()[-2:]
+    assert got == want and int(grows) >= 2
