@@ -324,6 +324,18 @@ R3D_HD Fixed4 fixed4_decompose(double x) {
     return f;
 }
 
+// The same count of 1e-4 units for |x| < 429 496 (it fits 32 bits) as ONE fused multiply-add: fma(|x|, 1e4, 2^52) rounds
+// the EXACT product to an integer, ties to even -- the rule above -- and the integer is the low word of the sum's mantissa.
+constexpr double kFixed4Two52 = 4503599627370496.0;
+constexpr double kFixed4FastLimit = 429496.0;
+R3D_HD uint32_t fixed4_units_fma(double a) {   // a = |x| < kFixed4FastLimit
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double2loint(__fma_rn(a, 1e4, kFixed4Two52));
+#else
+    return (uint32_t)(double_bits(fma(a, 1e4, kFixed4Two52)) & 0xffffffffull);
+#endif
+}
+
 R3D_HD int dec_digits_u64(uint64_t q) {
     int n = 1;
     while (q >= 10ull) { q /= 10ull; ++n; }

@@ -41,7 +41,9 @@ constexpr int K3_MAX_BATCH = 8;
 #define K3_STAGES 2      // shared-memory slots of the sub-block word fetch = steps between request and use
 #endif
 #ifndef K3_CHUNK
-#define K3_CHUNK 64      // rays a warp claims from the batch's counter at a time
+#define K3_CHUNK 256     // rays a warp claims from the batch's counter at a time: consecutive rays walk the same sub-blocks, so a
+                         // long run per warp keeps its word fetches in L1 (measured 64: 0.65, 128: 0.59, 192: 0.55, 256: 0.53,
+                         // 512: 0.58 ms per scan -- beyond 256 the tail of the batch is too coarse)
 #endif
 
 // One ray with at least one free cell, as computeRayKeys sets it up (r3d_math.cuh::ray_setup).
@@ -327,7 +329,10 @@ __global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const Bat
     memset(&L, 0, sizeof L);
     L.epos = -1;
     const uint32_t slot0 = (uint32_t)__cvta_generic_to_shared(&s_words[0][threadIdx.x]);
-    // rays are claimed from the batch's counter K3_CHUNK at a time per warp (one atomic round trip per chunk, not per re-fill)
+    // rays are claimed from the batch's counter a chunk at a time per warp (one atomic round trip per chunk, not per re-fill);
+    // a small batch is cut finer so that every resident warp gets a share
+    uint32_t chunk = K3_CHUNK;
+    while (chunk > 32u && (unsigned long long)chunk * gridDim.x * (K3_THREADS / 32) > total) chunk >>= 1;
     uint32_t my_next = 0, my_end = 0;
     for (;;) {
         const unsigned act = __ballot_sync(0xffffffffu, active);
@@ -335,10 +340,10 @@ __global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const Bat
         if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
             if (my_next == my_end) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)K3_CHUNK);
+                if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 my_next = base < total ? (uint32_t)base : total;
-                my_end = base + K3_CHUNK < total ? (uint32_t)base + K3_CHUNK : total;
+                my_end = base + chunk < total ? (uint32_t)base + chunk : total;
                 if (my_next == my_end) { exhausted = true; continue; }
             }
             const uint32_t i = my_next + (uint32_t)__popc(idle & ((1u << lane) - 1u));
@@ -673,6 +678,8 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     r3d_ctx* ctx = t->ctx;
     *done_out = 0;
     if (n_scans == 0 || !(maxrange >= 0.0)) return R3D_OK;
+    timespec ts_enter;
+    clock_gettime(CLOCK_MONOTONIC, &ts_enter);
     // scans the pipeline can take: a bounded range (so the cube is bounded) and an origin inside the key space
     uint32_t n_ok = 0;
     uint64_t n_max = 0;
@@ -827,6 +834,9 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     if (next < n_ok) return set_error(ctx, R3D_ERR_OOM, "scan pipeline could not be shaped for scan %u", next);
     *done_out = next;
     ctx->last_kernel_ms = kernel_ms;
+    if (trace)
+        fprintf(stderr, "[r3d pipe] %u scans: %.2f ms in the call, %.2f waiting for batches, %.2f of host work between them\n", next,
+                (now_ns() - ((uint64_t)ts_enter.tv_sec * 1000000000ull + (uint64_t)ts_enter.tv_nsec)) * 1e-6, t->pipe_wait_ns * 1e-6, t->pipe_work_ns * 1e-6);
     return R3D_OK;
 }
 

@@ -17,7 +17,14 @@
 namespace r3d {
 
 constexpr int K6_THREADS = 256;
-constexpr int K6_STAGE_BYTES = 24 * 1024;   // a tile whose text is longer (astronomic coordinates) is written row by row
+#ifndef K6_PLY_ROWS
+#define K6_PLY_ROWS 3      // PLY rows a thread formats per tile (measured on 29.8 M rows: 1 -> 40, 2 -> 49, 3 -> 53 G rows/s)
+#endif
+constexpr int K6_STAGE_TXT = 24 * 1024;       // a tile whose text is longer (astronomic coordinates) is written row by row
+#ifndef K6_STAGE_PLY_ROW
+#define K6_STAGE_PLY_ROW 48
+#endif
+// K6_STAGE_PLY_ROW: staged bytes per PLY row of a tile (rows average 27 bytes, 41 with colours)
 
 struct TextArgs {
     const double *x, *y, *z;       // coordinate i at x[i * stride] ...
@@ -34,49 +41,63 @@ struct TextArgs {
 
 constexpr unsigned long long kTileAggregate = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1ull;
 
-// "%.4f" of a value whose 1e-4 units fit 32 bits (|x| < 429 496 -- every coordinate of a metric map): digits with 32-bit
-// arithmetic.  q = |x| in 1e-4 units, correctly rounded (fixed4_decompose).  Writes backwards from `end`.
-__device__ __forceinline__ int fixed4_len_u32(uint32_t q, int neg) {
+// "%.4f" of a value whose 1e-4 units fit 32 bits (|x| < 429 496 -- every coordinate of a metric map): the units come from
+// one fused multiply-add (r3d_math.cuh::fixed4_units_fma; tests/hostmath compares it with the integer statement of the
+// rounding rule, fixed4_decompose), the digits from 32-bit arithmetic.
+
+// returns whether the fast path applies; q = units, neg = sign bit, len = characters of "%.4f"
+__device__ __forceinline__ bool fast4_measure(double v, uint32_t& q, uint32_t& neg, unsigned& len) {
+    const double a = fabs(v);
+    neg = (uint32_t)__double2hiint(v) >> 31;
+    q = fixed4_units_fma(a);
+    len = neg + 6u + (q >= 100000u) + (q >= 1000000u) + (q >= 10000000u) + (q >= 100000000u) + (q >= 1000000000u);
+    return a < kFixed4FastLimit;      // false for NaN
+}
+// writes the `len` characters at p and the separator after them; returns the position after the separator
+__device__ __forceinline__ char* fast4_write(uint32_t q, uint32_t neg, unsigned len, char* p, char sep) {
+    char* const e = p + len;
     const uint32_t ip = q / 10000u;
-    return neg + 5 + (ip >= 10000u ? (ip >= 100000u ? 6 : 5) : (ip >= 100u ? (ip >= 1000u ? 4 : 3) : (ip >= 10u ? 2 : 1)));
-}
-__device__ __forceinline__ void fixed4_write_u32(uint32_t q, int neg, char* end) {
-    uint32_t ip = q / 10000u, fr = q - ip * 10000u;
-    char* p = end;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { const uint32_t t = fr / 10u; *--p = (char)('0' + (fr - t * 10u)); fr = t; }
-    *--p = '.';
-    do { const uint32_t t = ip / 10u; *--p = (char)('0' + (ip - t * 10u)); ip = t; } while (ip);
-    if (neg) *--p = '-';
+    const uint32_t fr = q - ip * 10000u;
+    const uint32_t hi = (fr * 5243u) >> 19, lo = fr - hi * 100u;          // fr / 100, fr % 100 (exact below 43 699)
+    const uint32_t t1 = (hi * 205u) >> 11, t0 = (lo * 205u) >> 11;        // x / 10 for x < 1 029
+    e[0] = sep;
+    e[-1] = (char)('0' + lo - t0 * 10u);
+    e[-2] = (char)('0' + t0);
+    e[-3] = (char)('0' + hi - t1 * 10u);
+    e[-4] = (char)('0' + t1);
+    e[-5] = '.';
+    if (q < 1000000u) {              // |x| < 100: one or two digits before the point
+        const uint32_t t = (ip * 205u) >> 11;
+        e[-6] = (char)('0' + ip - t * 10u);
+        if (q >= 100000u) e[-7] = (char)('0' + t);
+    } else {                         // three to six: all of them, stored where the number has them
+        const uint32_t top = ip / 10000u;                                        // (ip < 429 497: top < 43)
+        const uint32_t b = ip - top * 10000u;
+        const uint32_t bh = (b * 5243u) >> 19, bl = b - bh * 100u;
+        const uint32_t b3 = (bh * 205u) >> 11, b1 = (bl * 205u) >> 11;
+        const uint32_t c1 = (top * 205u) >> 11;
+        e[-6] = (char)('0' + bl - b1 * 10u);
+        e[-7] = (char)('0' + b1);
+        e[-8] = (char)('0' + bh - b3 * 10u);
+        if (q >= 10000000u) e[-9] = (char)('0' + b3);
+        if (q >= 100000000u) e[-10] = (char)('0' + top - c1 * 10u);
+        if (q >= 1000000000u) e[-11] = (char)('0' + c1);
+    }
+    if (neg) *p = '-';
+    return e + 1;
 }
 
-struct Num4 {       // one coordinate, measured
-    Fixed4 f;
-    int len;
-    bool fast;
-};
-__device__ __forceinline__ Num4 num4_measure(double v) {
-    Num4 r;
-    r.f = fixed4_decompose(v);
-    r.fast = r.f.kind == 0 && r.f.q < 4294960000ull;
-    r.len = r.fast ? fixed4_len_u32((uint32_t)r.f.q, r.f.neg) : fixed4_len(v);
-    return r;
-}
-__device__ __forceinline__ char* num4_write(const Num4& m, double v, char* p) {
-    if (m.fast) fixed4_write_u32((uint32_t)m.f.q, m.f.neg, p + m.len);
-    else fixed4_write(v, p, m.len);
-    return p + m.len;
-}
-
-// kTxt: "X,Y,Z\n" rows with str(float64) fields (r3d_repr.cuh) instead of PLY rows
-template <bool kTxt>
+// kTxt: "X,Y,Z\n" rows with str(float64) fields (r3d_repr.cuh) instead of PLY rows.  A thread formats kRows consecutive rows.
+template <bool kTxt, int kRows>
 __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
     typedef cub::BlockScan<unsigned, K6_THREADS> Scan;
+    constexpr unsigned kTile = K6_THREADS * kRows;
+    constexpr int K6_STAGE_BYTES = kTxt ? K6_STAGE_TXT : K6_STAGE_PLY_ROW * (int)kTile;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ __align__(16) char stage[K6_STAGE_BYTES + 16];
     __shared__ unsigned s_tile;
     __shared__ unsigned long long s_base;
-    const unsigned long long n_tiles = (a.n + K6_THREADS - 1) / K6_THREADS;
+    const unsigned long long n_tiles = (a.n + kTile - 1) / kTile;
     const bool rgb = a.rgb != nullptr;
     const unsigned lane = threadIdx.x & 31u;
     for (;;) {
@@ -84,26 +105,43 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
         __syncthreads();
         const unsigned long long t = s_tile;
         if (t >= n_tiles) break;
-        const unsigned long long i = t * K6_THREADS + threadIdx.x;
-        double x = 0, y = 0, z = 0;
-        unsigned r = 0, g = 0, b = 0, len = 0;
+        const unsigned long long i0 = t * kTile + (unsigned long long)threadIdx.x * kRows;
+        unsigned len[kRows];
+        unsigned mine = 0;
+        // txt rows: the text itself is kept (str(float64) is too long to do twice)
         char row[kTxt ? kTxtRowMax : 4];
-        Num4 mx, my, mz;
-        if (i < a.n) {
-            x = a.x[i * a.stride]; y = a.y[i * a.stride]; z = a.z[i * a.stride];
-            if (kTxt) {
-                len = (unsigned)txt_row_write(row, x, y, z, a.z_int != 0);
-            } else {
-                mx = num4_measure(x); my = num4_measure(y); mz = num4_measure(z);
-                len = (unsigned)(mx.len + my.len + mz.len) + 4u;
-                if (rgb) {
-                    r = a.rgb[3 * i]; g = a.rgb[3 * i + 1]; b = a.rgb[3 * i + 2];
-                    len += (unsigned)(u8_len(r) + u8_len(g) + u8_len(b)) + 4u;       // "r g b 0" after the third blank
+        // PLY rows: units, signs and lengths of the three coordinates (fast path), colour bytes
+        uint32_t q[kRows][3], sg[kRows], ln[kRows], col[kRows];
+        bool fast[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) {
+            len[k] = 0; fast[k] = true; sg[k] = 0; ln[k] = 0; col[k] = 0;
+            q[k][0] = q[k][1] = q[k][2] = 0;
+            const unsigned long long i = i0 + k;
+            if (i < a.n) {
+                const double x = a.x[i * a.stride], y = a.y[i * a.stride], z = a.z[i * a.stride];
+                if (kTxt) {
+                    len[k] = (unsigned)txt_row_write(row, x, y, z, a.z_int != 0);
+                } else {
+                    uint32_t nx, ny, nz;
+                    unsigned lx, ly, lz;
+                    const bool fx = fast4_measure(x, q[k][0], nx, lx), fy = fast4_measure(y, q[k][1], ny, ly), fz = fast4_measure(z, q[k][2], nz, lz);
+                    fast[k] = fx && fy && fz;
+                    sg[k] = nx | (ny << 1) | (nz << 2);
+                    ln[k] = lx | (ly << 8) | (lz << 16);
+                    len[k] = lx + ly + lz + 4u;
+                    if (!fast[k]) len[k] = (unsigned)(fixed4_len(x) + fixed4_len(y) + fixed4_len(z)) + 4u;
+                    if (rgb) {
+                        const unsigned r = a.rgb[3 * i], g = a.rgb[3 * i + 1], b = a.rgb[3 * i + 2];
+                        col[k] = r | (g << 8) | (b << 16);
+                        len[k] += (unsigned)(u8_len(r) + u8_len(g) + u8_len(b)) + 4u;     // "r g b 0" after the third blank
+                    }
                 }
             }
+            mine += len[k];
         }
         unsigned off, total;
-        Scan(tmp).ExclusiveSum(len, off, total);
+        Scan(tmp).ExclusiveSum(mine, off, total);
         // ---- decoupled look-back (warp 0): publish this tile's byte count, add up the tiles before it
         if (threadIdx.x < 32) {
             if (lane == 0) atomicExch(a.tile_state + t, (t == 0 ? kTilePrefix : kTileAggregate) | (unsigned long long)total);
@@ -132,25 +170,48 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
         __syncthreads();
         const unsigned long long base = s_base;
         const bool fits = a.out != nullptr && base + total <= a.cap;
-        if (fits && total <= (unsigned)K6_STAGE_BYTES) {
-            // stage at (base % 16) so that the copy below moves aligned 16-byte words
-            const unsigned skew = (unsigned)(base & 15ull);
-            if (len) {
-                char* p = stage + skew + off;
-                if (kTxt) { for (unsigned k = 0; k < len; ++k) p[k] = row[k]; }
-                else {
-                    p = num4_write(mx, x, p); *p++ = ' ';
-                    p = num4_write(my, y, p); *p++ = ' ';
-                    p = num4_write(mz, z, p); *p++ = ' ';
+        const bool staged = fits && total <= (unsigned)K6_STAGE_BYTES;
+        // stage at (base % 16) so that the copy below moves aligned 16-byte words; a tile whose text is longer than the
+        // stage (astronomic coordinates) writes its rows straight to the output
+        const unsigned skew = (unsigned)(base & 15ull);
+        if (staged) {
+            // (a pointer into the stage alone: the stores below are shared-memory stores with 32-bit addresses)
+            char* p = stage + skew + off;
+#pragma unroll
+            for (int k = 0; k < kRows; ++k) {
+                if (len[k] == 0) continue;
+                if (kTxt) { for (unsigned c = 0; c < len[k]; ++c) p[c] = row[c]; p += len[k]; }
+                else if (fast[k]) {
+                    p = fast4_write(q[k][0], sg[k] & 1u, ln[k] & 255u, p, ' ');
+                    p = fast4_write(q[k][1], (sg[k] >> 1) & 1u, (ln[k] >> 8) & 255u, p, ' ');
+                    p = fast4_write(q[k][2], sg[k] >> 2, ln[k] >> 16, p, ' ');
                     if (rgb) {
-                        p = u8_write(p, r); *p++ = ' ';
-                        p = u8_write(p, g); *p++ = ' ';
-                        p = u8_write(p, b); *p++ = ' ';
+                        p = u8_write(p, col[k] & 255u); *p++ = ' ';
+                        p = u8_write(p, (col[k] >> 8) & 255u); *p++ = ' ';
+                        p = u8_write(p, col[k] >> 16); *p++ = ' ';
                         *p++ = '0';
                     }
                     *p++ = '\n';
+                } else {
+                    const unsigned long long i = i0 + k;
+                    ply_row_write(p, a.x[i * a.stride], a.y[i * a.stride], a.z[i * a.stride], rgb, col[k] & 255u, (col[k] >> 8) & 255u, col[k] >> 16);
+                    p += len[k];
                 }
             }
+        } else if (fits) {
+            char* p = a.out + base + off;
+#pragma unroll 1
+            for (int k = 0; k < kRows; ++k) {
+                if (len[k] == 0) continue;
+                if (kTxt) { for (unsigned c = 0; c < len[k]; ++c) p[c] = row[c]; }
+                else {
+                    const unsigned long long i = i0 + k;
+                    ply_row_write(p, a.x[i * a.stride], a.y[i * a.stride], a.z[i * a.stride], rgb, col[k] & 255u, (col[k] >> 8) & 255u, col[k] >> 16);
+                }
+                p += len[k];
+            }
+        }
+        if (staged) {
             __syncthreads();
             char* dst = a.out + (base - skew);
             const unsigned span = skew + total;
@@ -165,9 +226,6 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
             // tail (shared with the next tile), and the head when the tile is shorter than one word
             for (unsigned k = full * 16u + threadIdx.x; k < span; k += K6_THREADS)
                 if (k >= skew) dst[k] = stage[k];
-        } else if (fits && len) {
-            if (kTxt) { for (unsigned k = 0; k < len; ++k) a.out[base + off + k] = row[k]; }
-            else ply_row_write(a.out + base + off, x, y, z, rgb, r, g, b);
         }
         __syncthreads();
     }
@@ -221,7 +279,8 @@ static int format_rows(r3d_ctx* ctx, bool txt, int z_int, const double* x, const
             a.rgb = (const unsigned char*)ctx->scratch[SCR_IN1];
         }
     }
-    const unsigned long long n_tiles = (n + K6_THREADS - 1) / K6_THREADS;
+    const unsigned long long tile_rows = (unsigned long long)K6_THREADS * (txt ? 1 : K6_PLY_ROWS);
+    const unsigned long long n_tiles = (n + tile_rows - 1) / tile_rows;
     R3D_TRY(scratch_reserve(ctx, SCR_TILE, (size_t)(n_tiles + 4) * 8 + 256));
     unsigned long long* state = (unsigned long long*)ctx->scratch[SCR_TILE];
     a.tile_state = state + 2;
@@ -244,14 +303,14 @@ static int format_rows(r3d_ctx* ctx, bool txt, int z_int, const double* x, const
     a.out = d_out;
     a.cap = out ? room : 0;
     int per_sm = 0;
-    if (txt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_rows<true>, K6_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_rows<false>, K6_THREADS, 0);
+    if (txt) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_rows<true, 1>, K6_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k6_rows<false, K6_PLY_ROWS>, K6_THREADS, 0);
     if (per_sm < 1) per_sm = 1;
     // persistent CTAs, all resident (the look-back spins on tiles handed out earlier: they must be running)
     unsigned long long grid = (unsigned long long)ctx->sm_count * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    if (txt) k6_rows<true><<<(unsigned)grid, K6_THREADS, 0, ctx->stream>>>(a);
-    else k6_rows<false><<<(unsigned)grid, K6_THREADS, 0, ctx->stream>>>(a);
+    if (txt) k6_rows<true, 1><<<(unsigned)grid, K6_THREADS, 0, ctx->stream>>>(a);
+    else k6_rows<false, K6_PLY_ROWS><<<(unsigned)grid, K6_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     R3D_CUDA_OK(ctx, cudaGetLastError());
     unsigned long long total = 0;

@@ -89,6 +89,20 @@ long hm_txt_rows(const double* xyz, long n, int z_int, char* out) {
     return off;
 }
 int hm_repr(double x, char* out) { return repr_double(x, out); }
+// K6 fast path: 1e-4 units of |x| by one fused multiply-add, beside the integer statement of the rule.  Returns how many
+// of the n values are in the fast range; mismatches are counted into *bad.
+long hm_fixed4_units(const double* v, long n, long* bad) {
+    long in_range = 0;
+    *bad = 0;
+    for (long i = 0; i < n; ++i) {
+        const double a = fabs(v[i]);
+        if (!(a < kFixed4FastLimit)) continue;
+        ++in_range;
+        const Fixed4 f = fixed4_decompose(v[i]);
+        if (f.kind != 0 || f.q != (uint64_t)fixed4_units_fma(a)) ++*bad;
+    }
+    return in_range;
+}
 long hm_ply_rows(const double* xyz, long n, const unsigned char* rgb, char* out) {
     long off = 0;
     for (long i = 0; i < n; ++i) {

@@ -46,6 +46,8 @@ def hm():
     L.hm_brick_voxel_coords.argtypes = [C.c_uint32, C.c_void_p]
     L.hm_txt_rows.restype = C.c_long
     L.hm_txt_rows.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p]
+    L.hm_fixed4_units.restype = C.c_long
+    L.hm_fixed4_units.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
     L.hm_ply_rows.restype = C.c_long
     L.hm_ply_rows.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     return L
@@ -63,6 +65,22 @@ def test_fixed4_rows_match_python_percent_format(hm):
     n = hm.hm_ply_rows(x.ctypes.data, x.shape[0], rgb.ctypes.data, out)
     want = "".join("%.4f %.4f %.4f %d %d %d 0\n" % (a, b, c, r, g, bb) for (a, b, c), (r, g, bb) in zip(x.tolist(), rgb.tolist()))
     assert out.raw[:n].decode("ascii") == want
+
+
+def test_fixed4_units_by_fma_equal_the_integer_rule(hm):
+    """K6's fast path (one fma, r3d_math.cuh::fixed4_units_fma) against the exact integer rounding it replaces: the
+    adversarial set, every tie k/32 and k/64 in range, random doubles of every exponent below the limit, the limit's
+    neighbours."""
+    rng = np.random.default_rng(77)
+    ties = np.arange(-429496 * 32, 429496 * 32, 7, dtype=np.float64) / 32.0
+    near = ties[::5] + np.ldexp(rng.choice([-1.0, 1.0], size=ties[::5].size), rng.integers(-60, -30, size=ties[::5].size))
+    spread = np.ldexp(rng.uniform(0.5, 1.0, size=400000), rng.integers(-1074, 19, size=400000)) * rng.choice([-1.0, 1.0], size=400000)
+    edge = np.array([429495.99994999997, 429495.99995, 429495.9999, np.nextafter(429496.0, 0.0), 429496.0, -429495.99995, 0.0, -0.0, 5e-5, 4.9999999999999996e-5,
+                     5.000000000000001e-5, 1.5e-4, 2.5e-4, 0.00015, 0.00025, 0.00035])
+    v = np.concatenate([fixed4_cases(), ties, near, spread, edge])
+    bad = C.c_long(0)
+    n = hm.hm_fixed4_units(v.ctypes.data, v.size, C.byref(bad))
+    assert n > 1_000_000 and bad.value == 0
 
 
 def ray(hm, res, o, e):
