@@ -10,6 +10,8 @@
 // All arithmetic is fp64 with separately rounded products/sums (r3d_math.cuh) and is cast once.
 #include <cub/device/device_scan.cuh>
 
+#include <type_traits>
+
 #include "r3d_common.cuh"
 
 namespace r3d {
@@ -618,14 +620,23 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_compact(const K1
     unsigned pose_frame = 0xffffffffu;
     Pose pose;
     unsigned stage = 0, parity = 0, ob = 0;
+    unsigned nxt_valid = 0;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) nxt_valid += (unsigned)a.tile_counts[t0 * kGroups + g];
+    unsigned long long nxt_base = a.tile_offsets[t0 * kGroups];
     for (unsigned long long t = t0; t < t1; ++t) {
         mbar_wait(&full[stage], parity);
         const DepthT* tin = in_s + (size_t)stage * kTile + tid * 4u;
-        // what pass 1 counted in this tile: all-valid and all-invalid tiles skip the position bookkeeping
-        unsigned tile_valid = 0;
+        // what pass 1 counted in this tile (read one tile ahead: the loads have a whole tile to arrive): all-valid and
+        // all-invalid tiles skip the position bookkeeping
+        const unsigned tile_valid = nxt_valid;
+        const unsigned long long base = nxt_base;                       // records before this tile
+        if (t + 1 < t1) {
+            nxt_valid = 0;
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) tile_valid += (unsigned)a.tile_counts[t * kGroups + g];
-        const unsigned long long base = a.tile_offsets[t * kGroups];    // records before this tile
+            for (int g = 0; g < kGroups; ++g) nxt_valid += (unsigned)a.tile_counts[(t + 1) * kGroups + g];
+            nxt_base = a.tile_offsets[(t + 1) * kGroups];
+        }
         const unsigned skew = (unsigned)((base * 3ull) % (unsigned)kPerWord);
         OutT* buf = out_s + (size_t)ob * kOutStride + skew;
         unsigned long long meta = 0;
@@ -656,7 +667,42 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_compact(const K1
             excl = incl - c;
         }
         // ---- phase B: records, packed
-        if (tile_valid != 0u) {
+        bool packed = false;
+        if constexpr (sizeof(OutT) == 4) {
+            if (tile_valid == (unsigned)kTile) {
+                // every pixel of the tile is valid (the common case): the k1_bulk_vec loop with the records shifted to
+                // the 16-byte phase of their destination -- the phase is the same for every group of the tile, so the
+                // store variant is chosen once per tile
+                auto run = [&](auto phase) {
+                    constexpr int kS = decltype(phase)::value;
+#pragma unroll 1
+                    for (int g = 0; g < kGroups; ++g) {
+                        DepthT raw[4];
+                        load_samples4(tin + g * K1V_GROUP, raw);
+                        const unsigned pos0 = (unsigned)g * K1V_GROUP + tid * 4u;
+                        OutT* const dst = buf + pos0 * 3u;
+                        OutT o[12];
+                        const int last = k1_group4<DepthT, OutT, kWorld, kMode>(a, col, row, raw, u0, v0, f0, pose_frame, pose, [&](int j, OutT x, OutT y, OutT z) {
+                            o[3 * j] = x; o[3 * j + 1] = y; o[3 * j + 2] = z;
+                        });
+                        if constexpr (kS == 0) store_records4(dst, o);
+                        else store_records4_shifted<kS>(dst, o, lane);
+                        if (last >= 0) a.frame_ends[f0] = base + pos0 + (unsigned)last + 1u;
+                        u0 += r_grp; v0 += q_grp;
+                        if (u0 >= W) { u0 -= W; ++v0; }
+                        if (v0 >= H) { v0 -= H; ++f0; }
+                    }
+                };
+                switch (skew & 3u) {
+                    case 0: run(std::integral_constant<int, 0>()); break;
+                    case 1: run(std::integral_constant<int, 1>()); break;
+                    case 2: run(std::integral_constant<int, 2>()); break;
+                    default: run(std::integral_constant<int, 3>()); break;
+                }
+                packed = true;
+            }
+        }
+        if (!packed && tile_valid != 0u) {
 #pragma unroll 1
             for (int g = 0; g < kGroups; ++g) {
                 unsigned m = 15u, pos0 = (unsigned)g * K1V_GROUP + tid * 4u;   // all-valid tile: every pixel keeps its place
@@ -704,7 +750,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1V_MINB) k1_bulk_compact(const K1
                 if (u0 >= W) { u0 -= W; ++v0; }
                 if (v0 >= H) { v0 -= H; ++f0; }
             }
-        } else {
+        } else if (!packed) {
             // no valid pixel in the tile: nothing to compute; frames that end inside it still report their record count
 #pragma unroll 1
             for (int g = 0; g < kGroups; ++g) {

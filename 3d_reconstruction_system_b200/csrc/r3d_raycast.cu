@@ -715,6 +715,7 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     t->pipe_wait_ns = t->pipe_work_ns = t->pipe_max_turn_ns = t->pipe_scans = 0;
     uint32_t next = 0;          // first scan not yet consumed
     float kernel_ms = 0.f;
+    uint64_t pre_ns = 0;
     for (int attempt = 0; attempt < 24 && next < n_ok; ++attempt) {
         {
             const uint64_t t_r = trace ? now_ns() : 0;
@@ -731,6 +732,7 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
         }
         p->dirty = true;        // until every queued batch has been emitted
         uint64_t t_mark = now_ns();
+        if (trace && attempt == 0) pre_ns = t_mark - ((uint64_t)ts_enter.tv_sec * 1000000000ull + (uint64_t)ts_enter.tv_nsec);
         Batch cur, nxt;
         cur.first = next; cur.count = (uint32_t)B < n_ok - next ? (uint32_t)B : n_ok - next;
         cur.timed = cur.first + cur.count == n_ok;
@@ -835,8 +837,9 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     *done_out = next;
     ctx->last_kernel_ms = kernel_ms;
     if (trace)
-        fprintf(stderr, "[r3d pipe] %u scans: %.2f ms in the call, %.2f waiting for batches, %.2f of host work between them\n", next,
-                (now_ns() - ((uint64_t)ts_enter.tv_sec * 1000000000ull + (uint64_t)ts_enter.tv_nsec)) * 1e-6, t->pipe_wait_ns * 1e-6, t->pipe_work_ns * 1e-6);
+        fprintf(stderr, "[r3d pipe] %u scans: %.2f ms in the call (%.2f before the first batch), %.2f waiting for batches, %.2f of host work between them, longest turnaround %.2f\n", next,
+                (now_ns() - ((uint64_t)ts_enter.tv_sec * 1000000000ull + (uint64_t)ts_enter.tv_nsec)) * 1e-6, pre_ns * 1e-6, t->pipe_wait_ns * 1e-6, t->pipe_work_ns * 1e-6,
+                t->pipe_max_turn_ns * 1e-6);
     return R3D_OK;
 }
 

@@ -16,7 +16,9 @@
 
 namespace r3d {
 
-constexpr int K6_THREADS = 256;
+#ifndef K6_THREADS
+#define K6_THREADS 256
+#endif
 #ifndef K6_PLY_ROWS
 #define K6_PLY_ROWS 3      // PLY rows a thread formats per tile (measured on 29.8 M rows: 1 -> 40, 2 -> 49, 3 -> 53 G rows/s)
 #endif

@@ -14,7 +14,7 @@ except Exception as e:
 PY
 done
 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name regex:k6_rows -c 1 -o gpurun_out/r2_k6_rows_v3 -f python tools/k6_probe.py 64 > gpurun_out/ncu_k6.log 2>&1; echo "ncu exit $?"
-R3D_PIPE_TRACE=1 timeout 600 python bench.py --frames 2048 --steps 3 --warmup 3 --no-cpu-baseline --quick --octomap-scans 512 > gpurun_out/k3j_bench.json 2> gpurun_out/k3j_bench.err; grep "r3d pipe" gpurun_out/k3j_bench.err | tail -12
+R3D_PIPE_TRACE=1 timeout 600 python bench.py --frames 2048 --steps 3 --warmup 3 --no-cpu-baseline --quick --octomap-scans 512 > gpurun_out/k3j_bench.json 2> gpurun_out/k3j_bench.err; grep "r3d pipe" gpurun_out/k3j_bench.err | grep "scans:" | tail -5
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/k3j_bench.json'))['octomap']
