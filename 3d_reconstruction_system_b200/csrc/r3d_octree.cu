@@ -1195,7 +1195,7 @@ extern "C" int r3d_delta_expand_keys(const void* records_host, uint64_t n_record
 
 extern "C" int r3d_tree_last_scan_stats(r3d_tree* t, uint64_t out[4]) {
     if (!t || !out) return set_error(t ? t->ctx : nullptr, R3D_ERR_ARG, "null argument");
-    out[0] = t->last_scan_rays; out[1] = t->last_scan_steps; out[2] = t->delta_n; out[3] = t->pool_used;
+    out[0] = t->last_scan_rays; out[1] = t->last_scan_steps; out[2] = t->delta_n ? t->delta_n : t->last_batch_records; out[3] = t->pool_used;
     return R3D_OK;
 }
 

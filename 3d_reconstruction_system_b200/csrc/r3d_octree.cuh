@@ -69,6 +69,7 @@ struct r3d_tree {
     std::vector<Deferred> deferred;
     uint64_t n_pool_grow = 0, n_table_grow = 0;   // regrowth events since the tree was created (each copies / re-hashes)
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
+    uint64_t last_batch_records = 0;   // records of the last scan a batch insert applied (statistics; its delta is not kept)
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};
 };

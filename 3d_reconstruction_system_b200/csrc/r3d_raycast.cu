@@ -796,10 +796,6 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
                                 (now_ns() - t_a) * 1e-6, (unsigned long long)cap0, (unsigned long long)t->pool_cap, (unsigned long long)tcap0,
                                 (unsigned long long)t->tcap, (unsigned long long)t->pool_bound);
                     p->snap_after[0] += n_rec; p->snap_after[1] += n_rec;
-                    if (s + 1 == n_scans) {   // r3d_scan_delta_export after a batch call refers to its last scan
-                        if (n_rec > t->delta_cap) R3D_TRY(tree_reserve_delta(t, n_rec + n_rec / 4 + 1024));
-                        if (n_rec) R3D_CUDA_OK(ctx, cudaMemcpyAsync(t->delta, recs, n_rec * sizeof(DeltaRecord), cudaMemcpyDeviceToDevice, ctx->stream));
-                    }
                 } else if (sink->mode == ScanSink::EXPORT_USER) {
                     sink->counts[s] = n_rec;
                     if (sink->used + n_rec > sink->capacity) {
@@ -815,7 +811,10 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
                     if (n_rec > t->delta_cap) R3D_TRY(tree_reserve_delta(t, n_rec + n_rec / 4 + 1024));
                     if (n_rec) R3D_CUDA_OK(ctx, cudaMemcpyAsync(t->delta, recs, n_rec * sizeof(DeltaRecord), cudaMemcpyDeviceToDevice, ctx->stream));
                 }
-                t->delta_n = n_rec;
+                // (applied records stay in the pipeline's buffers: a batch insert leaves no delta to export -- copying the
+                // last one out cost a fresh tree a synchronising allocation at the end of every call)
+                t->delta_n = sink->mode == ScanSink::APPLY ? 0 : n_rec;
+                t->last_batch_records = n_rec;
                 *rays_out += n_points[s];
                 next = s + 1;
                 t->pipe_scans = next;

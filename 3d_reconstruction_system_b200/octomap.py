@@ -137,15 +137,23 @@ class OcTree:
         self._flush()
         check(self._lib.r3d_tree_update_inner_occupancy(self._h), self._ctx.handle)
 
+    def _serialise(self, fn, per_brick):
+        """bytes of a *_mem writer in ONE serialisation: the buffer is sized for the worst case (untouched pages cost
+        nothing) -- .bt: 73 inner nodes of 2 bytes per brick plus the levels above; .ot: 585 nodes of 5 bytes."""
+        n = C.c_size_t(0)
+        cap = min((1 << 16) + per_brick * int(self.numBricks()), 1 << 30)     # (a larger file takes a second pass)
+        while True:
+            buf = np.empty(cap, dtype=np.uint8)
+            check(fn(self._h, buf.ctypes.data, cap, C.byref(n)), self._ctx.handle)
+            if n.value <= cap:
+                return buf[: n.value].tobytes()
+            cap = n.value + n.value // 8
+
     def writeBinary(self, filename=None):
         """writeBinary(bytes path) -> bool; with no argument returns the .bt bytes (the binding's overload)."""
         self._flush()
         if filename is None:
-            n = C.c_size_t(0)
-            check(self._lib.r3d_tree_write_bt_mem(self._h, None, 0, C.byref(n)), self._ctx.handle)
-            buf = (C.c_uint8 * max(n.value, 1))()
-            check(self._lib.r3d_tree_write_bt_mem(self._h, buf, n.value, C.byref(n)), self._ctx.handle)
-            return bytes(buf[: n.value])
+            return self._serialise(self._lib.r3d_tree_write_bt_mem, 170)
         if isinstance(filename, str):
             filename = filename.encode("utf-8")
         rc = self._lib.r3d_tree_write_bt(self._h, filename)
@@ -177,11 +185,7 @@ class OcTree:
         """write(bytes path) -> bool: the .ot format (every node's log-odds kept); with no argument returns the bytes."""
         self._flush()
         if filename is None:
-            n = C.c_size_t(0)
-            check(self._lib.r3d_tree_write_ot_mem(self._h, None, 0, C.byref(n)), self._ctx.handle)
-            buf = (C.c_uint8 * max(n.value, 1))()
-            check(self._lib.r3d_tree_write_ot_mem(self._h, buf, n.value, C.byref(n)), self._ctx.handle)
-            return bytes(buf[: n.value])
+            return self._serialise(self._lib.r3d_tree_write_ot_mem, 3400)
         if isinstance(filename, str):
             filename = filename.encode("utf-8")
         rc = self._lib.r3d_tree_write_ot(self._h, filename)

@@ -4,7 +4,6 @@ thread while the next batch is formatted -- decode, upload / kernels / read-back
 bounded by two batches whatever the length of the sequence.  (The reference keeps every point of the sequence in three
 Python lists, transfer/camera_to_world.py:144-146.)"""
 import ctypes as C
-import os
 import queue
 import threading
 
@@ -99,44 +98,14 @@ class BatchDecoder:
 
 class AsyncFileWriter:
     """Appends byte blocks to an open binary file on a writer thread.  write(block, release) queues a block (a memoryview
-    into a buffer the caller must not touch until `release` is called by the writer).  A large block is cut into
-    `threads` slices written with os.pwrite side by side: the copy into the page cache is what a multi-gigabyte PLY costs,
-    and one core moves only 2-3 GB/s of it."""
+    into a buffer the caller must not touch until `release` is called by the writer)."""
 
-    PARALLEL_MIN = 32 << 20
-
-    def __init__(self, f, threads=4):
+    def __init__(self, f):
         self.f = f
         self.q = queue.Queue(maxsize=4)
         self.err = None
-        self.pool = None
-        self.threads = max(1, int(os.environ.get("R3D_WRITER_THREADS", threads)))
-        try:
-            self.fd = f.fileno()
-        except (AttributeError, OSError, ValueError):
-            self.fd = None
-        if self.fd is not None and self.threads > 1:
-            from concurrent.futures import ThreadPoolExecutor
-            self.pool = ThreadPoolExecutor(self.threads)
         self.thread = threading.Thread(target=self._work, daemon=True)
         self.thread.start()
-
-    def _put(self, block):
-        n = len(block)
-        if self.pool is None or n < self.PARALLEL_MIN:
-            self.f.write(block)
-            return
-        self.f.flush()
-        pos = self.f.tell()
-        mv = memoryview(block).cast("B")
-        step = (n + self.threads - 1) // self.threads
-
-        def piece(a):
-            b = min(n, a + step)
-            while a < b:
-                a += os.pwrite(self.fd, mv[a:b], pos + a)
-        list(self.pool.map(piece, range(0, n, step)))
-        self.f.seek(pos + n)
 
     def _work(self):
         while True:
@@ -146,7 +115,7 @@ class AsyncFileWriter:
             block, release = item
             try:
                 if self.err is None:
-                    self._put(block)
+                    self.f.write(block)
             except BaseException as exc:
                 self.err = exc
             finally:
@@ -161,8 +130,6 @@ class AsyncFileWriter:
     def close(self):
         self.q.put(None)
         self.thread.join()
-        if self.pool is not None:
-            self.pool.shutdown()
         if self.err is not None:
             raise self.err
 

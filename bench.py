@@ -534,9 +534,9 @@ def compaction_section(torch, ctx, dev, cfg, depth, rt, n=1024):
             "algorithmic_gbs": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peak}
 
 
-def text_section(torch, ctx, dev, cfg, depth, rt, n=16, with_cpu=True):
-    """K6 beside K1: the ASCII the reference scripts actually write.  World points of n frames (float64,
-    device resident) -> genply's "%.4f %.4f %.4f \\n" rows and the txt files' str(float64) rows, device to device.
+def text_section(torch, ctx, dev, cfg, depth, rt, n=64, with_cpu=True):
+    """K6 beside K1: the ASCII the reference scripts actually write.  World points of n frames (one streaming
+    batch of the drop-in scripts: 64 frames; float64, device resident) -> genply's "%.4f %.4f %.4f \\n" rows and the txt files' str(float64) rows, device to device.
     Timed with CUDA events on the context stream (each call contains one 8-byte size read-back)."""
     import ctypes as C
     H, W = cfg["H"], cfg["W"]

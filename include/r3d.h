@@ -234,6 +234,8 @@ int r3d_tree_insert_scans(r3d_tree *tree, const float *xyz, const uint64_t *n_po
 #define R3D_DELTA_RECORD_BYTES 136
 int r3d_scan_delta_compute(r3d_tree *tree, const float *xyz, uint64_t n, const float origin[3], double maxrange,
                            int discretize, uint64_t *n_records);
+/* exports the delta of the last r3d_scan_delta_compute / r3d_tree_insert_scan on this tree (r3d_tree_insert_scans applies
+ * its records straight from the pipeline's buffers and leaves none: *n_records = 0) */
 int r3d_scan_delta_export(r3d_tree *tree, void *records, uint64_t capacity_records, uint64_t *n_records);
 int r3d_tree_apply_delta(r3d_tree *tree, const void *records, uint64_t n_records);
 /* Multi-GPU apply with the map partitioned by brick: only the records whose brick is owned by `part` of `nparts`

@@ -63,20 +63,3 @@ def test_async_writer_and_text_slots(tmp_path):
         slots.close()
     assert path.read_bytes() == expect
     assert threading.active_count() < 20
-
-
-def test_async_writer_splits_large_blocks_across_threads(tmp_path, monkeypatch):
-    """Blocks above PARALLEL_MIN are written as pwrite slices side by side; small blocks and the header go through the
-    buffered file -- the bytes on disk must be the plain concatenation either way."""
-    monkeypatch.setattr(streaming.AsyncFileWriter, "PARALLEL_MIN", 1 << 16)
-    rng = np.random.default_rng(3)
-    blocks = [rng.integers(0, 256, size=n, dtype=np.uint8) for n in (10, (1 << 16) + 12345, 77, 3 * (1 << 16) + 1, (1 << 16))]
-    path = tmp_path / "big.bin"
-    with open(path, "wb") as f:
-        f.write(b"header\n")
-        w = streaming.AsyncFileWriter(f, threads=3)
-        for b in blocks:
-            w.write(memoryview(b))
-        w.close()
-        f.write(b"tail")
-    assert path.read_bytes() == b"header\n" + b"".join(b.tobytes() for b in blocks) + b"tail"
