@@ -320,11 +320,29 @@ __global__ void k_bt_morton(const uint64_t* pool_keys, uint32_t n, uint64_t* mor
 
 __global__ void k_bt_set_root_offset(UpNode* root) { root->offset = 0; }
 
+// The serialiser's temporaries come out of one context-level block (SCR_BT, grow-only): two dozen cudaMalloc / cudaFree
+// pairs per call, each a device-wide synchronisation, were most of the 80 ms a 5.8 MB .bt took (and the odd full second).
+// A piece that does not fit the block falls back to its own allocation.
+struct BtArena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+};
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
+    bool owned = false;
+    BtArena* arena = nullptr;
+    ~DevBuf() { if (p && owned) cudaFree(p); }
     template <typename T> T* as() { return reinterpret_cast<T*>(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    cudaError_t alloc(size_t bytes) {
+        bytes = (bytes ? bytes : 16) + 255 & ~(size_t)255;
+        if (arena && arena->used + bytes <= arena->cap) {
+            p = arena->base + arena->used;
+            arena->used += bytes;
+            return cudaSuccess;
+        }
+        owned = true;
+        return cudaMalloc(&p, bytes);
+    }
 };
 
 static unsigned blocks_for(uint64_t n, int block = 256) { return (unsigned)((n + block - 1) / block > 0 ? (n + block - 1) / block : 1); }
@@ -339,7 +357,21 @@ static int tree_shape(r3d_tree* t, bool ml, uint64_t* n_nodes, std::vector<uint8
     if (nb == 0) return R3D_OK;
     R3D_TRY(tree_refresh_pool_keys(t));
     cudaStream_t st = ctx->stream;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint64_t*)nullptr, (uint64_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)nb, 0, 39, st);
+    cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)nb, st);
+    BtArena arena;
+    {
+        // sort keys / indices / heads / sums (32 B per brick), level 13 and the (geometrically shrinking) levels above
+        // it (40 B per node), the CUB scratch, and room for a typical payload (2 B per inner node, ~9 B per brick measured)
+        const size_t want = (size_t)nb * (32 + 60 + 16) + tmp_sort + tmp_scan + (1u << 20);
+        if (scratch_reserve(ctx, SCR_BT, want) == R3D_OK) {
+            arena.base = (char*)ctx->scratch[SCR_BT];
+            arena.cap = ctx->scratch_bytes[SCR_BT];
+        }
+    }
     DevBuf morton_in, morton_out, idx_in, idx_out, cub_tmp, counters, heads, incl;
+    for (DevBuf* b : {&morton_in, &morton_out, &idx_in, &idx_out, &cub_tmp, &counters, &heads, &incl}) b->arena = &arena;
     R3D_CUDA_OK(ctx, morton_in.alloc((size_t)nb * 8));
     R3D_CUDA_OK(ctx, morton_out.alloc((size_t)nb * 8));
     R3D_CUDA_OK(ctx, idx_in.alloc((size_t)nb * 4));
@@ -350,10 +382,6 @@ static int tree_shape(r3d_tree* t, bool ml, uint64_t* n_nodes, std::vector<uint8
     R3D_CUDA_OK(ctx, cudaMemsetAsync(counters.p, 0, sizeof(BtCounters), st));
     k_bt_morton<<<blocks_for(nb), 256, 0, st>>>(t->pool_keys, nb, morton_in.as<uint64_t>(), idx_in.as<uint32_t>());
     ctx->launches++;
-    size_t tmp_sort = 0, tmp_scan = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, morton_in.as<uint64_t>(), morton_out.as<uint64_t>(), idx_in.as<uint32_t>(),
-                                    idx_out.as<uint32_t>(), (int)nb, 0, 39, st);
-    cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, heads.as<uint32_t>(), incl.as<uint32_t>(), (int)nb, st);
     R3D_CUDA_OK(ctx, cub_tmp.alloc((tmp_sort > tmp_scan ? tmp_sort : tmp_scan) + 256));
     R3D_CUDA_OK(ctx, cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_sort, morton_in.as<uint64_t>(), morton_out.as<uint64_t>(),
                                                      idx_in.as<uint32_t>(), idx_out.as<uint32_t>(), (int)nb, 0, 39, st));
@@ -376,6 +404,7 @@ static int tree_shape(r3d_tree* t, bool ml, uint64_t* n_nodes, std::vector<uint8
     }
     // levels 13 .. 0
     std::vector<DevBuf> level(14);
+    for (DevBuf& b : level) b.arena = &arena;
     std::vector<uint32_t> count(14, 0);
     count[13] = nb;
     R3D_CUDA_OK(ctx, level[13].alloc((size_t)nb * sizeof(UpNode)));
@@ -418,6 +447,7 @@ static int tree_shape(r3d_tree* t, bool ml, uint64_t* n_nodes, std::vector<uint8
     }
     const uint64_t n_inner = root.inner_cnt;
     DevBuf out;
+    out.arena = &arena;
     R3D_CUDA_OK(ctx, out.alloc((size_t)n_inner * 2));
     k_bt_set_root_offset<<<1, 1, 0, st>>>(level[0].as<UpNode>());
     for (int d = 0; d <= 12; ++d) {

@@ -28,8 +28,8 @@ struct r3d_ctx {
     uint64_t launches = 0;
     char err[1024] = {0};
     // reusable device scratch (grown on demand, freed in r3d_destroy)
-    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void* scratch[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SCR_COUNT slots
+    size_t scratch_bytes[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t cell_budget_bytes = 16ull << 30;   // cap of the ray caster's direct-mapped scratch (R3D_SCAN_SCRATCH_GB overrides)
     // K1, disparity mode with integer samples: Z = fB / (raw * depth_scale) for every possible sample value (r3d_backproject.cu)
     double* ztab = nullptr;
@@ -42,7 +42,8 @@ struct r3d_ctx {
 namespace r3d {
 
 // scratch slots
-enum { SCR_POSE = 0, SCR_IN0 = 1, SCR_IN1 = 2, SCR_OUT0 = 3, SCR_OUT1 = 4, SCR_TILE = 5, SCR_CUBTMP = 6, SCR_MISC = 7, SCR_COUNT = 8 };
+enum { SCR_POSE = 0, SCR_IN0 = 1, SCR_IN1 = 2, SCR_OUT0 = 3, SCR_OUT1 = 4, SCR_TILE = 5, SCR_CUBTMP = 6, SCR_MISC = 7, SCR_BT = 8, SCR_COUNT = 9 };
+static_assert(SCR_COUNT == 9, "r3d_ctx::scratch holds SCR_COUNT slots");
 
 extern char g_last_error[1024];
 

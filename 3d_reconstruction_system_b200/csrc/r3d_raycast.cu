@@ -41,9 +41,11 @@ constexpr int K3_MAX_BATCH = 8;
 #define K3_STAGES 2      // shared-memory slots of the sub-block word fetch = steps between request and use
 #endif
 #ifndef K3_CHUNK
-#define K3_CHUNK 256     // rays a warp claims from the batch's counter at a time: consecutive rays walk the same sub-blocks, so a
-                         // long run per warp keeps its word fetches in L1 (measured 64: 0.65, 128: 0.59, 192: 0.55, 256: 0.53,
-                         // 512: 0.58 ms per scan -- beyond 256 the tail of the batch is too coarse)
+#define K3_CHUNK 512     // most rays a warp claims from the batch's counter at a time; halved until every resident warp gets a
+                         // chunk (8 scans of 465 750 rays: 512, 4 scans: 256).  Long runs of consecutive rays per warp are
+                         // what pays: measured per scan with 4 scans per batch, 64: 0.65, 128: 0.59, 192: 0.55, 256: 0.53,
+                         // 384: 0.55, 512: 0.58 ms; with 8 per batch, 256: 0.498, 384: 0.487, 512 / 1024: 0.486 ms; claims
+                         // that shrink towards the end of the batch (guided self-scheduling) were slower (0.54-0.60)
 #endif
 
 // One ray with at least one free cell, as computeRayKeys sets it up (r3d_math.cuh::ray_setup).
@@ -288,6 +290,7 @@ struct WalkGrid {
 #ifndef K3_MIN_CTAS
 #define K3_MIN_CTAS 3
 #endif
+
 __global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const BatchArgs a) {
     __shared__ WalkGrid sg[K3_MAX_BATCH];
     __shared__ uint32_t s_prefix[K3_MAX_BATCH + 1];
@@ -340,10 +343,11 @@ __global__ void __launch_bounds__(K3_THREADS, K3_MIN_CTAS) k_scan_walk(const Bat
         if (!exhausted && __popc(idle) >= K3_REFILL_MIN) {
             if (my_next == my_end) {
                 unsigned long long base = 0;
+                const uint32_t take_n = chunk;
                 if (lane == 0) base = atomicAdd(ray_counter, (unsigned long long)chunk);
                 base = __shfl_sync(0xffffffffu, base, 0);
                 my_next = base < total ? (uint32_t)base : total;
-                my_end = base + chunk < total ? (uint32_t)base + chunk : total;
+                my_end = base + take_n < total ? (uint32_t)base + take_n : total;
                 if (my_next == my_end) { exhausted = true; continue; }
             }
             const uint32_t i = my_next + (uint32_t)__popc(idle & ((1u << lane) - 1u));
@@ -692,7 +696,7 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     if (n_ok == 0) return R3D_OK;
     ScanPipe* p = nullptr;
     R3D_TRY(pipe_get(ctx, &p));
-    int cfg_B = 4;
+    int cfg_B = 8;
     if (const char* v = getenv("R3D_SCAN_BATCH")) { const int b = atoi(v); if (b >= 1 && b <= K3_MAX_BATCH) cfg_B = b; }
     int want_B = (uint32_t)cfg_B > n_ok ? (int)n_ok : cfg_B;
     // first guess of the cube: 2^20 cells (128 MB) or the whole (2 reach + 1)^3 cube when that is smaller; a scan that
