@@ -891,6 +891,7 @@ extern "C" void r3d_tree_destroy(r3d_tree* t) {
     if (t->pool_vmm) { vmm_release(&t->vm_values); vmm_release(&t->vm_known); }
     else { cudaFree(t->values); cudaFree(t->known); }
     cudaFree(t->skeys); cudaFree(t->smasks); cudaFree(t->delta); cudaFree(t->counters);
+    if (t->cast_gate) cudaEventDestroy(t->cast_gate);
     delete t;
 }
 
@@ -1114,12 +1115,23 @@ extern "C" int r3d_scan_deltas_compute(r3d_tree* t, const float* xyz, const uint
     DeviceSetter ds(ctx->device);
     // the deltas noted by r3d_tree_defer_deltas_owned (the round before this one, every rank's share): ONE sorted,
     // scan-ordered pass, queued now that the stream is empty (its two small read-backs cost nothing here)
-    R3D_TRY(tree_flush_deferred(t));
+    // -- and the ray casting of THIS round does not depend on it (it reads the scans, not the tree): the slots' streams wait
+    // for the point of the stream before the pass (cast_gate), so the walkers start beside the apply kernel
+    // (device-resident scans only: a host scan is staged on the context stream AFTER this point)
+    if (!t->deferred.empty() && xyz && is_device_ptr(xyz) && !discretize) {
+        if (!t->cast_gate) R3D_CUDA_OK(ctx, cudaEventCreateWithFlags(&t->cast_gate, cudaEventDisableTiming));
+        R3D_CUDA_OK(ctx, cudaEventRecord(t->cast_gate, ctx->stream));
+        static const bool gate_on = !getenv("R3D_CAST_GATE") || atoi(getenv("R3D_CAST_GATE")) != 0;
+        t->cast_gate_armed = gate_on;
+    }
+    int rc = tree_flush_deferred(t);
     uint64_t rays = 0, steps = 0;
     ScanSink sink;
     sink.mode = ScanSink::EXPORT_USER;
     sink.records = records; sink.capacity = capacity_records; sink.counts = counts;
-    R3D_TRY(scans_run(t, xyz, n_points, origins, n_scans, maxrange, discretize, &sink, &rays, &steps));
+    if (rc == R3D_OK) rc = scans_run(t, xyz, n_points, origins, n_scans, maxrange, discretize, &sink, &rays, &steps);
+    t->cast_gate_armed = false;
+    R3D_TRY(rc);
     t->last_scan_rays = rays;
     t->last_scan_steps = steps;
     R3D_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -69,6 +69,8 @@ struct r3d_tree {
     std::vector<Deferred> deferred;
     uint64_t n_pool_grow = 0, n_table_grow = 0;   // regrowth events since the tree was created (each copies / re-hashes)
     uint64_t last_scan_rays = 0, last_scan_steps = 0;
+    cudaEvent_t cast_gate = nullptr;   // r3d_scan_deltas_compute: the context stream before the deferred applies were queued
+    bool cast_gate_armed = false;
     uint64_t last_batch_records = 0;   // records of the last scan a batch insert applied (statistics; its delta is not kept)
     uint32_t* counters = nullptr;
     uint32_t h_counters[r3d::CNT_COUNT] = {0};

@@ -495,6 +495,7 @@ struct ScanPipe {
     bool snap_valid[2] = {false, false};
     cudaStream_t rc_stream[2] = {nullptr, nullptr};
     cudaEvent_t cast_done[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, start = nullptr, t0 = nullptr, t1 = nullptr;
+    cudaEvent_t start_ev = nullptr;  // what the slots' streams wait for before a call's first batches: `start`, or the caller's gate
     int walk_blocks_per_sm = 0;
     int overlap = 1;
     bool dirty = false;              // a batch was abandoned half-way: cubes must be cleared before the next use
@@ -566,12 +567,14 @@ static int pipe_get(r3d_ctx* ctx, ScanPipe** out) {
 }
 
 // (Re)shape the pipeline's buffers.  Grow-only per dimension; changing B or the cube size re-lays the cubes out.
-static int pipe_reserve(r3d_ctx* ctx, ScanPipe* p, int B, uint64_t cube_cells, uint64_t rec_cap, uint64_t ray_cap) {
+static int pipe_reserve(r3d_ctx* ctx, ScanPipe* p, int B, uint64_t cube_cells, uint64_t rec_cap, uint64_t ray_cap, bool* shaped) {
     cube_cells = (cube_cells + 3) / 4 * 4;
+    *shaped = false;
     if (rec_cap < p->rec_cap) rec_cap = p->rec_cap;
     if (ray_cap < p->ray_cap) ray_cap = p->ray_cap;
     const bool same_cubes = B == p->B && cube_cells == p->cube_cells;
     if (same_cubes && rec_cap == p->rec_cap && ray_cap == p->ray_cap && !p->dirty) return R3D_OK;
+    *shaped = true;
     R3D_TRY(pipe_sync_all(ctx, p));
     if (B != p->B) {
         R3D_TRY(pipe_realloc(ctx, &p->geom, (size_t)2 * B * 8, "scan geometry"));
@@ -639,7 +642,7 @@ static int pipe_enqueue(r3d_tree* t, ScanPipe* p, const float* d_xyz, const uint
     if (p->overlap) {
         // the slot's stream starts after the call's set-up and after the slot's previous batch has been emitted and its
         // counters read back (that batch used the same cubes, counters, ray records and record buffers)
-        R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, p->start, 0));
+        R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, p->start_ev, 0));
         R3D_CUDA_OK(ctx, cudaStreamWaitEvent(rs, p->done[slot], 0));
     }
     R3D_CUDA_OK(ctx, cudaMemsetAsync(a.geom, 0x7f, (size_t)b.count * 8 * sizeof(int), rs));
@@ -721,18 +724,30 @@ int dense_scans_run(r3d_tree* t, const float* d_xyz, const uint64_t* n_points, c
     float kernel_ms = 0.f;
     uint64_t pre_ns = 0;
     for (int attempt = 0; attempt < 24 && next < n_ok; ++attempt) {
+        bool shaped = false;
         {
             const uint64_t t_r = trace ? now_ns() : 0;
-            R3D_TRY(pipe_reserve(ctx, p, lay, cube, rec_cap, ray_cap));
+            R3D_TRY(pipe_reserve(ctx, p, lay, cube, rec_cap, ray_cap, &shaped));
             if (trace && now_ns() - t_r > 1000000ull)
                 fprintf(stderr, "[r3d pipe] shaping the pipeline took %.2f ms (%d cubes per slot of %llu cells, %llu records, %llu rays per scan)\n", (now_ns() - t_r) * 1e-6,
                         lay, (unsigned long long)cube, (unsigned long long)rec_cap, (unsigned long long)ray_cap);
         }
         if (p->overlap) {
-            R3D_CUDA_OK(ctx, cudaEventRecord(p->start, ctx->stream));   // buffers shaped, cubes clear, scans resident
-            // nothing of an earlier call is pending on the slots
-            R3D_CUDA_OK(ctx, cudaEventRecord(p->done[0], ctx->stream));
-            R3D_CUDA_OK(ctx, cudaEventRecord(p->done[1], ctx->stream));
+            // A caller that queued work the ray casting does not depend on (the multi-GPU merge's sorted apply of the round
+            // before, r3d_scan_deltas_compute) passes the point of the context stream BEFORE that work as a gate: the first
+            // batches then start beside it instead of behind it.  Only when nothing was re-shaped and both slots are idle.
+            const bool gated = t->cast_gate_armed && attempt == 0 && !shaped && cudaEventQuery(p->done[0]) == cudaSuccess &&
+                               cudaEventQuery(p->done[1]) == cudaSuccess;
+            t->cast_gate_armed = false;     // one use: whatever this call queues later (staging copies of host scans) is not before the gate
+            if (gated) {
+                p->start_ev = t->cast_gate;
+            } else {
+                R3D_CUDA_OK(ctx, cudaEventRecord(p->start, ctx->stream));   // buffers shaped, cubes clear, scans resident
+                // nothing of an earlier call is pending on the slots
+                R3D_CUDA_OK(ctx, cudaEventRecord(p->done[0], ctx->stream));
+                R3D_CUDA_OK(ctx, cudaEventRecord(p->done[1], ctx->stream));
+                p->start_ev = p->start;
+            }
         }
         p->dirty = true;        // until every queued batch has been emitted
         uint64_t t_mark = now_ns();

@@ -56,10 +56,15 @@ def main():
         got = [get_scan(first + i) for i in range(n)]
         return np.concatenate([g[0] for g in got]), [g[0].shape[0] for g in got], np.stack([g[1] for g in got])
 
-    for owner, batched in ((False, False), (True, False), (True, True), (False, True)):
+    def get_scan_batch_device(first, n):
+        # device-resident scans: the path on which a round's ray casting starts beside the sorted apply of the round before
+        pts, counts, origins = get_scan_batch(first, n)
+        return torch.from_numpy(pts).cuda(), counts, origins
+
+    for owner, batched in ((False, False), (True, False), (True, True), (False, True), (True, "device"), (False, "device")):
         tree = octomap.OcTree(res, ctx=ctx)
         sh = sharding.OctreeSharder(tree, get_scan, maxrange=maxrange, owner_partition=owner, rank=rank, world=world,
-                                    get_scan_batch=get_scan_batch if batched else None)
+                                    get_scan_batch=get_scan_batch_device if batched == "device" else (get_scan_batch if batched else None))
         scans.clear()
         sh.run(n_scans, scans_per_rank=per_rank)
         mine = sorted(scans)
@@ -70,8 +75,8 @@ def main():
             sharding.gather_bricks(tree)
             assert world == 1 or tree.numBricks() > before
         k, v = tree.voxels()
-        assert np.array_equal(k, wk) and np.array_equal(v.view(np.uint32), wv.view(np.uint32)), "rank %d owner=%s voxels differ" % (rank, owner)
-        assert tree.writeBinary() == want_bt, "rank %d owner=%s .bt differs" % (rank, owner)
+        assert np.array_equal(k, wk) and np.array_equal(v.view(np.uint32), wv.view(np.uint32)), "rank %d owner=%s batched=%s voxels differ" % (rank, owner, batched)
+        assert tree.writeBinary() == want_bt, "rank %d owner=%s batched=%s .bt differs" % (rank, owner, batched)
     dist.barrier()
     dist.destroy_process_group()
     print("rank %d/%d ok: %d scans, %d voxels, bt %d bytes" % (rank, world, n_scans, wk.shape[0], len(want_bt)))
