@@ -25,6 +25,7 @@ import importlib
 import json
 import multiprocessing as mp
 import os
+import shutil
 import sys
 import threading
 import time
@@ -623,7 +624,7 @@ def png_decode_section(cfg, n_frames=64):
         shutil.rmtree(d, ignore_errors=True)
 
 
-def script_e2e_section(cfg, n_frames=256):
+def script_e2e_section(cfg, n_frames=256, root=None):
     """Script-level end to end (what the reference IS: files in -> files out, transfer/camera_to_world.py:138-174): n PNG
     depth files + a pose file -> the drop-in script's streamed driver -> one ASCII PLY, wall clock, with the reference's
     per-point text pipeline beside it on a bounded sample.  (The per-frame side files are off: they are 45 MB per frame.)"""
@@ -636,7 +637,7 @@ def script_e2e_section(cfg, n_frames=256):
     from oracle import points_oracle as po
     transfer = importlib.import_module("3d_reconstruction_system_b200.transfer")
     formats = importlib.import_module("3d_reconstruction_system_b200.formats")
-    d = tempfile.mkdtemp(prefix="r3d_e2e_")
+    d = tempfile.mkdtemp(prefix="r3d_e2e_", dir=root)
     cwd = os.getcwd()
     try:
         os.chdir(d)
@@ -675,6 +676,7 @@ def script_e2e_section(cfg, n_frames=256):
         _ = "".join("%.4f %.4f %.4f \n" % (a, b, c) for a, b, c in w)
         ref_sec = time.perf_counter() - t0
         return {"frames": n_frames, "points": npts, "seconds": sec, "points_per_s": npts / sec, "frames_per_s": n_frames / sec, "png_bytes_in": in_bytes,
+                "files_under": os.path.dirname(d),
                 "ply_bytes_out": out_bytes, "ply_sha256": sha.hexdigest(),
                 "path": "PNG files -> native batch decode (host threads, next batch decoded while this one runs) -> pinned stack -> K1 (fp64 world points stay on the GPU) -> K6 PLY rows -> text read back -> appended to the PLY",
                 "cpu_baseline": {"value": k / ref_sec, "unit": "points/s", "cores": 1, "kind": "port",
@@ -895,6 +897,14 @@ def run_gpu_arm(args):
         png = png_decode_section(cfg)
         try:
             script = script_e2e_section(cfg)
+            # the same run with the files on tmpfs: what the box's disk (3.25 GB of PLY through the page cache) costs the figure
+            shm = "/dev/shm"
+            try:
+                if script and os.path.isdir(shm) and shutil.disk_usage(shm).free > (8 << 30):
+                    mem = script_e2e_section(cfg, root=shm)
+                    script["on_tmpfs"] = {k: mem[k] for k in ("seconds", "points_per_s", "frames_per_s", "files_under", "ply_sha256")}
+            except Exception as exc:
+                script["on_tmpfs"] = {"error": str(exc)[:300]}
         except Exception as exc:
             script = {"error": str(exc)[:300]}
     if rank == 0:
