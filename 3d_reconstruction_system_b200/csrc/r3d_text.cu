@@ -1,14 +1,17 @@
 // r3d_text.cu -- K6: the ASCII side of the path on the GPU.
 //
 // genply / genply_RGB / genply_noRGB (transfer/camera_to_world.py:112-134, transfer/pixel_to_camera.py:55-124) format
-// every point with "%.4f" in a Python loop (1.2 s per 1242x375 frame in the reference); here one thread formats one
-// row, byte for byte what Python's "%.4f" produces (r3d_math.cuh::fixed4_*: exact integer arithmetic, round half to
-// even on the exact binary value).  Rows have different lengths, so the text of a tile of 256 rows can only be placed
-// once the length of everything before it is known.  ONE pass: a tile measures its rows, publishes its byte count,
-// obtains its offset by a decoupled look-back over the tiles before it (Merrill & Garland: one 64-bit word of
-// {status, value} per tile, tiles handed out by an atomic counter so that every predecessor is already running),
-// formats each row ONCE into a shared-memory staging buffer at its in-tile offset, and copies the buffer out with
-// coalesced 16-byte stores.  HBM-bound in principle: 24 B of coordinates in, ~27 B of text out per point.
+// every point with "%.4f" in a Python loop (1.2 s per 1242x375 frame in the reference); here a thread formats three
+// consecutive rows (one for the str(float64) rows of the txt files), byte for byte what Python produces: the count of 1e-4
+// units of a coordinate is one fused multiply-add (r3d_math.cuh::fixed4_units_fma -- the exact product rounded to an
+// integer, ties to even, which is "%.4f"'s rule), the digits 32-bit multiply-shifts; values beyond 429 496 m, infinities
+// and NaN take the exact integer / bignum path (r3d_math.cuh::fixed4_*).  Rows have different lengths, so the text of a
+// tile (768 PLY rows) can only be placed once the length of everything before it is known.  ONE pass: a tile measures its
+// rows, publishes its byte count, obtains its offset by a decoupled look-back over the tiles before it (Merrill & Garland:
+// one 64-bit word of {status, value} per tile, tiles handed out by an atomic counter so that every predecessor is already
+// running), formats each row ONCE into a shared-memory staging buffer at its in-tile offset, and copies the buffer out
+// with coalesced 16-byte stores.  HBM-bound in principle (24 B of coordinates in, ~27 B of text out per point); measured
+// at 0.44 of the HBM peak, bound by issue slots and the barrier behind the look-back.
 #include <cub/block/block_scan.cuh>
 
 #include "r3d_common.cuh"
