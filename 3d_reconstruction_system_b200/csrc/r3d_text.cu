@@ -46,51 +46,7 @@ struct TextArgs {
 
 constexpr unsigned long long kTileAggregate = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1ull;
 
-// "%.4f" of a value whose 1e-4 units fit 32 bits (|x| < 429 496 -- every coordinate of a metric map): the units come from
-// one fused multiply-add (r3d_math.cuh::fixed4_units_fma; tests/hostmath compares it with the integer statement of the
-// rounding rule, fixed4_decompose), the digits from 32-bit arithmetic.
-
-// returns whether the fast path applies; q = units, neg = sign bit, len = characters of "%.4f"
-__device__ __forceinline__ bool fast4_measure(double v, uint32_t& q, uint32_t& neg, unsigned& len) {
-    const double a = fabs(v);
-    neg = (uint32_t)__double2hiint(v) >> 31;
-    q = fixed4_units_fma(a);
-    len = neg + 6u + (q >= 100000u) + (q >= 1000000u) + (q >= 10000000u) + (q >= 100000000u) + (q >= 1000000000u);
-    return a < kFixed4FastLimit;      // false for NaN
-}
-// writes the `len` characters at p and the separator after them; returns the position after the separator
-__device__ __forceinline__ char* fast4_write(uint32_t q, uint32_t neg, unsigned len, char* p, char sep) {
-    char* const e = p + len;
-    const uint32_t ip = q / 10000u;
-    const uint32_t fr = q - ip * 10000u;
-    const uint32_t hi = (fr * 5243u) >> 19, lo = fr - hi * 100u;          // fr / 100, fr % 100 (exact below 43 699)
-    const uint32_t t1 = (hi * 205u) >> 11, t0 = (lo * 205u) >> 11;        // x / 10 for x < 1 029
-    e[0] = sep;
-    e[-1] = (char)('0' + lo - t0 * 10u);
-    e[-2] = (char)('0' + t0);
-    e[-3] = (char)('0' + hi - t1 * 10u);
-    e[-4] = (char)('0' + t1);
-    e[-5] = '.';
-    if (q < 1000000u) {              // |x| < 100: one or two digits before the point
-        const uint32_t t = (ip * 205u) >> 11;
-        e[-6] = (char)('0' + ip - t * 10u);
-        if (q >= 100000u) e[-7] = (char)('0' + t);
-    } else {                         // three to six: all of them, stored where the number has them
-        const uint32_t top = ip / 10000u;                                        // (ip < 429 497: top < 43)
-        const uint32_t b = ip - top * 10000u;
-        const uint32_t bh = (b * 5243u) >> 19, bl = b - bh * 100u;
-        const uint32_t b3 = (bh * 205u) >> 11, b1 = (bl * 205u) >> 11;
-        const uint32_t c1 = (top * 205u) >> 11;
-        e[-6] = (char)('0' + bl - b1 * 10u);
-        e[-7] = (char)('0' + b1);
-        e[-8] = (char)('0' + bh - b3 * 10u);
-        if (q >= 10000000u) e[-9] = (char)('0' + b3);
-        if (q >= 100000000u) e[-10] = (char)('0' + top - c1 * 10u);
-        if (q >= 1000000000u) e[-11] = (char)('0' + c1);
-    }
-    if (neg) *p = '-';
-    return e + 1;
-}
+// (fast4_measure / fast4_write, the 32-bit "%.4f" path: r3d_math.cuh, shared with the host test harness)
 
 // kTxt: "X,Y,Z\n" rows with str(float64) fields (r3d_repr.cuh) instead of PLY rows.  A thread formats kRows consecutive rows.
 template <bool kTxt, int kRows>

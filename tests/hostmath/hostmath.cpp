@@ -103,6 +103,32 @@ long hm_fixed4_units(const double* v, long n, long* bad) {
     }
     return in_range;
 }
+// K6's PLY row as the kernel writes it: the 32-bit fast path when all three coordinates are in range, else the exact path.
+// *fast_rows counts the rows that took the fast path.
+long hm_ply_rows_fast(const double* xyz, long n, char* out, long* fast_rows) {
+    long off = 0;
+    *fast_rows = 0;
+    for (long i = 0; i < n; ++i) {
+        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        uint32_t q[3], ng[3];
+        unsigned ln[3];
+        const bool fx = fast4_measure(x, q[0], ng[0], ln[0]), fy = fast4_measure(y, q[1], ng[1], ln[1]), fz = fast4_measure(z, q[2], ng[2], ln[2]);
+        char* p = out + off;
+        if (fx && fy && fz) {
+            ++*fast_rows;
+            p = fast4_write(q[0], ng[0], ln[0], p, ' ');
+            p = fast4_write(q[1], ng[1], ln[1], p, ' ');
+            p = fast4_write(q[2], ng[2], ln[2], p, ' ');
+            *p++ = '\n';
+            off = p - out;
+        } else {
+            const int len = ply_row_len(x, y, z, false, 0, 0, 0);
+            ply_row_write(p, x, y, z, false, 0, 0, 0);
+            off += len;
+        }
+    }
+    return off;
+}
 long hm_ply_rows(const double* xyz, long n, const unsigned char* rgb, char* out) {
     long off = 0;
     for (long i = 0; i < n; ++i) {

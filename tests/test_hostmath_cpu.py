@@ -48,6 +48,8 @@ def hm():
     L.hm_txt_rows.argtypes = [C.c_void_p, C.c_long, C.c_int, C.c_void_p]
     L.hm_fixed4_units.restype = C.c_long
     L.hm_fixed4_units.argtypes = [C.c_void_p, C.c_long, C.c_void_p]
+    L.hm_ply_rows_fast.restype = C.c_long
+    L.hm_ply_rows_fast.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     L.hm_ply_rows.restype = C.c_long
     L.hm_ply_rows.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
     return L
@@ -81,6 +83,23 @@ def test_fixed4_units_by_fma_equal_the_integer_rule(hm):
     bad = C.c_long(0)
     n = hm.hm_fixed4_units(v.ctypes.data, v.size, C.byref(bad))
     assert n > 1_000_000 and bad.value == 0
+
+
+def test_fixed4_fast_path_rows_match_python(hm):
+    """The row writer of K6 (fast4_measure / fast4_write: 32-bit digits, every length from 1 to 6 digits before the point,
+    signs, values that round up into the next length) on the host, against Python's "%.4f"."""
+    rng = np.random.default_rng(78)
+    mags = np.concatenate([10.0 ** np.arange(-6, 6), 10.0 ** np.arange(0, 6) - 5e-5, 10.0 ** np.arange(0, 6) - 5.1e-5, [429495.9999, 99999.99995, 9.99995]])
+    edge = np.concatenate([mags, -mags, [0.0, -0.0, -4e-5, 4e-5]])
+    v = np.concatenate([edge, rng.uniform(-429000, 429000, 300000), rng.normal(scale=30.0, size=300000), rng.normal(scale=0.01, size=100000),
+                        rng.integers(-10**7, 10**7, size=100000) / 32.0, fixed4_cases()])
+    v = v[: (v.size // 3) * 3].reshape(-1, 3).copy()
+    out = C.create_string_buffer(v.shape[0] * 3 * 330 + 64)
+    fast = C.c_long(0)
+    n = hm.hm_ply_rows_fast(v.ctypes.data, v.shape[0], out, C.byref(fast))
+    want = "".join("%.4f %.4f %.4f \n" % (a, b, c) for a, b, c in v.tolist())
+    assert out.raw[:n].decode("ascii") == want
+    assert fast.value > 200000
 
 
 def ray(hm, res, o, e):
