@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
         const unsigned long long i0 = t * kTile + (unsigned long long)threadIdx.x * kRows;
         unsigned len[kRows];
         unsigned mine = 0;
-        // txt rows: the text itself is kept (str(float64) is too long to do twice)
-        char row[kTxt ? kTxtRowMax : 4];
+        // txt rows (one per thread): the shortest digits of the three fields are kept (Ryu is too long to run twice), the
+        // characters are generated once, straight into the staging buffer
+        ReprDec rd[3];
         // PLY rows: units, signs and lengths of the three coordinates (fast path), colour bytes
         uint32_t q[kRows][3], sg[kRows], ln[kRows], col[kRows];
         bool fast[kRows];
@@ -82,7 +83,9 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
             if (i < a.n) {
                 const double x = a.x[i * a.stride], y = a.y[i * a.stride], z = a.z[i * a.stride];
                 if (kTxt) {
-                    len[k] = (unsigned)txt_row_write(row, x, y, z, a.z_int != 0);
+                    rd[0] = repr_decompose(x); rd[1] = repr_decompose(y);
+                    rd[2] = a.z_int ? repr_decompose_integer(z) : repr_decompose(z);
+                    len[k] = (unsigned)(repr_len(rd[0]) + repr_len(rd[1]) + repr_len(rd[2])) + 3u;
                 } else {
                     uint32_t nx, ny, nz;
                     unsigned lx, ly, lz;
@@ -141,8 +144,11 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
 #pragma unroll
             for (int k = 0; k < kRows; ++k) {
                 if (len[k] == 0) continue;
-                if (kTxt) { for (unsigned c = 0; c < len[k]; ++c) p[c] = row[c]; p += len[k]; }
-                else if (fast[k]) {
+                if (kTxt) {
+                    repr_write(rd[0], p); p += repr_len(rd[0]); *p++ = ',';
+                    repr_write(rd[1], p); p += repr_len(rd[1]); *p++ = ',';
+                    repr_write(rd[2], p); p += repr_len(rd[2]); *p++ = '\n';
+                } else if (fast[k]) {
                     p = fast4_write(q[k][0], sg[k] & 1u, ln[k] & 255u, p, ' ');
                     p = fast4_write(q[k][1], (sg[k] >> 1) & 1u, (ln[k] >> 8) & 255u, p, ' ');
                     p = fast4_write(q[k][2], sg[k] >> 2, ln[k] >> 16, p, ' ');
@@ -164,8 +170,12 @@ __global__ void __launch_bounds__(K6_THREADS) k6_rows(const TextArgs a) {
 #pragma unroll 1
             for (int k = 0; k < kRows; ++k) {
                 if (len[k] == 0) continue;
-                if (kTxt) { for (unsigned c = 0; c < len[k]; ++c) p[c] = row[c]; }
-                else {
+                if (kTxt) {
+                    char* w = p;
+                    repr_write(rd[0], w); w += repr_len(rd[0]); *w++ = ',';
+                    repr_write(rd[1], w); w += repr_len(rd[1]); *w++ = ',';
+                    repr_write(rd[2], w); w += repr_len(rd[2]); *w++ = '\n';
+                } else {
                     const unsigned long long i = i0 + k;
                     ply_row_write(p, a.x[i * a.stride], a.y[i * a.stride], a.z[i * a.stride], rgb, col[k] & 255u, (col[k] >> 8) & 255u, col[k] >> 16);
                 }
